@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE: generate tests/golden/*.npz from the LIVE, UNMODIFIED reference.
+
+Run in the build container (needs /root/reference; uses oracle/ref_shim.py's gym stub):
+
+    python oracle/gen_golden.py            # writes tests/golden/
+
+The reference has no golden vectors of its own, so these files *are*
+the pin for the C oracle and, through it, for the CUDA path.  Three families:
+
+  philox_<id>.npz  RNG injection: env.np_random = PhiloxShim(seed, env_id, episode);
+                   the reference's own _gen_grid / obstacle code consumes the shared
+                   counter-based stream, so layouts + trajectories must match draw for draw.
+  tape_<id>.npz    RNG tape: the reference runs with its own MT19937 RandomState, every
+                   randint result is recorded and replayed by oracle/kernel.
+  scenes_<name>.npz  state upload: random object soups (doors in all states, keys, balls,
+                   boxes, default + terminal goals, lava, floor, carried objects, agents at
+                   the borders) built with the reference's own classes, stepped with random
+                   actions WITHOUT reset; covers the directed cases of SURVEY §8c.
+
+Every file stores the config read off the reference env itself (width, height,
+max_steps, see_through_walls, action_space.n, ...), per-step obs / direction /
+reward (float64) / done, and periodic full-grid snapshots (Grid.encode layout).
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_shim as R  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+MAX_OBST = 8
+SNAP_EVERY = 50
+
+GEN_OF_CLASS = {"EmptyEnv": 0, "DoorKeyEnv": 1, "FourRoomsEnv": 2, "DynamicObstaclesEnv": 3, "KeyCorridor": 4}
+
+
+def config_of(env):
+    """Read the static config off a live reference env."""
+    env = env.unwrapped
+    gen = None
+    for klass in type(env).__mro__:
+        if klass.__name__ in GEN_OF_CLASS:
+            gen = GEN_OF_CLASS[klass.__name__]
+            break
+    assert gen is not None, type(env)
+    return dict(
+        gen=gen, width=env.width, height=env.height, max_steps=env.max_steps,
+        see_through=int(bool(env.see_through_walls)), n_actions=env.action_space.n,
+        n_obstacles=getattr(env, "n_obstacles", 0) if gen == 3 else 0,
+        room_size=getattr(env, "room_size", 0), num_rows=getattr(env, "num_rows", 0),
+        random_start=int(gen in (0, 3) and getattr(env, "agent_start_pos", 1) is None),
+        lava_v1=int("v1" in type(env).__name__),     # minigrid.py:1263 -- e.g. "DoorKeyEnv16x16" contains "v1"
+    )
+
+
+def pad_obst(o):
+    out = np.zeros((MAX_OBST, 2), np.int16)
+    out[:len(o)] = o
+    return out
+
+
+def run_trace(env_id, seed, env_index, T, act_seed, mode):
+    """One env, T steps, auto-reset by the caller exactly like run_tests.py:37-46."""
+    env = R.make(env_id)
+    cfg = config_of(env)
+    if mode == "philox":
+        shim = R.PhiloxShim(seed, env_index, 0)
+    else:
+        shim = R.TapeRecorder(np.random.RandomState((seed * 7919 + env_index) % (2 ** 32)))
+    env.np_random = shim
+    episode = 0
+    obs = env.reset()
+    episode += 1
+    rs = np.random.RandomState(act_seed)
+    actions = rs.randint(0, cfg["n_actions"], size=T).astype(np.uint8)
+    out = dict(obs=np.zeros((T, 7, 7, 3), np.uint8), dir=np.zeros(T, np.uint8),
+               reward=np.zeros(T, np.float64), done=np.zeros(T, np.uint8))
+    snaps, snap_t, missions = [], [], [obs["mission"]]
+    first = dict(obs0=obs["image"].copy(), dir0=np.uint8(obs["direction"]))
+    snap0 = R.snapshot(env)
+    for t in range(T):
+        obs, r, d, _ = env.step(int(actions[t]))
+        if d:
+            if mode == "philox":
+                shim.new_episode(episode)
+            obs = env.reset()
+            episode += 1
+            missions.append(obs["mission"])
+        out["obs"][t] = obs["image"]
+        out["dir"][t] = obs["direction"]
+        out["reward"][t] = float(r)
+        out["done"][t] = d
+        if (t + 1) % SNAP_EVERY == 0 or t == T - 1:
+            s = R.snapshot(env)
+            snaps.append(s)
+            snap_t.append(t)
+    res = dict(cfg=cfg, actions=actions, **out, **first,
+               snap_t=np.array(snap_t, np.int32),
+               snap_grid=np.stack([s["grid"] for s in snaps]),
+               snap_agent=np.stack([s["agent"] for s in snaps]),
+               snap_carrying=np.stack([s["carrying"] for s in snaps]),
+               snap_obst=np.stack([pad_obst(s["obstacles"]) for s in snaps]),
+               snap_target=np.stack([s["target"] for s in snaps]),
+               grid0=snap0["grid"], agent0=snap0["agent"], obst0=pad_obst(snap0["obstacles"]),
+               target0=snap0["target"], n_episodes=episode, mission0=missions[0])
+    if mode == "tape":
+        res["tape"] = np.array(shim.tape, np.int32)
+    return res
+
+
+def save_traces(name, env_id, traces, seed, env_indices, act_seeds):
+    cfg = traces[0]["cfg"]
+    d = dict(env_id=env_id, seed=np.uint64(seed), env_indices=np.array(env_indices, np.int64),
+             act_seeds=np.array(act_seeds, np.int64),
+             cfg_keys=np.array(list(cfg.keys())), cfg_vals=np.array(list(cfg.values()), np.int32),
+             missions0=np.array([t["mission0"] for t in traces]),
+             n_episodes=np.array([t["n_episodes"] for t in traces], np.int32))
+    for k in ("actions", "obs", "dir", "reward", "done", "obs0", "dir0", "snap_t", "snap_grid", "snap_agent",
+              "snap_carrying", "snap_obst", "snap_target", "grid0", "agent0", "obst0", "target0"):
+        d[k] = np.stack([t[k] for t in traces])
+    if "tape" in traces[0]:
+        d["tape"] = np.concatenate([t["tape"] for t in traces])
+        d["tape_offsets"] = np.concatenate([[0], np.cumsum([len(t["tape"]) for t in traces])]).astype(np.int64)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    return path
+
+
+# ---------------------------------------------------------------------------
+# scene fuzz: object soups built from the reference's own classes
+# ---------------------------------------------------------------------------
+def build_scene(env, rs, density):
+    mg = sys.modules["gym_minigrid.minigrid"]
+    env = env.unwrapped
+    W, H = env.width, env.height
+    env.grid = mg.Grid(W, H)
+    env.grid.wall_rect(0, 0, W, H)
+    colors = list(mg.COLOR_TO_IDX.keys())
+
+    def rand_obj():
+        k = rs.randint(0, 12)
+        c = colors[rs.randint(0, len(colors))]
+        if k == 0:
+            return mg.Wall(c)
+        if k == 1:
+            return mg.Wall()
+        if k == 2:
+            return mg.Floor(c)
+        if k in (3, 4, 5):
+            st = rs.randint(0, 3)
+            return mg.Door(c, is_open=(st == 0), is_locked=(st == 2))
+        if k == 6:
+            return mg.Key(c)
+        if k == 7:
+            return mg.Ball(c)
+        if k == 8:
+            return mg.Box(c)
+        if k == 9:
+            return mg.Goal()
+        if k == 10:
+            return mg.Goal(toggletimes=0)       # the only kind of goal that terminates (minigrid.py:157-160,1259)
+        return mg.Lava()
+
+    for x in range(1, W - 1):
+        for y in range(1, H - 1):
+            if rs.rand() < density:
+                env.grid.set(x, y, rand_obj())
+    # agent on an overlappable cell, biased towards the borders so every view clip is hit
+    while True:
+        if rs.rand() < 0.5:
+            ax = [1, W - 2][rs.randint(0, 2)] if rs.rand() < 0.5 else rs.randint(1, W - 1)
+            ay = [1, H - 2][rs.randint(0, 2)] if rs.rand() < 0.5 else rs.randint(1, H - 1)
+        else:
+            ax, ay = rs.randint(1, W - 1), rs.randint(1, H - 1)
+        c = env.grid.get(ax, ay)
+        if c is None or c.can_overlap():
+            break
+        env.grid.set(ax, ay, None)
+        break
+    env.agent_pos = np.array([ax, ay])
+    env.agent_dir = int(rs.randint(0, 4))
+    env.carrying = None
+    k = rs.randint(0, 5)
+    if k == 1:
+        env.carrying = mg.Key(colors[rs.randint(0, len(colors))])
+    elif k == 2:
+        env.carrying = mg.Ball(colors[rs.randint(0, len(colors))])
+    elif k == 3:
+        env.carrying = mg.Box(colors[rs.randint(0, len(colors))])
+    env.step_count = int(rs.randint(0, env.max_steps))
+
+
+def run_scene(env_id, scene_seed, T, density):
+    env = R.make(env_id)
+    rs = np.random.RandomState(scene_seed)
+    build_scene(env, rs, density)
+    cfg = config_of(env)
+    s0 = R.snapshot(env)
+    actions = rs.randint(0, 7, size=T).astype(np.uint8)
+    obs0 = env.gen_obs()
+    out = dict(obs=np.zeros((T, 7, 7, 3), np.uint8), dir=np.zeros(T, np.uint8),
+               reward=np.zeros(T, np.float64), done=np.zeros(T, np.uint8))
+    for t in range(T):
+        obs, r, d, _ = env.step(int(actions[t]))       # never reset: stepping past done is legal in the reference
+        out["obs"][t] = obs["image"]
+        out["dir"][t] = obs["direction"]
+        out["reward"][t] = float(r)
+        out["done"][t] = d
+    s1 = R.snapshot(env)
+    return dict(cfg=cfg, actions=actions, **out, obs0=obs0["image"], dir0=np.uint8(obs0["direction"]),
+                grid0=s0["grid"], aux0=s0["aux"], agent0=s0["agent"], carrying0=s0["carrying"],
+                grid1=s1["grid"], aux1=s1["aux"], agent1=s1["agent"], carrying1=s1["carrying"])
+
+
+def save_scenes(name, env_id, scenes):
+    cfg = scenes[0]["cfg"]
+    d = dict(env_id=env_id, cfg_keys=np.array(list(cfg.keys())), cfg_vals=np.array(list(cfg.values()), np.int32))
+    for k in scenes[0]:
+        if k != "cfg":
+            d[k] = np.stack([s[k] for s in scenes])
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    return path
+
+
+HEADLINE = [
+    # id, (n_long, T_long), (n_short, T_short)
+    ("MiniGrid-Empty-8x8-v0", (2, 800), (6, 300)),
+    ("MiniGrid-DoorKey-16x16-v0", (1, 7800), (7, 400)),
+    ("MiniGrid-FourRooms-v0", (2, 1600), (6, 300)),
+    ("MiniGrid-Dynamic-Obstacles-16x16-v0", (2, 1500), (6, 400)),
+    ("MiniGrid-KeyCorridorS6R3-v0", (1, 3400), (11, 300)),
+]
+VARIANTS = [
+    "MiniGrid-Empty-5x5-v0", "MiniGrid-Empty-6x6-v0", "MiniGrid-Empty-16x16-v0",
+    "MiniGrid-Empty-Random-5x5-v0", "MiniGrid-Empty-Random-6x6-v0", "MiniGrid-Empty-Random-8x8-v0",
+    "MiniGrid-DoorKey-5x5-v0", "MiniGrid-DoorKey-6x6-v0", "MiniGrid-DoorKey-8x8-v0",
+    "MiniGrid-Dynamic-Obstacles-5x5-v0", "MiniGrid-Dynamic-Obstacles-Random-5x5-v0",
+    "MiniGrid-Dynamic-Obstacles-6x6-v0", "MiniGrid-Dynamic-Obstacles-Random-6x6-v0",
+    "MiniGrid-Dynamic-Obstacles-8x8-v0",
+    "MiniGrid-KeyCorridorS3R1-v0", "MiniGrid-KeyCorridorS3R2-v0", "MiniGrid-KeyCorridorS3R3-v0",
+    "MiniGrid-KeyCorridorS4R3-v0", "MiniGrid-KeyCorridorS5R3-v0",
+]
+
+
+def short(env_id):
+    return env_id.replace("MiniGrid-", "").replace("-v0", "").replace("-", "_").lower()
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    R.load_reference()
+    t0 = time.time()
+    seed = 20261018
+    for env_id, (nl, Tl), (ns, Ts) in HEADLINE:
+        for mode in ("philox", "tape"):
+            # equal-length traces are stacked per file: long and short go to separate files
+            for tag, n, T, base in (("long", nl, Tl, 0), ("short", ns, Ts, 100)):
+                if mode == "tape" and tag == "short":
+                    n = min(n, 3)
+                idx = [base + 37 * k + (1 << 33) * (k == 1) for k in range(n)]   # one id beyond 32 bits
+                acts = [1000 + base + k for k in range(n)]
+                traces = [run_trace(env_id, seed, i, T, a, mode) for i, a in zip(idx, acts)]
+                p = save_traces("%s_%s_%s" % (mode, short(env_id), tag), env_id, traces, seed, idx, acts)
+                print("%-60s %7.1f KB  episodes=%s  [%.0fs]" % (os.path.basename(p), os.path.getsize(p) / 1024,
+                      [t["n_episodes"] for t in traces], time.time() - t0), flush=True)
+    for env_id in VARIANTS:
+        idx = [5, 77, 4242]
+        acts = [2000, 2001, 2002]
+        traces = [run_trace(env_id, seed + 1, i, 300, a, "philox") for i, a in zip(idx, acts)]
+        p = save_traces("philox_%s" % short(env_id), env_id, traces, seed + 1, idx, acts)
+        print("%-60s %7.1f KB  episodes=%s  [%.0fs]" % (os.path.basename(p), os.path.getsize(p) / 1024,
+              [t["n_episodes"] for t in traces], time.time() - t0), flush=True)
+    # scenes: see-through (Empty classes) and occluded (DoorKey classes, FourRooms 19x19)
+    for name, env_id, n, T, dens in (
+        ("scenes_seethrough_8x8", "MiniGrid-Empty-8x8-v0", 48, 120, 0.30),
+        ("scenes_seethrough_16x16", "MiniGrid-Empty-16x16-v0", 16, 200, 0.25),
+        ("scenes_occluded_8x8", "MiniGrid-DoorKey-8x8-v0", 48, 120, 0.30),
+        ("scenes_occluded_16x16", "MiniGrid-DoorKey-16x16-v0", 24, 200, 0.25),
+        ("scenes_occluded_19x19", "MiniGrid-FourRooms-v0", 24, 200, 0.20),
+        ("scenes_occluded_5x5", "MiniGrid-DoorKey-5x5-v0", 32, 80, 0.35),
+    ):
+        scenes = [run_scene(env_id, 9000 + k, T, dens) for k in range(n)]
+        p = save_scenes(name, env_id, scenes)
+        dn = sum(int(s["done"].sum()) for s in scenes)
+        rw = sum(int((s["reward"] != 0).sum()) for s in scenes)
+        print("%-60s %7.1f KB  done-steps=%d reward-steps=%d [%.0fs]" % (os.path.basename(p), os.path.getsize(p) / 1024,
+              dn, rw, time.time() - t0), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,88 @@
+/* TEST INFRASTRUCTURE ONLY.  CPU restatement (plain C) of the reference hot path
+ * of rohitrango/gym-minigrid: MiniGridEnv.step / gen_obs / gen_obs_grid /
+ * Grid.slice / rotate_left / process_vis / encode and reset/_gen_grid of the
+ * five BASELINE configs (+ their registered size variants).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs may load this library.  The product path
+ * (gym_minigrid_b200 -> libmgb200.so) never does.
+ *
+ * Parity pin: tests/golden/ holds traces produced by the *live* reference
+ * (oracle/gen_golden.py, run in the build container where /root/reference is
+ * mounted); tests/test_oracle_golden.py replays them through this library and
+ * requires bit-exact obs / direction / reward(fp64 bits) / done / full grid.
+ */
+#ifndef MINIGRID_ORACLE_H
+#define MINIGRID_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* generator kinds (one per reference env file on the path) */
+enum {
+    ORC_GEN_EMPTY = 0,       /* envs/empty.py:30-57          */
+    ORC_GEN_DOORKEY = 1,     /* envs/doorkey.py:15-44        */
+    ORC_GEN_FOURROOMS = 2,   /* envs/fourrooms.py:19-69      */
+    ORC_GEN_DYNOBS = 3,      /* envs/dynamicobstacles.py:35-58 */
+    ORC_GEN_KEYCORRIDOR = 4  /* roomgrid.py:118-169 + envs/keycorridor.py:26-49 */
+};
+
+typedef struct {
+    int32_t gen;            /* ORC_GEN_* */
+    int32_t width, height;
+    int32_t max_steps;
+    int32_t see_through;    /* see_through_walls */
+    int32_t n_actions;      /* action_space.n (7; 3 for DynObs) */
+    int32_t n_obstacles;    /* DynObs */
+    int32_t room_size;      /* KeyCorridor / RoomGrid */
+    int32_t num_rows;       /* KeyCorridor / RoomGrid (num_cols == 3) */
+    int32_t random_start;   /* Empty-Random / DynObs-Random: agent_start_pos=None */
+    int32_t lava_v1;        /* 'v1' in type(env).__name__ (minigrid.py:1263-1266): true for e.g. DoorKeyEn*v1*6x16 */
+} orc_config;
+
+#define ORC_OBS_BYTES 147
+#define ORC_MAX_OBST 8
+
+typedef struct orc_vec orc_vec;
+
+/* n independent envs with global ids env0 .. env0+n-1; Philox key = seed */
+orc_vec *orc_vec_create(const orc_config *cfg, uint64_t seed, int64_t env0, int32_t n);
+void orc_vec_destroy(orc_vec *v);
+void orc_set_threads(int nthreads);
+
+/* RNG tape (parity mode 2): draws[offsets[i] .. offsets[i+1]) are the raw randint
+ * results env i will consume, in order.  NULL disables. */
+int orc_vec_set_tape(orc_vec *v, const int32_t *draws, const int64_t *offsets);
+
+/* reset envs where mask[i]!=0 (all if mask NULL): obs [n][147], dir [n] */
+int orc_vec_reset(orc_vec *v, const uint8_t *mask, uint8_t *obs, uint8_t *dir);
+
+/* one step; if autoreset, a done env is reset and obs/dir are those of the new episode */
+int orc_vec_step(orc_vec *v, const uint8_t *actions, int autoreset,
+                 uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir);
+
+/* T steps; actions [T][n]; outputs [T][n]...; any output may be NULL */
+int orc_vec_rollout(orc_vec *v, int32_t T, const uint8_t *actions, int autoreset,
+                    uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir);
+
+/* state exchange, layout = Grid.encode (minigrid.py:571-594): grid [n][W][H][3];
+ * aux [n][W][H] bit0 = Goal.overlap; agent [n][4] = x,y,dir,step_count;
+ * carrying [n][3] ((0,0,0)=none); obstacles [n][8][2]; target [n][2]=(type,color);
+ * rng [n][2] = (episode, ndraws) */
+int orc_vec_get_state(orc_vec *v, uint8_t *grid, uint8_t *aux, int32_t *agent,
+                      uint8_t *carrying, int16_t *obstacles, uint8_t *target, uint32_t *rng);
+int orc_vec_set_state(orc_vec *v, const uint8_t *grid, const uint8_t *aux, const int32_t *agent,
+                      const uint8_t *carrying, const int16_t *obstacles, const uint8_t *target,
+                      const uint32_t *rng);
+
+/* Philox4x32-10 known-answer hook */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+const char *orc_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
