@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec (observations materialised in HBM) of the batched MiniGrid hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--env-id ID] [--num-envs N_PER_GPU] [--rollout-T T]
+
+One bench "step" = one pass of the hot path over one batch: ONE persistent mgb_rollout launch that
+advances every env of the batch by T env-steps and writes all T*N observations (+reward/done/dir)
+to HBM.  value = (envs over all ranks) * T * K / max-over-ranks device time.
+
+Workload (BASELINE.json configs[0], fits one GPU): MiniGrid-Empty-8x8-v0, uniform random actions
+pre-generated on the device (torch.randint, seed 1234), 2^20 envs per GPU, T = 32, auto-reset on.
+Outputs per launch (~5 GB) are far larger than L2 (126 MB), so no L2 flush is needed between steps.
+
+Extra keys: roofline (HBM bound, 158 algorithmic B / env-step), cpu_baseline (C oracle port on the
+host cores, bounded sample), e2e (mgb_step_host: pinned host actions in, host obs/reward/done/dir
+out, copies inside the timed region), clocks (nvidia-smi sampled during the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_STEP = 158        # 147 obs + 8 reward + 1 done + 1 direction (writes) + 1 action (read); SURVEY §8d
+METRIC = "env-steps/sec (with obs)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--env-id", default="MiniGrid-Empty-8x8-v0")
+    ap.add_argument("--num-envs", type=int, default=1 << 20, help="envs per GPU")
+    ap.add_argument("--rollout-T", type=int, default=32, help="env-steps per launch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-envs", type=int, default=1 << 14)
+    ap.add_argument("--cpu-sample-T", type=int, default=64)
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cfg(env_id):
+    import gym_minigrid_b200 as mgb
+    return {k: v for k, v in mgb.spec(env_id)["config"].items() if k not in ("mission", "reward_range")}
+
+
+def cpu_leg(env_id, n_envs, T, reps, threads=0):
+    """Times the CPU oracle (the C port of the reference algorithm) on the host cores."""
+    import numpy as np
+    from oracle.oracle import OracleVec
+    cfg = oracle_cfg(env_id)
+    cores = threads or os.cpu_count() or 1
+    orc = OracleVec(cfg, n_envs, seed=0, threads=cores)
+    orc.reset()
+    rs = np.random.RandomState(1234)
+    acts = rs.randint(0, cfg["n_actions"], size=(T, n_envs)).astype(np.uint8)
+    orc.rollout(acts, autoreset=True)                      # warm-up
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.rollout(acts, autoreset=True)                  # obs [T,n,147] materialised in host memory
+        times.append(time.perf_counter() - t0)
+    return n_envs * T / min(times), times, cores
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference is pure Python and does not travel to the GPU box; per the
+    task contract the arm times the CPU oracle port with all host threads on the same config."""
+    if rank != 0:
+        return
+    n, T = args.cpu_sample_envs, args.cpu_sample_T
+    for _ in range(args.warmup):
+        cpu_leg(args.env_id, n, T, 1)
+    t0 = time.perf_counter()
+    best = 0.0
+    per = []
+    cores = os.cpu_count() or 1
+    for _ in range(args.steps):
+        v, ts, cores = cpu_leg(args.env_id, n, T, 1)
+        per.append(ts[0])
+        best = max(best, v)
+    value = n * T * len(per) / sum(per)
+    sample = "%d envs x %d env-steps per bench step, C oracle port, %d threads" % (n, T, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(per) / len(per), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.env_id + " random-action rollout, auto-reset", "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gym_minigrid_b200 as mgb
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, T, K, W = args.num_envs, args.rollout_T, args.steps, max(args.warmup, 3)
+    cfg = mgb.spec(args.env_id)["config"]
+    env = mgb.make(args.env_id, num_envs=N, device=dev, seed=0, env_id_base=rank * N)   # shard by global env id
+    env.reset()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n_pool = 4
+    acts = [torch.randint(0, cfg["n_actions"], (T, N), dtype=torch.uint8, device=dev, generator=g) for _ in range(n_pool)]
+    out = (torch.empty((T, N, 7, 7, 3), dtype=torch.uint8, device=dev),
+           torch.empty((T, N), dtype=torch.float64, device=dev),
+           torch.empty((T, N), dtype=torch.uint8, device=dev),
+           torch.empty((T, N), dtype=torch.uint8, device=dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        env.rollout(acts[i % n_pool], out=out)
+    barrier()
+    launches0 = env.kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e_start.record()
+    for i in range(K):
+        evs[i][0].record()
+        env.rollout(acts[i % n_pool], out=out)
+        evs[i][1].record()
+    e_end.record()
+    barrier()
+    total_ms = e_start.elapsed_time(e_end)
+    launches = env.kernel_launches - launches0
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    clocks = sampler.stop() if rank == 0 else None
+    env.check_errors()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * N * T * K / (total_ms_max * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel: algorithmic bytes / CUDA-event launch duration ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    avg_kern_s = statistics.mean(kern_ms) * 1e-3
+    achieved = ALGO_BYTES_PER_STEP * N * T / avg_kern_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")        # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if tj.get("env_id") == args.env_id and tj.get("num_envs") == N and tj.get("rollout_T") == T:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "mgb::k_rollout", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_STEP * N * T,
+                "avg_launch_ms": statistics.mean(kern_ms), "peak_source": peak_src}
+
+    # ---- e2e: host buffers through mgb_step_host (H2D actions + kernel + D2H results per step) ----
+    e2e = None
+    if not args.no_e2e:
+        Ke = max(3, min(K, 10))
+        hacts = [torch.randint(0, cfg["n_actions"], (N,), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        for i in range(2):
+            env.step_host(hacts[i % 2])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            env.step_host(hacts[i % 2])            # synchronous: outputs are in pinned host memory on return
+        torch.cuda.synchronize(dev)
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * N * Ke / float(te.item()), "unit": "env-steps/s", "h2d_bytes_per_step": N,
+               "d2h_bytes_per_step": N * (147 + 8 + 1 + 1), "steps": Ke, "api": "VecMiniGridEnv.step_host -> mgb_step_host"}
+
+    # ---- secondary: single-step launches (state round-trips HBM every step) ----
+    Ks = 16
+    a1 = acts[0]
+    o1 = (out[0][0], out[1][0], out[2][0], out[3][0])
+    for t_ in range(3):
+        env.step(a1[t_], out=o1)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for t_ in range(Ks):
+        env.step(a1[t_ % T], out=o1)
+    s1.record()
+    barrier()
+    step_mode = N * Ks / (s0.elapsed_time(s1) * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, times, cores = cpu_leg(args.env_id, args.cpu_sample_envs, args.cpu_sample_T, 3)
+        cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+               "sample": "%d envs x %d env-steps, best of 3, C oracle port (oracle/minigrid_oracle.c), obs materialised"
+                         % (args.cpu_sample_envs, args.cpu_sample_T)}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.env_id + " random-action rollout, auto-reset on, obs+reward+done+dir written every env-step",
+                       "envs_per_gpu": N, "env_steps_per_launch": T, "actions": "torch.randint on device, seed 1234",
+                       "l2": "outputs per launch (%.1f GB) exceed L2; no flush needed" % (N * T * 157 / 1e9),
+                       "parallelism": "env shards by global env id, no collective"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "step_mode_env_steps_per_s_per_gpu": step_mode,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

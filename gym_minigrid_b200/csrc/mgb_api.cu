@@ -1,0 +1,340 @@
+// mgb200 C-ABI (include/mgb200.h): handle management, launch plumbing, host<->device pipeline.
+// No torch types, no CPU fallback: every compute entry point launches sm_100a kernels.
+#include "../../include/mgb200.h"
+#include "mgb_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using namespace mgb;
+
+static thread_local char g_err[512] = "";
+static int fail(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return -1;
+}
+#define CUDA_OK(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int HOST_PIPE_STREAMS = 3;
+
+struct mgb_handle {
+    mgb_config cfg;
+    DevCfg dc;
+    int device = 0;
+    int64_t n_envs = 0;
+    int32_t n_groups = 0;
+    uint64_t seed = 0;
+    int64_t env_id_base = 0;
+    int autoreset = 1;
+    uint32_t *state = nullptr;
+    uint32_t *tmpl = nullptr;
+    uint32_t *err = nullptr;
+    const int32_t *tape = nullptr;
+    const int64_t *tape_off = nullptr;
+    int sm_count = 0;
+    int blocks_per_sm = 0;
+    size_t smem_bytes = 0;
+    int64_t launches = 0;
+    // host pipeline (mgb_step_host)
+    cudaStream_t pipe[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
+    uint8_t *d_actions = nullptr, *d_obs = nullptr, *d_done = nullptr, *d_dir = nullptr;
+    double *d_reward = nullptr;
+    // kernel timing
+    int timing = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+typedef void (*rollout_fn)(const RolloutParams);
+static rollout_fn pick_kernel(const mgb_config &c) {
+    switch (c.gen) {
+    case MGB_GEN_EMPTY: return c.see_through ? k_rollout<GEN_EMPTY, true> : k_rollout<GEN_EMPTY, false>;
+    case MGB_GEN_DOORKEY: return c.see_through ? nullptr : k_rollout<GEN_DOORKEY, false>;
+    case MGB_GEN_FOURROOMS: return c.see_through ? nullptr : k_rollout<GEN_FOURROOMS, false>;
+    case MGB_GEN_DYNOBS: return c.see_through ? k_rollout<GEN_DYNOBS, true> : nullptr;
+    case MGB_GEN_KEYCORRIDOR: return c.see_through ? nullptr : k_rollout<GEN_KEYCORRIDOR, false>;
+    }
+    return nullptr;
+}
+
+// static part of each layout (walls + fixed goal) as packed cell codes, x-major like Grid.encode
+static std::vector<uint32_t> build_template(const mgb_config &c, int GW) {
+    const int W = c.width, H = c.height;
+    std::vector<uint8_t> g((size_t)GW * 4, (uint8_t)CODE_EMPTY);
+    auto set = [&](int x, int y, int code) { g[(size_t)x * H + y] = (uint8_t)code; };
+    auto wall_rect = [&](int x0, int y0, int w, int h) {   // Grid.wall_rect minigrid.py:433-437
+        for (int i = 0; i < w; ++i) { set(x0 + i, y0, CODE_WALL); set(x0 + i, y0 + h - 1, CODE_WALL); }
+        for (int j = 0; j < h; ++j) { set(x0, y0 + j, CODE_WALL); set(x0 + w - 1, y0 + j, CODE_WALL); }
+    };
+    switch (c.gen) {
+    case MGB_GEN_EMPTY: case MGB_GEN_DOORKEY: case MGB_GEN_DYNOBS:
+        wall_rect(0, 0, W, H);
+        set(W - 2, H - 2, CODE_GOAL);                      // empty.py:48, doorkey.py:23, dynamicobstacles.py:43
+        break;
+    case MGB_GEN_FOURROOMS: {                              // fourrooms.py:24-53 (walls only; gaps are drawn on device)
+        wall_rect(0, 0, W, H);
+        const int rw = W / 2, rh = H / 2;
+        for (int y = 0; y < 2 * rh; ++y) set(rw, y, CODE_WALL);
+        for (int x = 0; x < 2 * rw; ++x) set(x, rh, CODE_WALL);
+        break;
+    }
+    case MGB_GEN_KEYCORRIDOR:                              // roomgrid.py:125-137
+        for (int j = 0; j < c.num_rows; ++j)
+            for (int i = 0; i < 3; ++i) wall_rect(i * (c.room_size - 1), j * (c.room_size - 1), c.room_size, c.room_size);
+        break;
+    }
+    std::vector<uint32_t> w(GW);
+    memcpy(w.data(), g.data(), (size_t)GW * 4);
+    return w;
+}
+
+extern "C" {
+
+const char *mgb_version(void) { return "mgb200 0.1 (sm_100a)"; }
+const char *mgb_last_error(void) { return g_err; }
+
+int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t seed, int64_t env_id_base, mgb_handle **out) {
+    if (!cfg || !out) return fail("mgb_create: null argument");
+    *out = nullptr;
+    const mgb_config &c = *cfg;
+    if (c.width < 3 || c.height < 3 || c.width > 64 || c.height > 64) return fail("mgb_create: grid size %dx%d unsupported (3..64)", c.width, c.height);
+    if (c.max_steps < 1 || c.max_steps > 65535) return fail("mgb_create: max_steps %d out of range", c.max_steps);
+    if (num_envs < 1 || num_envs > ((int64_t)1 << 31) - 64) return fail("mgb_create: num_envs %lld out of range", (long long)num_envs);
+    if (c.n_obstacles < 0 || c.n_obstacles > MGB_MAX_OBSTACLES) return fail("mgb_create: n_obstacles %d out of range", c.n_obstacles);
+    if (c.gen == MGB_GEN_KEYCORRIDOR) {
+        if (c.num_rows < 1 || c.num_rows > 3 || c.room_size < 3) return fail("mgb_create: bad RoomGrid shape");
+        if (c.width != (c.room_size - 1) * 3 + 1 || c.height != (c.room_size - 1) * c.num_rows + 1) return fail("mgb_create: RoomGrid size mismatch (roomgrid.py:85-86)");
+    }
+    if (c.gen == MGB_GEN_DYNOBS && c.n_actions != 3) return fail("mgb_create: Dynamic-Obstacles has 3 actions");
+    if (c.gen != MGB_GEN_DYNOBS && c.n_actions != 7) return fail("mgb_create: n_actions must be 7");
+    rollout_fn fn = pick_kernel(c);
+    if (!fn) return fail("mgb_create: unsupported (gen=%d, see_through=%d) combination", c.gen, c.see_through);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("mgb_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail("mgb_create: device %d out of range (%d devices)", device, ndev);
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("mgb_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+    mgb_handle *h = new (std::nothrow) mgb_handle();
+    if (!h) return fail("mgb_create: out of host memory");
+    h->cfg = c; h->device = device; h->n_envs = num_envs; h->seed = seed; h->env_id_base = env_id_base;
+    h->n_groups = (int32_t)((num_envs + 31) / 32);
+    DevCfg &d = h->dc;
+    d.gen = c.gen; d.W = c.width; d.H = c.height; d.max_steps = c.max_steps; d.see_through = c.see_through;
+    d.n_actions = c.n_actions; d.n_obst = c.n_obstacles; d.room_size = c.room_size; d.num_rows = c.num_rows;
+    d.random_start = c.random_start; d.lava_v1 = c.lava_v1;
+    d.GW = (c.width * c.height + 3) / 4;
+    d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0);
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_bytes = 1024 + (size_t)WARPS_PER_BLOCK * (STAGE_BYTES + (size_t)d.S * 32 * 4);
+
+    auto cleanup = [&](int rc) { mgb_destroy(h); return rc; };
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess)
+        return cleanup(fail("mgb_create: %zu bytes of shared memory per block not available", h->smem_bytes));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, fn, THREADS, h->smem_bytes) != cudaSuccess || h->blocks_per_sm < 1)
+        return cleanup(fail("mgb_create: kernel does not fit on an SM"));
+    const size_t state_bytes = (size_t)h->n_groups * d.S * 32 * 4;
+    if (cudaMalloc(&h->state, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: cudaMalloc(%zu) for env state failed", state_bytes));
+    if (cudaMemset(h->state, 0, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: memset failed"));
+    std::vector<uint32_t> t = build_template(c, d.GW);
+    if (cudaMalloc(&h->tmpl, t.size() * 4) != cudaSuccess || cudaMemcpy(h->tmpl, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+        return cleanup(fail("mgb_create: template upload failed"));
+    if (cudaMalloc(&h->err, 4) != cudaSuccess || cudaMemset(h->err, 0, 4) != cudaSuccess) return cleanup(fail("mgb_create: err flag alloc failed"));
+    *out = h;
+    return 0;
+}
+
+int mgb_destroy(mgb_handle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaFree(h->state); cudaFree(h->tmpl); cudaFree(h->err);
+    cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_dir); cudaFree(h->d_reward);
+    for (auto &s : h->pipe) if (s) cudaStreamDestroy(s);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+    return 0;
+}
+
+int64_t mgb_num_envs(const mgb_handle *h) { return h ? h->n_envs : -1; }
+int64_t mgb_kernel_launches(const mgb_handle *h) { return h ? h->launches : -1; }
+
+int mgb_set_autoreset(mgb_handle *h, int on) {
+    if (!h) return fail("null handle");
+    h->autoreset = on ? 1 : 0;
+    return 0;
+}
+
+int mgb_set_rng_tape(mgb_handle *h, const int32_t *draws, const int64_t *offsets) {
+    if (!h) return fail("null handle");
+    if ((draws == nullptr) != (offsets == nullptr)) return fail("mgb_set_rng_tape: draws and offsets must both be set or both be NULL");
+    h->tape = draws; h->tape_off = offsets;
+    return 0;
+}
+
+int mgb_set_kernel_timing(mgb_handle *h, int on) {
+    if (!h) return fail("null handle");
+    CUDA_OK(cudaSetDevice(h->device));
+    h->timing = on ? 1 : 0;
+    if (on && !h->ev0) { CUDA_OK(cudaEventCreate(&h->ev0)); CUDA_OK(cudaEventCreate(&h->ev1)); }
+    h->ev_valid = false;
+    return 0;
+}
+
+double mgb_last_kernel_ms(mgb_handle *h) {
+    if (!h || !h->timing || !h->ev_valid) return -1.0;
+    float ms = 0.f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+// launch over groups [g0, g0+ng)
+static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset, const uint8_t *mask,
+                  const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir,
+                  int64_t stride, cudaStream_t stream, bool timed) {
+    if (ng <= 0) return 0;
+    RolloutParams p;
+    p.cfg = h->dc; p.state = h->state; p.tmpl = h->tmpl; p.n_envs = h->n_envs;
+    p.group0 = g0; p.n_groups = ng; p.T = T; p.do_reset = do_reset; p.autoreset = h->autoreset;
+    p.reset_mask = mask; p.actions = actions; p.obs = obs; p.reward = reward; p.done = done; p.dir = dir;
+    p.stride = stride; p.seed = h->seed; p.env_id_base = h->env_id_base;
+    p.tape = h->tape; p.tape_off = h->tape_off; p.err = h->err;
+    rollout_fn fn = pick_kernel(h->cfg);
+    const int want = (ng + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const int grid = std::max(1, std::min(want, h->sm_count * h->blocks_per_sm));
+    if (timed && h->timing) CUDA_OK(cudaEventRecord(h->ev0, stream));
+    fn<<<grid, THREADS, h->smem_bytes, stream>>>(p);
+    CUDA_OK(cudaGetLastError());
+    if (timed && h->timing) { CUDA_OK(cudaEventRecord(h->ev1, stream)); h->ev_valid = true; }
+    h->launches++;
+    return 0;
+}
+
+int mgb_seed(mgb_handle *h, uint64_t seed) {
+    if (!h) return fail("null handle");
+    CUDA_OK(cudaSetDevice(h->device));
+    h->seed = seed;
+    // rewind the episode counters: word GW+2 of every env
+    const DevCfg &d = h->dc;
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemset2D(h->state + (size_t)(d.GW + 2) * 32, (size_t)d.S * 32 * 4, 0, 2 * 32 * 4, h->n_groups));
+    return 0;
+}
+
+int mgb_reset(mgb_handle *h, const uint8_t *mask, uint8_t *obs, uint8_t *dir, void *stream) {
+    if (!h) return fail("null handle");
+    CUDA_OK(cudaSetDevice(h->device));
+    return launch(h, 0, h->n_groups, 0, 1, mask, nullptr, obs, nullptr, nullptr, dir, h->n_envs, (cudaStream_t)stream, false);
+}
+
+int mgb_step(mgb_handle *h, const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir, void *stream) {
+    if (!h) return fail("null handle");
+    if (!actions) return fail("mgb_step: actions is NULL");
+    CUDA_OK(cudaSetDevice(h->device));
+    return launch(h, 0, h->n_groups, 1, 0, nullptr, actions, obs, reward, done, dir, h->n_envs, (cudaStream_t)stream, true);
+}
+
+int mgb_rollout(mgb_handle *h, int32_t T, const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir, void *stream) {
+    if (!h) return fail("null handle");
+    if (T < 1) return fail("mgb_rollout: T must be >= 1");
+    if (!actions) return fail("mgb_rollout: actions is NULL");
+    CUDA_OK(cudaSetDevice(h->device));
+    return launch(h, 0, h->n_groups, T, 0, nullptr, actions, obs, reward, done, dir, h->n_envs, (cudaStream_t)stream, true);
+}
+
+int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host, double *reward_host, uint8_t *done_host, uint8_t *dir_host) {
+    if (!h) return fail("null handle");
+    if (!actions_host) return fail("mgb_step_host: actions is NULL");
+    CUDA_OK(cudaSetDevice(h->device));
+    const int64_t N = h->n_envs;
+    if (!h->pipe[0]) {
+        for (auto &s : h->pipe) CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        CUDA_OK(cudaMalloc(&h->d_actions, N));
+        CUDA_OK(cudaMalloc(&h->d_obs, (size_t)N * OBS_BYTES));
+        CUDA_OK(cudaMalloc(&h->d_reward, (size_t)N * 8));
+        CUDA_OK(cudaMalloc(&h->d_done, N));
+        CUDA_OK(cudaMalloc(&h->d_dir, N));
+    }
+    // chunk the env range so that H2D, kernel and D2H of neighbouring chunks overlap
+    const int32_t G = h->n_groups;
+    int32_t nchunks = G >= 12288 ? 12 : (G >= 1024 ? 6 : 1);
+    const int32_t per = (G + nchunks - 1) / nchunks;
+    CUDA_OK(cudaDeviceSynchronize());   // order against whatever the caller enqueued on other streams
+    for (int32_t c = 0, g0 = 0; g0 < G; ++c, g0 += per) {
+        cudaStream_t s = h->pipe[c % HOST_PIPE_STREAMS];
+        const int32_t ng = std::min(per, G - g0);
+        const int64_t e0 = (int64_t)g0 * 32, ne = std::min((int64_t)ng * 32, N - e0);
+        CUDA_OK(cudaMemcpyAsync(h->d_actions + e0, actions_host + e0, ne, cudaMemcpyHostToDevice, s));
+        if (launch(h, g0, ng, 1, 0, nullptr, h->d_actions, obs_host ? h->d_obs : nullptr, reward_host ? h->d_reward : nullptr,
+                   done_host ? h->d_done : nullptr, dir_host ? h->d_dir : nullptr, N, s, false)) return -1;
+        if (obs_host) CUDA_OK(cudaMemcpyAsync(obs_host + e0 * OBS_BYTES, h->d_obs + e0 * OBS_BYTES, (size_t)ne * OBS_BYTES, cudaMemcpyDeviceToHost, s));
+        if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host + e0, h->d_reward + e0, (size_t)ne * 8, cudaMemcpyDeviceToHost, s));
+        if (done_host) CUDA_OK(cudaMemcpyAsync(done_host + e0, h->d_done + e0, ne, cudaMemcpyDeviceToHost, s));
+        if (dir_host) CUDA_OK(cudaMemcpyAsync(dir_host + e0, h->d_dir + e0, ne, cudaMemcpyDeviceToHost, s));
+    }
+    for (auto &s : h->pipe) CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+static int state_io(mgb_handle *h, bool set, int full_obs, int64_t first, int64_t count, uint8_t *grid, uint8_t *aux, int32_t *agent,
+                    uint8_t *carrying, int16_t *obstacles, uint8_t *target, uint32_t *rng, void *stream) {
+    if (!h) return fail("null handle");
+    if (first < 0 || count < 0 || first + count > h->n_envs) return fail("state range [%lld,+%lld) outside [0,%lld)", (long long)first, (long long)count, (long long)h->n_envs);
+    if (count == 0) return 0;
+    CUDA_OK(cudaSetDevice(h->device));
+    StateIO io;
+    io.cfg = h->dc; io.state = h->state; io.first = first; io.count = count;
+    io.grid = grid; io.aux = aux; io.agent = agent; io.carrying = carrying;
+    io.obstacles = h->dc.n_obst > 0 ? obstacles : nullptr; io.target = target; io.rng = rng; io.err = h->err;
+    const int64_t threads = count * h->dc.S;
+    const int block = 256;
+    const int64_t grid_dim = (threads + block - 1) / block;
+    if (grid_dim > 0x7FFFFFFF) return fail("state_io: too many envs for one launch");
+    if (set) k_set_state<<<(unsigned)grid_dim, block, 0, (cudaStream_t)stream>>>(io);
+    else k_get_state<<<(unsigned)grid_dim, block, 0, (cudaStream_t)stream>>>(io, full_obs);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int mgb_set_state(mgb_handle *h, int64_t first, int64_t count, const uint8_t *grid, const uint8_t *aux, const int32_t *agent,
+                  const uint8_t *carrying, const int16_t *obstacles, const uint8_t *target, const uint32_t *rng, void *stream) {
+    return state_io(h, true, 0, first, count, const_cast<uint8_t *>(grid), const_cast<uint8_t *>(aux), const_cast<int32_t *>(agent),
+                    const_cast<uint8_t *>(carrying), const_cast<int16_t *>(obstacles), const_cast<uint8_t *>(target),
+                    const_cast<uint32_t *>(rng), stream);
+}
+
+int mgb_get_state(mgb_handle *h, int64_t first, int64_t count, uint8_t *grid, uint8_t *aux, int32_t *agent, uint8_t *carrying,
+                  int16_t *obstacles, uint8_t *target, uint32_t *rng, void *stream) {
+    return state_io(h, false, 0, first, count, grid, aux, agent, carrying, obstacles, target, rng, stream);
+}
+
+int mgb_full_obs(mgb_handle *h, uint8_t *out, void *stream) {
+    if (!out) return fail("mgb_full_obs: out is NULL");
+    return state_io(h, false, 1, 0, h ? h->n_envs : 0, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int mgb_error_flags(mgb_handle *h, void *stream, uint32_t *flags_host) {
+    if (!h || !flags_host) return fail("null argument");
+    CUDA_OK(cudaSetDevice(h->device));
+    CUDA_OK(cudaMemcpyAsync(flags_host, h->err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_OK(cudaMemsetAsync(h->err, 0, 4, (cudaStream_t)stream));
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,772 @@
+// mgb200 device code: the batched MiniGrid hot path for sm_100a.
+//
+// Mapping: one THREAD owns one environment, one WARP owns a "group" of 32
+// environments and never talks to another warp.  A group's state lives in HBM as a
+// lane-interleaved block  state[group][word k][lane]  so that
+//   * loading/storing it is a run of perfectly coalesced 128-byte rows, and
+//   * once in shared memory every lane only ever touches bank == lane: the per-env random
+//     grid accesses of the view gather are bank-conflict free by construction.
+// Grid cells are 1-byte codes (type*21 + colour*3 + state, 231 combinations; 231..237 =
+// terminal goal of colour c), four per word.  A 256-entry shared-memory LUT expands a code to
+// (type | colour<<8 | state<<16 | flags<<24).
+//
+// Per step a thread applies the transition (minigrid.py:1227-1325 + subclass hooks), gathers
+// its 7x7 view with the closed form of slice+rotate_left, runs process_vis as
+// carry-propagation floods on 7-bit row masks, packs the 147 output bytes into 37
+// registers, realigns them with funnel shifts + one warp shuffle into a contiguous 4704-byte
+// shared-memory block per warp, and ONE lane hands that block to the TMA engine
+// (cp.async.bulk.global.shared::cta) -- the observation stream, which is ~93% of the
+// algorithmic bytes, leaves the SM as full-line bulk writes without occupying the LSU.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mgb {
+
+constexpr int VIEW = 7;
+constexpr int OBS_BYTES = 147;
+constexpr int GROUP = 32;
+constexpr int STAGE_BYTES = GROUP * OBS_BYTES;   // 4704 = 294 * 16
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int THREADS = WARPS_PER_BLOCK * 32;
+constexpr int MAX_OBST = 8;
+constexpr int XWORDS = 4;                        // agent, steps/target, episode, ndraws
+constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
+
+// minigrid.py:40-52 / 27-35 / 57-61
+enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
+             T_BOX = 7, T_GOAL = 8, T_LAVA = 9, T_AGENT = 10 };
+enum : int { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5, C_WHITE = 6 };
+enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
+enum : int { GEN_EMPTY = 0, GEN_DOORKEY = 1, GEN_FOURROOMS = 2, GEN_DYNOBS = 3, GEN_KEYCORRIDOR = 4 };
+enum : uint32_t { ERR_ACTION = 1, ERR_TAPE_END = 2, ERR_TAPE_RANGE = 4, ERR_SAMPLING = 8, ERR_BOUNDS = 16, ERR_CODE = 32 };
+
+__host__ __device__ constexpr int code_of(int t, int c, int s) { return t * 21 + c * 3 + s; }
+constexpr int CODE_EMPTY = code_of(T_EMPTY, 0, 0);            // 21
+constexpr int CODE_WALL = code_of(T_WALL, C_GREY, 0);          // out-of-grid cells (minigrid.py:469)
+constexpr int CODE_GOAL = code_of(T_GOAL, C_GREEN, 0);
+constexpr int CODE_TGOAL0 = 231;                               // + colour: Goal(toggletimes=0), overlap=True
+constexpr uint32_t EMPTY_WORD = 0x15151515u;                   // 4 x CODE_EMPTY
+static_assert(CODE_EMPTY == 0x15, "EMPTY_WORD");
+
+enum : uint32_t { F_OPAQUE = 1, F_OVERLAP = 2, F_PICKUP = 4, F_TGOAL = 8, F_LAVA = 16 };
+
+// code -> type | colour<<8 | state<<16 | flags<<24   (WorldObj.encode + the predicates
+// can_overlap / can_pickup / see_behind, minigrid.py:93-115,164-166,192-193,211-212,233-250,305-343)
+__host__ __device__ inline uint32_t lut_entry(int code) {
+    int t, c, s;
+    uint32_t f = 0;
+    if (code >= CODE_TGOAL0) {
+        if (code >= CODE_TGOAL0 + 7) return 0;
+        t = T_GOAL; c = code - CODE_TGOAL0; s = 0; f = F_TGOAL;
+    } else {
+        t = code / 21; c = (code % 21) / 3; s = code % 3;
+    }
+    if (t == T_WALL) f |= F_OPAQUE;
+    if (t == T_DOOR) f |= (s != 0) ? F_OPAQUE : F_OVERLAP;
+    if (t == T_EMPTY || t == T_UNSEEN || t == T_FLOOR || t == T_GOAL || t == T_LAVA) f |= F_OVERLAP;
+    if (t == T_LAVA) f |= F_LAVA;
+    if (t == T_KEY || t == T_BALL || t == T_BOX) f |= F_PICKUP;
+    return (uint32_t)t | ((uint32_t)c << 8) | ((uint32_t)s << 16) | (f << 24);
+}
+
+struct DevCfg {
+    int32_t gen, W, H, max_steps, see_through, n_actions, n_obst, room_size, num_rows, random_start, lava_v1;
+    int32_t GW;   // grid words per env = ceil(W*H/4)
+    int32_t S;    // state words per env
+};
+
+struct RolloutParams {
+    DevCfg cfg;
+    uint32_t *state;            // [n_groups][S][32]
+    const uint32_t *tmpl;       // [GW] static part of the layout (walls, fixed goal)
+    int64_t n_envs;
+    int32_t group0, n_groups;   // group sub-range handled by this launch
+    int32_t T;                  // steps (0 = reset/observe only)
+    int32_t do_reset;
+    int32_t autoreset;
+    const uint8_t *reset_mask;
+    const uint8_t *actions;     // [T][stride]
+    uint8_t *obs;               // [T][stride][147]
+    double *reward;
+    uint8_t *done;
+    uint8_t *dir;
+    int64_t stride;             // elements between step t and t+1 in the outputs
+    uint64_t seed;
+    int64_t env_id_base;
+    const int32_t *tape;
+    const int64_t *tape_off;
+    uint32_t *err;
+};
+
+// ------------------------------------------------------------------------------------------
+// per-thread environment context (registers) + shared-memory column
+// ------------------------------------------------------------------------------------------
+struct Env {                    // hot: stays in registers (its address never escapes)
+    uint32_t *st;               // &state_smem[0*32 + lane]; word k at st[k*32]
+    int ax, ay, dir, carry, steps, target;
+    bool dirty;                 // grid words modified since load
+};
+struct Rng {                    // cold: passed by reference to the out-of-line draw routine
+    uint32_t episode, ndraws;
+    uint32_t rb0, rb1, rb2, rb3, rblk;   // cached Philox block
+    uint32_t err;
+    int64_t gid;                // global env id (Philox counter)
+    int64_t lid;                // env index inside this handle (tape offsets)
+};
+
+__device__ __forceinline__ uint32_t cell_rd(const uint32_t *st, int idx) {
+    return __byte_perm(st[(idx >> 2) * 32], 0, 0x4440 | (idx & 3));
+}
+__device__ __forceinline__ void cell_wr(uint32_t *st, int idx, uint32_t code) {
+    uint32_t *p = &st[(idx >> 2) * 32];
+    const int sh = (idx & 3) * 8;
+    *p = (*p & ~(0xFFu << sh)) | (code << sh);
+}
+
+// Philox4x32-10, Salmon et al. SC'11
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t &o0, uint32_t &o1,
+                                              uint32_t &o2, uint32_t &o3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+// MiniGridEnv._rand_int (minigrid.py:939-944): low + mulhi32(u32, high-low) on the stream
+// (seed, global env id, episode); or the next tape entry in RNG-tape mode.
+__device__ __noinline__ int rand_int(Rng &e, const RolloutParams &p, int low, int high) {
+    if (p.tape) {
+        const int64_t off = p.tape_off[e.lid], len = p.tape_off[e.lid + 1] - off;
+        if ((int64_t)e.ndraws >= len) { e.err |= ERR_TAPE_END; return low; }
+        const int v = p.tape[off + e.ndraws++];
+        if (v < low || v >= high) e.err |= ERR_TAPE_RANGE;
+        return v;
+    }
+    const uint32_t blk = e.ndraws >> 2;
+    if (blk != e.rblk) {
+        philox4x32_10(blk, e.episode - 1u, (uint32_t)e.gid, (uint32_t)((uint64_t)e.gid >> 32),
+                      (uint32_t)p.seed, (uint32_t)(p.seed >> 32), e.rb0, e.rb1, e.rb2, e.rb3);
+        e.rblk = blk;
+    }
+    const uint32_t sel = e.ndraws & 3;
+    const uint32_t u = sel == 0 ? e.rb0 : sel == 1 ? e.rb1 : sel == 2 ? e.rb2 : e.rb3;
+    e.ndraws++;
+    return low + (int)__umulhi(u, (uint32_t)(high - low));
+}
+
+constexpr int HARD_TRY_CAP = 1 << 16;   // the reference would spin forever; we flag ERR_SAMPLING
+
+// MiniGridEnv.place_obj (minigrid.py:1003-1061).  max_tries < 0 == math.inf.
+// check_agent: "don't place the object where the agent is" (agent_pos may be None -> false).
+__device__ __forceinline__ bool place_obj(Env &e, Rng &rg, const RolloutParams &p, int code, int topx, int topy,
+                                          int sx, int sy, bool reject_next_to, int max_tries,
+                                          bool check_agent, int &ox, int &oy) {
+    const int W = p.cfg.W, H = p.cfg.H;
+    topx = max(topx, 0); topy = max(topy, 0);
+    const int hx = min(topx + sx, W), hy = min(topy + sy, H);
+    int tries = 0, x, y;
+    for (;;) {
+        if ((max_tries >= 0 && tries > max_tries) || tries > HARD_TRY_CAP) return false;
+        tries++;
+        x = rand_int(rg, p, topx, hx);
+        y = rand_int(rg, p, topy, hy);
+        if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) return false;
+        if (cell_rd(e.st, x * H + y) != CODE_EMPTY) continue;
+        if (check_agent && x == e.ax && y == e.ay) continue;
+        if (reject_next_to && (abs(e.ax - x) + abs(e.ay - y) < 2)) continue;   // roomgrid.py:3-12
+        break;
+    }
+    if (code != CODE_EMPTY) { cell_wr(e.st, x * H + y, (uint32_t)code); e.dirty = true; }
+    ox = x; oy = y;
+    return true;
+}
+
+// MiniGridEnv.place_agent (minigrid.py:1072-1090)
+__device__ __forceinline__ bool place_agent(Env &e, Rng &rg, const RolloutParams &p, int topx, int topy, int sx,
+                                            int sy, int max_tries) {
+    int x, y;
+    if (!place_obj(e, rg, p, CODE_EMPTY, topx, topy, sx, sy, false, max_tries, false, x, y)) return false;
+    e.ax = x; e.ay = y;
+    e.dir = rand_int(rg, p, 0, 4);
+    return true;
+}
+
+// COLOR_NAMES = sorted(COLORS) = blue, green, grey, purple, red, white, yellow (minigrid.py:24)
+__device__ __forceinline__ int rand_color(Rng &rg, const RolloutParams &p) {
+    const int k = rand_int(rg, p, 0, 7);
+    return (int)((0x4603512u >> (4 * k)) & 0xF);   // [2,1,5,3,0,6,4]
+}
+
+// obstacle k = byte pair (k&1)*2 of word GW+XWORDS+(k>>1)
+__device__ __forceinline__ void obst_get(const Env &e, const DevCfg &c, int k, int &x, int &y) {
+    const uint32_t w = e.st[(c.GW + XWORDS + (k >> 1)) * 32] >> ((k & 1) * 16);
+    x = w & 0xFF; y = (w >> 8) & 0xFF;
+}
+__device__ __forceinline__ void obst_set(Env &e, const DevCfg &c, int k, int x, int y) {
+    uint32_t *q = &e.st[(c.GW + XWORDS + (k >> 1)) * 32];
+    const int sh = (k & 1) * 16;
+    *q = (*q & ~(0xFFFFu << sh)) | ((uint32_t)(x | (y << 8)) << sh);
+}
+
+// ------------------------------------------------------------------------------------------
+// layout generators (reset): the static part comes from the template, the random part mirrors
+// the reference draw for draw.
+// ------------------------------------------------------------------------------------------
+struct Rooms {                       // RoomGrid bookkeeping (roomgrid.py:14-37), room r = j*3 + i
+    uint8_t dpx[9][4], dpy[9][4], has[9][4], doors[9][4], locked[9];
+};
+__device__ __forceinline__ int room_nb(int r, int k, int rows) {   // right, down, left, up
+    const int i = r % 3, j = r / 3;
+    if (k == 0) return i < 2 ? r + 1 : -1;
+    if (k == 1) return j < rows - 1 ? r + 3 : -1;
+    if (k == 2) return i > 0 ? r - 1 : -1;
+    return j > 0 ? r - 3 : -1;
+}
+__device__ __forceinline__ void add_door(Env &e, const DevCfg &c, Rooms &R, int r, int k, int color, bool locked) {
+    // roomgrid.py:212-246 with door_idx, colour and locked given
+    R.locked[r] = locked;
+    cell_wr(e.st, R.dpx[r][k] * c.H + R.dpy[r][k], (uint32_t)code_of(T_DOOR, color, locked ? 2 : 1));
+    R.doors[r][k] = 1;
+    R.doors[room_nb(r, k, c.num_rows)][(k + 2) & 3] = 1;
+}
+
+template <int GEN>
+__device__ __noinline__ void generate(Env &e, Rng &rg, const RolloutParams &p) {
+    const DevCfg &c = p.cfg;
+    const int W = c.W, H = c.H;
+    // Grid(width,height) + static walls/goal
+    for (int k = 0; k < c.GW; ++k) e.st[k * 32] = __ldg(&p.tmpl[k]);
+    e.dirty = true;
+    rg.episode++;
+    if (!p.tape) rg.ndraws = 0;
+    rg.rblk = 0xFFFFFFFFu;
+    e.carry = 0; e.steps = 0; e.target = 0;
+    bool ok = true;
+    int x, y;
+    if (GEN == GEN_EMPTY) {                              // envs/empty.py:30-57 (extra == 0)
+        if (!c.random_start) { e.ax = 1; e.ay = 1; e.dir = 0; }
+        else ok = place_agent(e, rg, p, 0, 0, W, H, -1);
+    } else if (GEN == GEN_DOORKEY) {                     // envs/doorkey.py:15-44
+        const int split = rand_int(rg, p, 2, W - 2);
+        for (int j = 0; j < H; ++j) cell_wr(e.st, split * H + j, CODE_WALL);
+        ok = place_agent(e, rg, p, 0, 0, split, H, -1);
+        const int door = rand_int(rg, p, 1, W - 2);
+        cell_wr(e.st, split * H + door, code_of(T_DOOR, C_YELLOW, 2));
+        ok = ok && place_obj(e, rg, p, code_of(T_KEY, C_YELLOW, 0), 0, 0, split, H, false, -1, true, x, y);
+    } else if (GEN == GEN_FOURROOMS) {                   // envs/fourrooms.py:19-69
+        const int rw = W / 2, rh = H / 2;
+        // walls are in the template; gaps in reference draw order (j,i) = (0,0),(0,1),(1,0)
+        const int g1 = rand_int(rg, p, 1, rh);            cell_wr(e.st, rw * H + g1, CODE_EMPTY);
+        const int g2 = rand_int(rg, p, 1, rw);            cell_wr(e.st, g2 * H + rh, CODE_EMPTY);
+        const int g3 = rand_int(rg, p, rw + 1, 2 * rw);   cell_wr(e.st, g3 * H + rh, CODE_EMPTY);
+        const int g4 = rand_int(rg, p, rh + 1, 2 * rh);   cell_wr(e.st, rw * H + g4, CODE_EMPTY);
+        ok = place_agent(e, rg, p, 0, 0, W, H, -1);
+        ok = ok && place_obj(e, rg, p, CODE_GOAL, 0, 0, W, H, false, -1, true, x, y);
+    } else if (GEN == GEN_DYNOBS) {                      // envs/dynamicobstacles.py:35-58
+        if (!c.random_start) { e.ax = 1; e.ay = 1; e.dir = 0; }
+        else ok = place_agent(e, rg, p, 0, 0, W, H, -1);
+        for (int k = 0; k < c.n_obst; ++k) {
+            ok = place_obj(e, rg, p, code_of(T_BALL, C_BLUE, 0), 0, 0, W, H, false, 100, true, x, y) && ok;
+            obst_set(e, c, k, x, y);
+        }
+    } else if (GEN == GEN_KEYCORRIDOR) {                 // roomgrid.py:118-169 + envs/keycorridor.py:26-49
+        Rooms R;
+        const int rs = c.room_size, rows = c.num_rows;
+        for (int r = 0; r < 9; ++r) {
+            R.locked[r] = 0;
+            for (int k = 0; k < 4; ++k) { R.has[r][k] = 0; R.doors[r][k] = 0; R.dpx[r][k] = 0; R.dpy[r][k] = 0; }
+        }
+        for (int j = 0; j < rows; ++j)
+            for (int i = 0; i < 3; ++i) {
+                const int r = j * 3 + i, tx = i * (rs - 1), ty = j * (rs - 1);
+                const int x_l = tx + 1, y_l = ty + 1, x_m = tx + rs - 1, y_m = ty + rs - 1;
+                if (i < 2) { R.dpx[r][0] = x_m; R.dpy[r][0] = rand_int(rg, p, y_l, y_m); R.has[r][0] = 1; }
+                if (j < rows - 1) { R.dpx[r][1] = rand_int(rg, p, x_l, x_m); R.dpy[r][1] = y_m; R.has[r][1] = 1; }
+                if (i > 0) { R.dpx[r][2] = R.dpx[r - 1][0]; R.dpy[r][2] = R.dpy[r - 1][0]; R.has[r][2] = R.has[r - 1][0]; }
+                if (j > 0) { R.dpx[r][3] = R.dpx[r - 3][1]; R.dpy[r][3] = R.dpy[r - 3][1]; R.has[r][3] = R.has[r - 3][1]; }
+            }
+        e.ax = 1 * (rs - 1) + rs / 2; e.ay = (rows / 2) * (rs - 1) + rs / 2; e.dir = 0;
+        // remove_wall(1, j, 3) (roomgrid.py:248-282)
+        for (int j = 1; j < rows; ++j) {
+            const int r = j * 3 + 1, tx = rs - 1, ty = j * (rs - 1);
+            for (int m = 1; m < rs - 1; ++m) cell_wr(e.st, (tx + m) * H + ty, CODE_EMPTY);
+            R.doors[r][3] = 1; R.doors[r - 3][1] = 1;
+        }
+        const int room_idx = rand_int(rg, p, 0, rows);
+        const int door_color = rand_color(rg, p);                     // add_door(2, room_idx, 2, locked=True)
+        add_door(e, c, R, room_idx * 3 + 2, 2, door_color, true);
+        const int obj_color = rand_color(rg, p);                      // add_object(2, room_idx, "ball")
+        ok = place_obj(e, rg, p, code_of(T_BALL, obj_color, 0), 2 * (rs - 1), room_idx * (rs - 1), rs, rs, true, 1000, true, x, y);
+        const int key_room = rand_int(rg, p, 0, rows);                // add_object(0, ri, "key", door.color)
+        ok = place_obj(e, rg, p, code_of(T_KEY, door_color, 0), 0, key_room * (rs - 1), rs, rs, true, 1000, true, x, y) && ok;
+        // RoomGrid.place_agent(1, rows//2) (roomgrid.py:284-303)
+        for (int guard = 0; ok && guard < HARD_TRY_CAP; ++guard) {
+            ok = place_agent(e, rg, p, rs - 1, (rows / 2) * (rs - 1), rs, rs, 1000);
+            if (!ok) break;
+            const int dx = (e.dir & 1) ? 0 : 1 - e.dir, dy = (e.dir & 1) ? 2 - e.dir : 0;
+            const uint32_t f = cell_rd(e.st, (e.ax + dx) * H + (e.ay + dy));
+            if (f == CODE_EMPTY || f / 21 == T_WALL) break;
+        }
+        // connect_all (roomgrid.py:305-359)
+        const int start = (e.ay / (rs - 1)) * 3 + e.ax / (rs - 1);
+        for (int it = 0; ok; ++it) {
+            if (it > 5000) { ok = false; break; }
+            uint32_t reach = 1u << start;
+            for (bool grew = true; grew;) {
+                grew = false;
+                for (int r = 0; r < rows * 3; ++r)
+                    if ((reach >> r) & 1)
+                        for (int k = 0; k < 4; ++k)
+                            if (R.doors[r][k]) {
+                                const uint32_t b = 1u << room_nb(r, k, rows);
+                                if (!(reach & b)) { reach |= b; grew = true; }
+                            }
+            }
+            if (__popc(reach) == rows * 3) break;
+            const int i = rand_int(rg, p, 0, 3);
+            const int j = rand_int(rg, p, 0, rows);
+            const int k = rand_int(rg, p, 0, 4);
+            if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) { ok = false; break; }
+            const int r = j * 3 + i;
+            if (!R.has[r][k] || R.doors[r][k]) continue;
+            if (R.locked[r] || R.locked[room_nb(r, k, rows)]) continue;
+            const int color = rand_color(rg, p);
+            add_door(e, c, R, r, k, color, false);
+        }
+        e.target = code_of(T_BALL, obj_color, 0);
+    }
+    if (!ok) rg.err |= ERR_SAMPLING;
+}
+
+// ------------------------------------------------------------------------------------------
+// transition: MiniGridEnv.step (minigrid.py:1227-1325) + subclass hooks
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double reward_formula(int steps, int max_steps) {
+    // _reward (minigrid.py:933-937): 1 - 0.9 * (step_count / max_steps), three separately
+    // rounded fp64 operations -- explicit _rn intrinsics so that nvcc cannot contract to an FMA.
+    return __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)max_steps)));
+}
+
+template <int GEN>
+__device__ __forceinline__ void transition(Env &e, Rng &rg, const RolloutParams &p, const uint32_t *lut, int action,
+                                           double &reward, bool &done) {
+    const DevCfg &c = p.cfg;
+    const int W = c.W, H = c.H;
+    reward = 0.0; done = false;
+    bool not_clear = false;
+    if (GEN == GEN_DYNOBS) {                             // envs/dynamicobstacles.py:60-78
+        if (action >= c.n_actions) action = 0;
+        const int dx0 = (e.dir & 1) ? 0 : 1 - e.dir, dy0 = (e.dir & 1) ? 2 - e.dir : 0;
+        const int fx0 = e.ax + dx0, fy0 = e.ay + dy0;
+        uint32_t front = CODE_WALL;
+        if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(e.st, fx0 * H + fy0);
+        not_clear = front != CODE_EMPTY && (lut[front] & 0xFF) != T_GOAL;
+        for (int k = 0; k < c.n_obst; ++k) {
+            int ox, oy, nx, ny;
+            obst_get(e, c, k, ox, oy);
+            const uint32_t ball = cell_rd(e.st, ox * H + oy);
+            if (place_obj(e, rg, p, (int)ball, ox - 1, oy - 1, 3, 3, false, 100, true, nx, ny)) {
+                obst_set(e, c, k, nx, ny);
+                cell_wr(e.st, ox * H + oy, CODE_EMPTY);
+            }
+        }
+    } else if (action >= c.n_actions) {
+        rg.err |= ERR_ACTION;                             // reference: assert False, "unknown action"
+        action = A_DONE;
+    }
+    e.steps++;
+    const int dx = (e.dir & 1) ? 0 : 1 - e.dir, dy = (e.dir & 1) ? 2 - e.dir : 0;
+    const int fx = e.ax + dx, fy = e.ay + dy;
+    uint32_t fc = CODE_WALL;
+    const int fidx = fx * H + fy;
+    const bool f_in = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
+    if (f_in) fc = cell_rd(e.st, fidx); else rg.err |= ERR_BOUNDS;
+    const uint32_t fw = lut[fc];
+    const uint32_t ff = fw >> 24;
+    const int ftype = fw & 0xFF;
+    if (action == A_LEFT) {
+        e.dir = (e.dir + 3) & 3;
+    } else if (action == A_RIGHT) {
+        e.dir = (e.dir + 1) & 3;
+    } else if (action == A_FORWARD) {
+        if (ff & F_OVERLAP) { e.ax = fx; e.ay = fy; }
+        if (ff & F_TGOAL) { done = true; reward = reward_formula(e.steps, c.max_steps); }
+        if (ff & F_LAVA) { if (c.lava_v1) { done = false; reward = -1.0; } else done = true; }
+    } else if (action == A_PICKUP) {
+        if ((ff & F_PICKUP) && e.carry == 0 && f_in) { e.carry = (int)fc; cell_wr(e.st, fidx, CODE_EMPTY); e.dirty = true; }
+    } else if (action == A_DROP) {
+        if (fc == CODE_EMPTY && e.carry != 0 && f_in) { cell_wr(e.st, fidx, (uint32_t)e.carry); e.carry = 0; e.dirty = true; }
+    } else if (action == A_TOGGLE) {
+        if (f_in) {
+            if (ftype == T_DOOR) {                       // Door.toggle minigrid.py:252-262
+                const int s = (fw >> 16) & 0xFF, col = (fw >> 8) & 0xFF;
+                int ns = s;
+                if (s == 2) { if (e.carry == code_of(T_KEY, col, 0)) ns = 0; }
+                else ns = s ^ 1;
+                if (ns != s) { cell_wr(e.st, fidx, fc - s + ns); e.dirty = true; }
+            } else if (ftype == T_BOX || (ftype == T_GOAL && !(ff & F_TGOAL))) {
+                // default Box (contains None) and default Goal (toggletimes 1) vanish: :171-177, :355-360
+                cell_wr(e.st, fidx, CODE_EMPTY); e.dirty = true;
+            }
+        }
+    }
+    if (e.steps >= c.max_steps) done = true;
+    if (GEN == GEN_KEYCORRIDOR) {                        // envs/keycorridor.py:51-59
+        if (action == A_PICKUP && e.carry != 0 && e.carry == e.target) { reward = reward_formula(e.steps, c.max_steps); done = true; }
+    }
+    if (GEN == GEN_DYNOBS) {                             // envs/dynamicobstacles.py:84-87
+        e.dirty = true;
+        if (action == A_FORWARD && not_clear) { reward = -1.0; done = true; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// observation: gen_obs_grid + Grid.encode (minigrid.py:1327-1381, 571-594)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rev7(uint32_t v) { return __brev(v) >> 25; }
+// cells reachable towards higher bits through runs of transparent cells (one sweep of
+// process_vis, minigrid.py:624-635) as a carry chain: ((v&t)+t)^t marks [lowest seed .. run end+1]
+__device__ __forceinline__ uint32_t flood_up(uint32_t v, uint32_t t) { return ((((v & t) + t) ^ t) | v) & 0x7Fu; }
+
+// insert the 3 low bytes of x at byte offset sh of the word pair (a, b); sh folds after unrolling
+__device__ __forceinline__ void put3(int sh, uint32_t &a, uint32_t &b, uint32_t x) {
+    if (sh == 0) a = __byte_perm(a, x, 0x3654);
+    else if (sh == 1) a = __byte_perm(a, x, 0x6540);
+    else if (sh == 2) { a = __byte_perm(a, x, 0x5410); b = __byte_perm(b, x, 0x3216); }
+    else { a = __byte_perm(a, x, 0x4210); b = __byte_perm(b, x, 0x3265); }
+}
+
+template <bool SEE>
+__device__ __forceinline__ void observe(const Env &e, const DevCfg &c, const uint32_t *lut,
+                                        uint32_t *stage_w, int lane) {
+    const int W = c.W, H = c.H;
+    const int dx = (e.dir & 1) ? 0 : 1 - e.dir, dy = (e.dir & 1) ? 2 - e.dir : 0;
+    const int rx = -dy, ry = dx;
+    uint32_t acc[38];
+#pragma unroll
+    for (int i = 0; i < 38; ++i) acc[i] = 0;
+    uint32_t rowvis = 1u << 3;                              // mask[(3,6)] = True (minigrid.py:619)
+    const int dstep = rx * H + ry;
+#pragma unroll
+    for (int vy = VIEW - 1; vy >= 0; --vy) {
+        // world(vx,vy) = agent + d*(6-vy) + r*(vx-3)      
+        int wx = e.ax + dx * (6 - vy) - 3 * rx, wy = e.ay + dy * (6 - vy) - 3 * ry;
+        int idx = wx * H + wy;
+        uint32_t xs[VIEW];
+        uint32_t opaque = 0;
+#pragma unroll
+        for (int vx = 0; vx < VIEW; ++vx) {
+            uint32_t code = CODE_WALL;
+            if ((unsigned)wx < (unsigned)W && (unsigned)wy < (unsigned)H) code = cell_rd(e.st, idx);
+            const uint32_t x = lut[code];
+            xs[vx] = x;
+            if (!SEE) opaque |= ((x >> 24) & 1u) << vx;
+            wx += rx; wy += ry; idx += dstep;
+        }
+        uint32_t vis = 0x7F;
+        if (!SEE) {
+            const uint32_t t = ~opaque & 0x7Fu;
+            const uint32_t f = flood_up(rowvis, t);                       // forward sweep i = 0..5
+            vis = rev7(flood_up(rev7(f), rev7(t)));                        // reverse sweep i = 6..1
+            const uint32_t s = vis & t;
+            rowvis = (s | (s << 1) | (s >> 1)) & 0x7Fu;                    // seeds of row vy-1
+        }
+        if (vy == VIEW - 1) xs[3] = e.carry ? lut[e.carry] : (uint32_t)T_EMPTY;   // minigrid.py:1349-1356
+#pragma unroll
+        for (int vx = 0; vx < VIEW; ++vx) {
+            uint32_t x = xs[vx];
+            if (!SEE) x = ((vis >> vx) & 1u) ? x : 0u;
+            const int b = 3 * (vx * VIEW + vy);
+            put3(b & 3, acc[b >> 2], acc[(b >> 2) + 1], x);
+        }
+    }
+    acc[36] &= 0x00FFFFFFu;
+    acc[37] = 0;
+    // realign the 147-byte record to its byte offset lane*147 inside the warp's 4704-byte block
+    const int boff = lane * OBS_BYTES;
+    const int q = boff >> 2;
+    const uint32_t s8 = (boff & 3) * 8;
+    uint32_t prev = 0;
+    uint32_t first = 0, w36 = 0, w37 = 0;
+#pragma unroll
+    for (int j = 0; j < 38; ++j) {
+        const uint32_t o = __funnelshift_l(prev, acc[j], s8);
+        prev = acc[j];
+        if (j == 0) first = o;
+        else if (j < 36) stage_w[q + j] = o;
+        else if (j == 36) w36 = o;
+        else w37 = o;
+    }
+    // the partial last word of lane t-1 shares a 32-bit word with the head of lane t
+    const uint32_t tail = (s8 >= 16) ? w37 : w36;
+    const uint32_t ptail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+    if (s8 != 0 && lane > 0) first |= ptail;
+    stage_w[q] = first;
+    if (s8 != 0) stage_w[q + 36] = w36;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA bulk store of the staged observation block
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store(void *gptr, const void *sptr, uint32_t bytes) {
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sptr);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gptr), "r"(saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// the persistent rollout kernel (also serves reset and single step)
+// ------------------------------------------------------------------------------------------
+template <int GEN, bool SEE>
+__global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ RolloutParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const DevCfg &c = p.cfg;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
+    uint8_t *stage_base = smem_raw + 1024;
+    uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * STAGE_BYTES);
+    uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + WARPS_PER_BLOCK * STAGE_BYTES) + warp * (c.S * 32);
+    for (int i = threadIdx.x; i < 256; i += THREADS) lut[i] = lut_entry(i);
+    __syncthreads();
+
+    const int S = c.S, GW = c.GW;
+    const int64_t stride = p.stride;
+    for (int g = blockIdx.x * WARPS_PER_BLOCK + warp; g < p.n_groups; g += gridDim.x * WARPS_PER_BLOCK) {
+        const int group = p.group0 + g;
+        uint32_t *gst = p.state + (size_t)group * S * 32 + lane;
+        // ---- load the group's state block: S coalesced 128-byte rows -> bank == lane ----
+        for (int k = 0; k < S; ++k) st_warp[k * 32 + lane] = gst[k * 32];
+        Env e;
+        Rng rg;
+        e.st = st_warp + lane;
+        rg.lid = (int64_t)group * 32 + lane;
+        rg.gid = p.env_id_base + rg.lid;
+        const int64_t lid = rg.lid;
+        const bool valid = lid < p.n_envs;
+        {
+            const uint32_t w0 = e.st[(GW + 0) * 32], w1 = e.st[(GW + 1) * 32];
+            e.ax = w0 & 0xFF; e.ay = (w0 >> 8) & 0xFF; e.dir = (w0 >> 16) & 3; e.carry = w0 >> 24;
+            e.steps = w1 & 0xFFFF; e.target = (w1 >> 16) & 0xFF;
+            rg.episode = e.st[(GW + 2) * 32]; rg.ndraws = e.st[(GW + 3) * 32];
+        }
+        rg.rblk = 0xFFFFFFFFu; rg.err = 0; e.dirty = false;
+        rg.rb0 = rg.rb1 = rg.rb2 = rg.rb3 = 0;
+
+        const bool full = ((int64_t)group * 32 + 32) <= p.n_envs;
+        const int nvalid = full ? 32 : (int)max((int64_t)0, p.n_envs - (int64_t)group * 32);
+
+        if (p.do_reset) {
+            const bool m = valid && (!p.reset_mask || p.reset_mask[lid]);
+            if (m) { Env tmp = e; generate<GEN>(tmp, rg, p); e = tmp; }   // copy-in/out keeps `e` in registers
+        }
+        const int nsteps = p.T > 0 ? p.T : 1;
+        int a_next = 0;
+        if (p.T > 0 && valid) a_next = p.actions[lid];
+        for (int t = 0; t < nsteps; ++t) {
+            double reward = 0.0; bool done = false;
+            if (p.T > 0) {
+                const int action = a_next;
+                if (t + 1 < p.T && valid) a_next = p.actions[(int64_t)(t + 1) * stride + lid];
+                if (valid) {
+                    transition<GEN>(e, rg, p, lut, action, reward, done);
+                    if (done && p.autoreset) { Env tmp = e; generate<GEN>(tmp, rg, p); e = tmp; }
+                }
+            }
+            const int64_t o = (int64_t)t * stride + lid;
+            if (p.obs) {
+                if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
+                __syncwarp();
+                observe<SEE>(e, c, lut, stage_w, lane);
+                uint8_t *gobs = p.obs + ((int64_t)t * stride + (int64_t)group * 32) * OBS_BYTES;
+                if (full && ((reinterpret_cast<uintptr_t>(gobs) & 15) == 0)) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) bulk_store(gobs, stage_w, STAGE_BYTES);
+                } else {                                         // ragged tail group / unaligned base
+                    __syncwarp();
+                    const uint8_t *sb = reinterpret_cast<const uint8_t *>(stage_w);
+                    for (int b = lane; b < nvalid * OBS_BYTES; b += 32) gobs[b] = sb[b];
+                    __syncwarp();
+                }
+            }
+            if (valid) {
+                if (p.T > 0) {
+                    if (p.reward) p.reward[o] = reward;
+                    if (p.done) p.done[o] = done ? 1 : 0;
+                }
+                if (p.dir) p.dir[o] = (uint8_t)e.dir;
+            }
+        }
+        // ---- write the state back ----
+        e.st[(GW + 0) * 32] = (uint32_t)e.ax | ((uint32_t)e.ay << 8) | ((uint32_t)e.dir << 16) | ((uint32_t)e.carry << 24);
+        e.st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16);
+        e.st[(GW + 2) * 32] = rg.episode;
+        e.st[(GW + 3) * 32] = rg.ndraws;
+        const bool any_dirty = __any_sync(0xFFFFFFFFu, e.dirty);
+        __syncwarp();
+        for (int k = any_dirty ? 0 : GW; k < S; ++k) gst[k * 32] = st_warp[k * 32 + lane];
+        if (rg.err) atomicOr(p.err, rg.err);
+        __syncwarp();
+    }
+    if (lane == 0) bulk_store_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------
+// state exchange kernels (K3): reference encoding <-> device layout
+// ------------------------------------------------------------------------------------------
+struct StateIO {
+    DevCfg cfg;
+    uint32_t *state;
+    int64_t first, count;
+    uint8_t *grid;        // [count][W][H][3]
+    uint8_t *aux;         // [count][W][H]
+    int32_t *agent;       // [count][4]
+    uint8_t *carrying;    // [count][3]
+    int16_t *obstacles;   // [count][8][2]
+    uint8_t *target;      // [count][2]
+    uint32_t *rng;        // [count][2]
+    uint32_t *err;
+};
+
+__device__ __forceinline__ int encode_cell(int t, int c, int s, int auxbits, uint32_t &err) {
+    if (t == T_UNSEEN) t = T_EMPTY;                       // both decode to None (minigrid.py:124-125)
+    if (t > T_LAVA || c > 6 || s > 2) { err |= ERR_CODE; return CODE_EMPTY; }
+    if (t != T_DOOR) s = 0;                               // WorldObj.decode ignores state for non-doors
+    if (t == T_EMPTY) return CODE_EMPTY;
+    if (t == T_GOAL && (auxbits & 1)) return CODE_TGOAL0 + c;
+    return code_of(t, c, s);
+}
+
+// one thread per (env, state word)
+__global__ void k_set_state(const StateIO io) {
+    const DevCfg &c = io.cfg;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = tid / c.S;
+    const int k = (int)(tid % c.S);
+    if (n >= io.count) return;
+    const int64_t env = io.first + n;
+    uint32_t *dst = io.state + ((env >> 5) * c.S + k) * 32 + (env & 31);
+    uint32_t err = 0;
+    const int cells = c.W * c.H;
+    if (k < c.GW) {
+        if (!io.grid) return;
+        uint32_t w = 0;
+        for (int b = 0; b < 4; ++b) {
+            const int idx = k * 4 + b;
+            int code = CODE_EMPTY;
+            if (idx < cells) {
+                const uint8_t *g = io.grid + ((size_t)n * cells + idx) * 3;
+                code = encode_cell(g[0], g[1], g[2], io.aux ? io.aux[(size_t)n * cells + idx] : 0, err);
+            }
+            w |= (uint32_t)code << (8 * b);
+        }
+        *dst = w;
+    } else if (k == c.GW) {
+        uint32_t w = *dst;
+        if (io.agent) {
+            const int32_t *a = io.agent + n * 4;
+            if (a[0] < 0 || a[0] >= c.W || a[1] < 0 || a[1] >= c.H || a[2] < 0 || a[2] > 3) err |= ERR_BOUNDS;
+            w = (w & 0xFF000000u) | (uint32_t)(a[0] & 0xFF) | ((uint32_t)(a[1] & 0xFF) << 8) | ((uint32_t)(a[2] & 3) << 16);
+        }
+        if (io.carrying) {
+            const uint8_t *q = io.carrying + n * 3;
+            int code = 0;
+            if (q[0] != 0) { code = encode_cell(q[0], q[1], q[2], 0, err); if (code == CODE_EMPTY) code = 0; }
+            w = (w & 0x00FFFFFFu) | ((uint32_t)code << 24);
+        }
+        *dst = w;
+    } else if (k == c.GW + 1) {
+        uint32_t w = *dst;
+        if (io.agent) w = (w & 0xFFFF0000u) | (uint32_t)(io.agent[n * 4 + 3] & 0xFFFF);
+        if (io.target) {
+            const uint8_t *q = io.target + n * 2;
+            const int code = q[0] ? code_of(q[0], q[1], 0) : 0;
+            w = (w & 0xFF00FFFFu) | ((uint32_t)code << 16);
+        }
+        *dst = w;
+    } else if (k == c.GW + 2) {
+        if (io.rng) *dst = io.rng[n * 2];
+    } else if (k == c.GW + 3) {
+        if (io.rng) *dst = io.rng[n * 2 + 1];
+    } else {
+        if (!io.obstacles) return;
+        const int o = (k - c.GW - XWORDS) * 2;
+        const int16_t *q = io.obstacles + (n * MAX_OBST + o) * 2;
+        *dst = (uint32_t)(q[0] & 0xFF) | ((uint32_t)(q[1] & 0xFF) << 8) | ((uint32_t)(q[2] & 0xFF) << 16) | ((uint32_t)(q[3] & 0xFF) << 24);
+    }
+    if (err) atomicOr(io.err, err);
+}
+
+// one thread per (env, state word); full_obs != 0: FullyObsWrapper (wrappers.py:311-338)
+__global__ void k_get_state(const StateIO io, int full_obs) {
+    const DevCfg &c = io.cfg;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n = tid / c.S;
+    const int k = (int)(tid % c.S);
+    if (n >= io.count) return;
+    const int64_t env = io.first + n;
+    const uint32_t *base = io.state + (env >> 5) * c.S * 32 + (env & 31);
+    const uint32_t w = base[k * 32];
+    const int cells = c.W * c.H;
+    if (k < c.GW) {
+        int aidx = -1, adir = 0;
+        if (full_obs) {
+            const uint32_t w0 = base[c.GW * 32];
+            aidx = (int)(w0 & 0xFF) * c.H + (int)((w0 >> 8) & 0xFF);
+            adir = (w0 >> 16) & 3;
+        }
+        for (int b = 0; b < 4; ++b) {
+            const int idx = k * 4 + b;
+            if (idx >= cells) break;
+            const uint32_t x = lut_entry((w >> (8 * b)) & 0xFF);
+            if (io.grid) {
+                uint8_t *g = io.grid + ((size_t)n * cells + idx) * 3;
+                if (idx == aidx) { g[0] = T_AGENT; g[1] = 0; g[2] = (uint8_t)adir; }
+                else { g[0] = x & 0xFF; g[1] = (x >> 8) & 0xFF; g[2] = (x >> 16) & 0xFF; }
+            }
+            if (io.aux) io.aux[(size_t)n * cells + idx] = ((x >> 24) & F_TGOAL) ? 1 : 0;
+        }
+    } else if (k == c.GW) {
+        if (io.agent) { int32_t *a = io.agent + n * 4; a[0] = w & 0xFF; a[1] = (w >> 8) & 0xFF; a[2] = (w >> 16) & 3; }
+        if (io.carrying) {
+            uint8_t *q = io.carrying + n * 3;
+            const uint32_t code = w >> 24;
+            const uint32_t x = code ? lut_entry(code) : 0;
+            q[0] = x & 0xFF; q[1] = (x >> 8) & 0xFF; q[2] = (x >> 16) & 0xFF;
+        }
+    } else if (k == c.GW + 1) {
+        if (io.agent) io.agent[n * 4 + 3] = w & 0xFFFF;
+        if (io.target) {
+            const uint32_t code = (w >> 16) & 0xFF;
+            const uint32_t x = code ? lut_entry(code) : 0;
+            io.target[n * 2] = x & 0xFF; io.target[n * 2 + 1] = (x >> 8) & 0xFF;
+        }
+    } else if (k == c.GW + 2) {
+        if (io.rng) io.rng[n * 2] = w;
+    } else if (k == c.GW + 3) {
+        if (io.rng) io.rng[n * 2 + 1] = w;
+    } else {
+        if (!io.obstacles) return;
+        const int o = (k - c.GW - XWORDS) * 2;
+        int16_t *q = io.obstacles + (n * MAX_OBST + o) * 2;
+        q[0] = w & 0xFF; q[1] = (w >> 8) & 0xFF; q[2] = (w >> 16) & 0xFF; q[3] = (w >> 24) & 0xFF;
+    }
+}
+
+}  // namespace mgb

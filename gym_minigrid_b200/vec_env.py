@@ -1,0 +1,300 @@
+"""VecMiniGridEnv: the batched, GPU-resident mirror of the reference's MiniGridEnv interface
+(gym_minigrid/minigrid.py:720-1381).  Same attribute and method names, batched:
+
+    env = make('MiniGrid-Empty-8x8-v0', num_envs=1 << 20)
+    obs = env.reset()                              # {'image': uint8[N,7,7,3] (cuda), 'direction': uint8[N], 'mission': seq}
+    obs, reward, done, info = env.step(actions)    # reward float64[N], done bool[N]; auto-reset on done
+
+PyTorch is plumbing only (device memory, streams); all computation happens in libmgb200.so.
+"""
+from enum import IntEnum
+
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib, spaces
+
+# minigrid.py:27-61
+COLOR_TO_IDX = {'red': 0, 'green': 1, 'blue': 2, 'purple': 3, 'yellow': 4, 'grey': 5, 'white': 6}
+IDX_TO_COLOR = {v: k for k, v in COLOR_TO_IDX.items()}
+OBJECT_TO_IDX = {'unseen': 0, 'empty': 1, 'wall': 2, 'floor': 3, 'door': 4, 'key': 5, 'ball': 6, 'box': 7,
+                 'goal': 8, 'lava': 9, 'agent': 10}
+IDX_TO_OBJECT = {v: k for k, v in OBJECT_TO_IDX.items()}
+STATE_TO_IDX = {'open': 0, 'closed': 1, 'locked': 2}
+
+
+class Actions(IntEnum):          # MiniGridEnv.Actions, minigrid.py:731-745
+    left = 0
+    right = 1
+    forward = 2
+    pickup = 3
+    drop = 4
+    toggle = 5
+    done = 6
+
+
+class MissionBatch:
+    """obs['mission'] for N envs without materialising N Python strings per step."""
+
+    def __init__(self, env):
+        self._env = env
+        self._targets = None
+
+    def __len__(self):
+        return self._env.num_envs
+
+    def __getitem__(self, i):
+        tmpl = self._env._mission
+        if "%s" not in tmpl:
+            return tmpl
+        if self._targets is None:          # KeyCorridor: "pick up the <colour> <type>" (keycorridor.py:49)
+            self._targets = self._env.get_state(("target",))["target"].cpu().numpy()
+        t, c = self._targets[i]
+        return tmpl % (IDX_TO_COLOR[int(c)], IDX_TO_OBJECT[int(t)])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class VecMiniGridEnv:
+    metadata = {'render.modes': [], 'video.frames_per_second': 10}
+    Actions = Actions
+
+    def __init__(self, spec, num_envs=1, device=None, seed=1337, env_id_base=0, autoreset=True):
+        self.spec = spec
+        cfg = spec["config"]
+        self._cfg = cfg
+        self._L = _lib.load()                      # raises loudly when libmgb200.so is missing
+        if not torch.cuda.is_available():
+            raise _lib.MgbError("gym_minigrid_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MgbError("device must be a CUDA device, got %s" % self.device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.num_envs = int(num_envs)
+        # reference attribute names (minigrid.py:785-819)
+        self.actions = Actions
+        self.action_space = spaces.Discrete(cfg["n_actions"])
+        self.agent_view_size = 7
+        self.observation_space = spaces.Dict({'image': spaces.Box(0, 255, (7, 7, 3), 'uint8')})
+        self.reward_range = cfg["reward_range"]
+        self.width, self.height = cfg["width"], cfg["height"]
+        self.max_steps = cfg["max_steps"]
+        self.see_through_walls = bool(cfg["see_through"])
+        self._mission = cfg["mission"]
+        c = _lib.MgbConfig(**{k: int(cfg[k]) for k, _ in _lib.MgbConfig._fields_})
+        h = C.c_void_p()
+        _lib.check(self._L.mgb_create(C.byref(c), self.num_envs, self.device.index, C.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                      int(env_id_base), C.byref(h)))
+        self._h = h
+        self._seed = seed
+        if not autoreset:
+            _lib.check(self._L.mgb_set_autoreset(self._h, 0))
+        self._tape = None
+        N = self.num_envs
+        with torch.cuda.device(self.device):
+            self._obs = torch.empty((N, 7, 7, 3), dtype=torch.uint8, device=self.device)
+            self._dir = torch.empty((N,), dtype=torch.uint8, device=self.device)
+            self._reward = torch.empty((N,), dtype=torch.float64, device=self.device)
+            self._done = torch.empty((N,), dtype=torch.uint8, device=self.device)
+        self._host = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _actions(self, actions, shape):
+        a = actions
+        if not torch.is_tensor(a):
+            a = torch.as_tensor(np.asarray(a))
+        if a.dtype != torch.uint8:
+            a = a.to(torch.uint8)
+        a = a.to(self.device, non_blocking=True).contiguous()
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError("actions must have shape %s, got %s" % (tuple(shape), tuple(a.shape)))
+        return a
+
+    def _obs_dict(self, image, direction):
+        return {'image': image, 'direction': direction, 'mission': MissionBatch(self)}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mgb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def unwrapped(self):
+        return self
+
+    # ------------------------------------------------------------------ gym protocol
+    def seed(self, seed=1337):
+        """MiniGridEnv.seed (minigrid.py:860-863): re-key the RNG; effective at the next reset."""
+        _lib.check(self._L.mgb_seed(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1))))
+        self._seed = seed
+        return [seed]
+
+    def reset(self, mask=None):
+        """MiniGridEnv.reset for every env (or those with mask != 0); returns the batched obs dict."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask).to(self.device).to(torch.uint8).contiguous()
+            assert m.shape == (self.num_envs,)
+        _lib.check(self._L.mgb_reset(self._h, _ptr(m), _ptr(self._obs), _ptr(self._dir), self._stream()))
+        return self._obs_dict(self._obs, self._dir)
+
+    def step(self, actions, out=None):
+        """MiniGridEnv.step for every env.  `out` = optional (obs, reward, done, dir) tensors to write into."""
+        a = self._actions(actions, (self.num_envs,))
+        obs, reward, done, d = out if out is not None else (self._obs, self._reward, self._done, self._dir)
+        _lib.check(self._L.mgb_step(self._h, _ptr(a), _ptr(obs), _ptr(reward), _ptr(done), _ptr(d), self._stream()))
+        return self._obs_dict(obs, d), reward, done.view(torch.bool), {}
+
+    def rollout(self, actions, out=None, want_obs=True):
+        """T steps in one persistent kernel.  actions [T,N] -> obs [T,N,7,7,3], reward, done, dir [T,N]."""
+        T = int(actions.shape[0])
+        a = self._actions(actions, (T, self.num_envs))
+        N = self.num_envs
+        if out is None:
+            obs = torch.empty((T, N, 7, 7, 3), dtype=torch.uint8, device=self.device) if want_obs else None
+            reward = torch.empty((T, N), dtype=torch.float64, device=self.device)
+            done = torch.empty((T, N), dtype=torch.uint8, device=self.device)
+            d = torch.empty((T, N), dtype=torch.uint8, device=self.device)
+        else:
+            obs, reward, done, d = out
+        _lib.check(self._L.mgb_rollout(self._h, T, _ptr(a), _ptr(obs), _ptr(reward), _ptr(done), _ptr(d), self._stream()))
+        return obs, reward, done.view(torch.bool), d
+
+    def step_host(self, actions_host):
+        """End-to-end step with HOST buffers: actions (pinned uint8[N]) in, pinned numpy-viewable
+        obs/reward/done/dir out; H2D + kernel + D2H are pipelined inside libmgb200 (mgb_step_host)."""
+        N = self.num_envs
+        if self._host is None:
+            self._host = dict(
+                obs=torch.empty((N, 7, 7, 3), dtype=torch.uint8).pin_memory(),
+                reward=torch.empty((N,), dtype=torch.float64).pin_memory(),
+                done=torch.empty((N,), dtype=torch.uint8).pin_memory(),
+                dir=torch.empty((N,), dtype=torch.uint8).pin_memory())
+        a = actions_host
+        if not torch.is_tensor(a):
+            a = torch.as_tensor(np.asarray(a))
+        a = a.to(torch.uint8).contiguous()
+        assert a.device.type == "cpu" and a.shape == (N,)
+        hb = self._host
+        _lib.check(self._L.mgb_step_host(self._h, _ptr(a), _ptr(hb["obs"]), _ptr(hb["reward"]), _ptr(hb["done"]), _ptr(hb["dir"])))
+        return self._obs_dict(hb["obs"], hb["dir"]), hb["reward"], hb["done"].view(torch.bool), {}
+
+    # ------------------------------------------------------------------ state / checkpoint
+    _STATE_FIELDS = ("grid", "aux", "agent", "carrying", "obstacles", "target", "rng")
+
+    def _state_shapes(self, n):
+        W, H = self.width, self.height
+        return dict(grid=((n, W, H, 3), torch.uint8), aux=((n, W, H), torch.uint8), agent=((n, 4), torch.int32),
+                    carrying=((n, 3), torch.uint8), obstacles=((n, _lib.MAX_OBSTACLES, 2), torch.int16),
+                    target=((n, 2), torch.uint8), rng=((n, 2), torch.int32))
+
+    def get_state(self, fields=None, first=0, count=None):
+        """Snapshot in the reference's encoding (Grid.encode layout); also the checkpoint format."""
+        count = self.num_envs - first if count is None else count
+        fields = self._STATE_FIELDS if fields is None else fields
+        shapes = self._state_shapes(count)
+        out = {k: torch.zeros(shapes[k][0], dtype=shapes[k][1], device=self.device) for k in fields}
+        args = [_ptr(out.get(k)) for k in self._STATE_FIELDS]
+        _lib.check(self._L.mgb_get_state(self._h, first, count, *args, self._stream()))
+        return out
+
+    def set_state(self, state, first=0):
+        shapes = self._state_shapes(0)
+        count = None
+        ts = {}
+        for k in self._STATE_FIELDS:
+            if k in state and state[k] is not None:
+                v = state[k]
+                if not torch.is_tensor(v):
+                    v = torch.as_tensor(np.ascontiguousarray(v))
+                if k == "rng":
+                    v = v.to(torch.int64).to(torch.int32) if v.dtype not in (torch.int32,) else v
+                v = v.to(self.device).to(shapes[k][1]).contiguous()
+                n = v.shape[0]
+                if k == "obstacles" and v.shape[1] != _lib.MAX_OBSTACLES:
+                    pad = torch.zeros((n, _lib.MAX_OBSTACLES, 2), dtype=torch.int16, device=self.device)
+                    pad[:, :v.shape[1]] = v
+                    v = pad
+                assert tuple(v.shape[1:]) == tuple(self._state_shapes(n)[k][0][1:]), (k, v.shape)
+                count = n if count is None else count
+                assert n == count
+                ts[k] = v
+        if count is None:
+            return
+        args = [_ptr(ts.get(k)) for k in self._STATE_FIELDS]
+        _lib.check(self._L.mgb_set_state(self._h, first, count, *args, self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()     # ts goes out of scope
+        self.check_errors()
+
+    def set_rng_tape(self, draws, offsets):
+        """RNG-tape parity mode (SURVEY §8c mode 2)."""
+        if draws is None:
+            self._tape = None
+            _lib.check(self._L.mgb_set_rng_tape(self._h, None, None))
+            return
+        d = torch.as_tensor(np.ascontiguousarray(draws, dtype=np.int32)).to(self.device)
+        o = torch.as_tensor(np.ascontiguousarray(offsets, dtype=np.int64)).to(self.device)
+        assert o.shape == (self.num_envs + 1,)
+        self._tape = (d, o)
+        _lib.check(self._L.mgb_set_rng_tape(self._h, _ptr(d), _ptr(o)))
+
+    def full_obs(self):
+        """FullyObsWrapper.observation (wrappers.py:311-338) for every env: uint8[N,W,H,3]."""
+        out = torch.empty((self.num_envs, self.width, self.height, 3), dtype=torch.uint8, device=self.device)
+        _lib.check(self._L.mgb_full_obs(self._h, _ptr(out), self._stream()))
+        return out
+
+    def check_errors(self):
+        """Synchronise and raise if the device flagged anything the reference would have asserted on."""
+        f = C.c_uint32(0)
+        _lib.check(self._L.mgb_error_flags(self._h, self._stream(), C.byref(f)))
+        if f.value:
+            msgs = [m for b, m in _lib.ERROR_BITS.items() if f.value & b]
+            raise _lib.MgbError("device error flags 0x%x: %s" % (f.value, "; ".join(msgs)))
+
+    # ------------------------------------------------------------------ reference attributes, batched
+    @property
+    def agent_pos(self):
+        return self.get_state(("agent",))["agent"][:, :2]
+
+    @property
+    def agent_dir(self):
+        return self.get_state(("agent",))["agent"][:, 2]
+
+    @property
+    def step_count(self):
+        return self.get_state(("agent",))["agent"][:, 3]
+
+    @property
+    def carrying(self):
+        return self.get_state(("carrying",))["carrying"]
+
+    @property
+    def mission(self):
+        return MissionBatch(self)
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.mgb_kernel_launches(self._h))
+
+    def set_kernel_timing(self, on=True):
+        _lib.check(self._L.mgb_set_kernel_timing(self._h, int(on)))
+
+    def last_kernel_ms(self):
+        return float(self._L.mgb_last_kernel_ms(self._h))

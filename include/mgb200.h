@@ -1,0 +1,145 @@
+/* mgb200 -- B200-native batched MiniGrid simulator: the C-ABI drop-in boundary.
+ *
+ * One shared library (libmgb200.so, built for sm_100a only) replaces the hot path
+ * of rohitrango/gym-minigrid:
+ *     MiniGridEnv.step          gym_minigrid/minigrid.py:1227-1325
+ *     gen_obs / gen_obs_grid    gym_minigrid/minigrid.py:1327-1381
+ *     Grid.slice/rotate_left/process_vis/encode/decode
+ *                               gym_minigrid/minigrid.py:439-473,571-648
+ *     reset + _gen_grid         gym_minigrid/minigrid.py:831-858 and
+ *                               envs/{empty,doorkey,fourrooms,dynamicobstacles,keycorridor}.py, roomgrid.py
+ * for a *batch* of independent environments resident in HBM.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, <0 on error; mgb_last_error() gives the
+ *     thread-local message.  Nothing throws across the boundary.
+ *   - all data pointers are DEVICE pointers unless the name ends in _host; the caller
+ *     owns them and keeps them alive until `stream` reaches the call.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls
+ *     enqueue and return immediately unless stated otherwise.
+ *   - there is no CPU fallback: without a CUDA device mgb_create fails.
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef MGB200_H
+#define MGB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGB_OBS_BYTES 147      /* 7*7*3 uint8, layout [vx][vy][c] = Grid.encode (minigrid.py:571-594) */
+#define MGB_MAX_OBSTACLES 8
+
+/* layout generators, one per reference env file on the path */
+enum {
+    MGB_GEN_EMPTY = 0,        /* envs/empty.py:30-57 */
+    MGB_GEN_DOORKEY = 1,      /* envs/doorkey.py:15-44 */
+    MGB_GEN_FOURROOMS = 2,    /* envs/fourrooms.py:19-69 */
+    MGB_GEN_DYNOBS = 3,       /* envs/dynamicobstacles.py:35-89 */
+    MGB_GEN_KEYCORRIDOR = 4   /* roomgrid.py:118-359 + envs/keycorridor.py:26-59 */
+};
+
+/* static per-env-id configuration: what the reference bakes into constructor kwargs
+ * (SURVEY.md Appendix B).  Replaces MiniGridEnv.__init__ kwargs, minigrid.py:767-778. */
+typedef struct {
+    int32_t gen;            /* MGB_GEN_* */
+    int32_t width, height;  /* grid size */
+    int32_t max_steps;
+    int32_t see_through;    /* see_through_walls: skip process_vis (minigrid.py:1344-1347) */
+    int32_t n_actions;      /* action_space.n: 7, or 3 for Dynamic-Obstacles (dynamicobstacles.py:32) */
+    int32_t n_obstacles;    /* Dynamic-Obstacles */
+    int32_t room_size;      /* RoomGrid (KeyCorridor) */
+    int32_t num_rows;       /* RoomGrid (KeyCorridor); num_cols is 3 */
+    int32_t random_start;   /* agent_start_pos=None variants (Empty-Random-*, Dynamic-Obstacles-Random-*) */
+    int32_t lava_v1;        /* 'v1' in class name => lava gives reward -1, not done (minigrid.py:1263-1266) */
+} mgb_config;
+
+typedef struct mgb_handle mgb_handle;
+
+const char *mgb_version(void);
+const char *mgb_last_error(void);
+
+/* Replaces gym.make(id) x num_envs (register.py:5-21 -> MiniGridEnv.__init__).
+ * env_id_base: global id of env 0 of this handle; the Philox stream of an env is keyed by
+ * (seed, global env id, episode), so results do not depend on how envs are sharded over GPUs.
+ * The envs are NOT reset: call mgb_reset. */
+int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t seed,
+               int64_t env_id_base, mgb_handle **out);
+int mgb_destroy(mgb_handle *h);
+int64_t mgb_num_envs(const mgb_handle *h);
+
+/* auto-reset on done (default 1).  With 0 a done env simply keeps stepping, exactly like a
+ * reference env whose caller ignores `done`. */
+int mgb_set_autoreset(mgb_handle *h, int on);
+
+/* Replaces env.seed(s) (minigrid.py:860-863): re-keys the Philox streams and rewinds the
+ * episode counters; takes effect at the next reset. */
+int mgb_seed(mgb_handle *h, uint64_t seed);
+
+/* Replaces MiniGridEnv.reset (minigrid.py:831-858) for envs with mask[i]!=0 (all when NULL).
+ * obs [N][147] (may be NULL), dir [N] (may be NULL). */
+int mgb_reset(mgb_handle *h, const uint8_t *mask, uint8_t *obs, uint8_t *dir, void *stream);
+
+/* Replaces MiniGridEnv.step + subclass hooks + gen_obs (minigrid.py:1227-1381) for all N envs.
+ * actions [N]; obs [N][147]; reward [N] fp64 (0.0, -1.0 or 1-0.9*(step_count/max_steps) with
+ * the reference's three roundings); done [N]; dir [N].  With auto-reset, obs/dir of a done env
+ * are those of the first observation of its next episode. */
+int mgb_step(mgb_handle *h, const uint8_t *actions, uint8_t *obs, double *reward,
+             uint8_t *done, uint8_t *dir, void *stream);
+
+/* T consecutive steps in ONE persistent kernel; env state stays in shared memory between steps.
+ * actions [T][N]; obs [T][N][147]; reward/done/dir [T][N].  Any output may be NULL (not written). */
+int mgb_rollout(mgb_handle *h, int32_t T, const uint8_t *actions, uint8_t *obs, double *reward,
+                uint8_t *done, uint8_t *dir, void *stream);
+
+/* One step with HOST buffers (pinned memory recommended): H2D of actions, the step kernel and
+ * D2H of obs/reward/done/dir are pipelined over internal streams in env chunks.  Synchronous:
+ * returns when the outputs are in host memory.  This is the end-to-end path a CPU-side caller
+ * of env.step() sees. */
+int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host,
+                  double *reward_host, uint8_t *done_host, uint8_t *dir_host);
+
+/* State exchange in the reference's own encoding (Grid.encode, minigrid.py:571-594):
+ *   grid      [count][W][H][3]   (type, colour, state)
+ *   aux       [count][W][H]      bit0 = Goal.overlap (minigrid.py:160) -- hidden attribute
+ *   agent     [count][4] int32   x, y, dir, step_count
+ *   carrying  [count][3]         (0,0,0) = nothing
+ *   obstacles [count][8][2] int16 obstacle list in reference order (dynamicobstacles.py:53-56)
+ *   target    [count][2]         (type, colour) of KeyCorridor.obj (keycorridor.py:48)
+ *   rng       [count][2] uint32  (#resets so far, draws consumed in the current episode)
+ * Any pointer may be NULL (left unchanged / not written).  This is also the checkpoint format. */
+int mgb_set_state(mgb_handle *h, int64_t first, int64_t count, const uint8_t *grid,
+                  const uint8_t *aux, const int32_t *agent, const uint8_t *carrying,
+                  const int16_t *obstacles, const uint8_t *target, const uint32_t *rng, void *stream);
+int mgb_get_state(mgb_handle *h, int64_t first, int64_t count, uint8_t *grid, uint8_t *aux,
+                  int32_t *agent, uint8_t *carrying, int16_t *obstacles, uint8_t *target,
+                  uint32_t *rng, void *stream);
+
+/* RNG-tape parity mode: env i consumes draws[offsets[i] ...) in order instead of Philox
+ * (values are final randint results).  NULL switches back to Philox.  Device pointers,
+ * offsets has N+1 entries. */
+int mgb_set_rng_tape(mgb_handle *h, const int32_t *draws, const int64_t *offsets);
+
+/* FullyObsWrapper.observation (wrappers.py:311-338): full grid encode with the agent cell set
+ * to (10, 0, dir).  out [N][W][H][3]. */
+int mgb_full_obs(mgb_handle *h, uint8_t *out, void *stream);
+
+/* Synchronises `stream` and returns the sticky device error flags (then clears them):
+ *   1 unknown action (reference: assert False, minigrid.py:1316-1318)   2 RNG tape exhausted
+ *   4 tape value outside [low,high)    8 rejection sampling gave up (RecursionError in reset)
+ *  16 agent/cell index out of bounds   32 unsupported cell code in set_state */
+int mgb_error_flags(mgb_handle *h, void *stream, uint32_t *flags_host);
+
+/* number of kernels this handle has launched so far */
+int64_t mgb_kernel_launches(const mgb_handle *h);
+
+/* duration in ms of the most recent mgb_step/mgb_rollout kernel, measured with CUDA events on
+ * the launching stream (blocks until that kernel has finished); <0 if timing is disabled. */
+int mgb_set_kernel_timing(mgb_handle *h, int on);
+double mgb_last_kernel_ms(mgb_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -293,5 +293,25 @@ def main():
               dn, rw, time.time() - t0), flush=True)
 
 
+def reward_table():
+    """_reward() (minigrid.py:933-937) evaluated BY THE REFERENCE for every step_count of every
+    max_steps in the registry (and 50 beyond): r_<max_steps>[k] = reward at step_count == k."""
+    d = {}
+    for env_id in [h[0] for h in HEADLINE] + VARIANTS:
+        env = R.make(env_id).unwrapped
+        ms = env.max_steps
+        if "r_%d" % ms in d:
+            continue
+        out = np.zeros(ms + 51, np.float64)
+        for k in range(ms + 51):
+            env.step_count = k
+            out[k] = env._reward()
+        d["r_%d" % ms] = out
+    np.savez_compressed(os.path.join(OUT, "reward_table.npz"), **d)
+    print("reward_table.npz", sorted(d.keys()))
+
+
 if __name__ == "__main__":
-    main()
+    if "--reward-table-only" not in sys.argv:
+        main()
+    reward_table()

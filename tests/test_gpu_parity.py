@@ -1,0 +1,282 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI
+(gym_minigrid_b200 -> ctypes -> libmgb200.so); the CPU oracle and the committed golden traces of
+the live reference are only the checkers.  Integer/byte outputs must be bit-exact; rewards are
+compared as fp64 bit patterns (tolerance: 0 ulp)."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_same, bits, golden_files, load
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+HEADLINE = ["MiniGrid-Empty-8x8-v0", "MiniGrid-DoorKey-16x16-v0", "MiniGrid-FourRooms-v0",
+            "MiniGrid-Dynamic-Obstacles-16x16-v0", "MiniGrid-KeyCorridorS6R3-v0"]
+
+
+def _mgb():
+    import gym_minigrid_b200 as mgb
+    return mgb
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _oracle_cfg(env_id):
+    cfg = dict(_mgb().spec(env_id)["config"])
+    cfg.pop("mission", None)
+    cfg.pop("reward_range", None)
+    return cfg
+
+
+def _check_trace_gpu(d, k, mode):
+    mgb = _mgb()
+    T = d["actions"].shape[1]
+    env = mgb.make(d["env_id"], num_envs=1, seed=int(d["seed"]), env_id_base=int(d["env_indices"][k]))
+    # the product's own config table must agree with what the reference env reported
+    for key, val in d["cfg"].items():
+        assert int(env._cfg[key]) == val, (key, env._cfg[key], val)
+    if mode == "tape":
+        lo, hi = int(d["tape_offsets"][k]), int(d["tape_offsets"][k + 1])
+        env.set_rng_tape(d["tape"][lo:hi], np.array([0, hi - lo]))
+    tag = "%s[%d]" % (os.path.basename(d["path"]), k)
+    obs = env.reset()
+    assert_same(tag + " obs0", _np(obs["image"])[0], d["obs0"][k])
+    assert int(obs["direction"][0]) == int(d["dir0"][k])
+    assert obs["mission"][0] == str(d["missions0"][k])
+    s = env.get_state()
+    assert_same(tag + " grid0", _np(s["grid"])[0], d["grid0"][k])
+    assert_same(tag + " agent0", _np(s["agent"])[0], d["agent0"][k])
+    t0 = 0
+    nob = d["cfg"]["n_obstacles"]
+    for si, ts in enumerate(d["snap_t"][k]):
+        a = torch.as_tensor(d["actions"][k, t0:ts + 1].reshape(-1, 1))
+        if si % 2 == 0:      # alternate the persistent rollout kernel and single-step launches
+            o, r, dn, dr = env.rollout(a)
+            o, r, dn, dr = _np(o)[:, 0], _np(r)[:, 0], _np(dn)[:, 0], _np(dr)[:, 0]
+        else:
+            o, r, dn, dr = [], [], [], []
+            for t in range(a.shape[0]):
+                ob, rr, dd, _ = env.step(a[t])
+                o.append(_np(ob["image"])[0].copy()); r.append(float(rr[0])); dn.append(bool(dd[0])); dr.append(int(ob["direction"][0]))
+            o, r, dn, dr = np.stack(o), np.array(r), np.array(dn), np.array(dr, np.uint8)
+        assert_same(tag + " done", dn.astype(np.uint8), d["done"][k, t0:ts + 1])
+        assert_same(tag + " obs", o, d["obs"][k, t0:ts + 1])
+        assert_same(tag + " dir", dr, d["dir"][k, t0:ts + 1])
+        assert_same(tag + " reward bits", bits(r), bits(d["reward"][k, t0:ts + 1]))
+        s = env.get_state()
+        assert_same(tag + " snap_grid@%d" % ts, _np(s["grid"])[0], d["snap_grid"][k, si])
+        assert_same(tag + " snap_agent@%d" % ts, _np(s["agent"])[0], d["snap_agent"][k, si])
+        assert_same(tag + " snap_carrying@%d" % ts, _np(s["carrying"])[0], d["snap_carrying"][k, si])
+        assert_same(tag + " snap_obst@%d" % ts, _np(s["obstacles"])[0, :nob], d["snap_obst"][k, si, :nob])
+        assert_same(tag + " snap_target@%d" % ts, _np(s["target"])[0], d["snap_target"][k, si])
+        t0 = ts + 1
+    assert t0 == T
+    env.check_errors()
+    env.close()
+
+
+@pytest.mark.parametrize("path", golden_files("philox_"), ids=os.path.basename)
+def test_cuda_matches_reference_philox(path):
+    d = load(path)
+    d["path"] = path
+    for k in range(d["actions"].shape[0]):
+        _check_trace_gpu(d, k, "philox")
+
+
+@pytest.mark.parametrize("path", golden_files("tape_"), ids=os.path.basename)
+def test_cuda_matches_reference_tape(path):
+    d = load(path)
+    d["path"] = path
+    for k in range(d["actions"].shape[0]):
+        _check_trace_gpu(d, k, "tape")
+
+
+@pytest.mark.parametrize("path", golden_files("scenes_"), ids=os.path.basename)
+def test_cuda_matches_reference_scenes(path):
+    """uploaded object soups (doors in all states, boxes, terminal goals, lava, carried objects,
+    agents hugging every border), stepped without reset -- all envs of a file in ONE batch."""
+    mgb = _mgb()
+    d = load(path)
+    n, T = d["actions"].shape
+    env = mgb.make(d["env_id"], num_envs=n, autoreset=False)
+    env.set_state(dict(grid=d["grid0"], aux=d["aux0"], agent=d["agent0"], carrying=d["carrying0"]))
+    tag = os.path.basename(path)
+    obs0 = env.reset(mask=np.zeros(n, np.uint8))          # observe without resetting anything
+    assert_same(tag + " obs0", _np(obs0["image"]), d["obs0"])
+    o, r, dn, dr = env.rollout(torch.as_tensor(d["actions"].T.copy()))
+    assert_same(tag + " obs", _np(o).transpose(1, 0, 2, 3, 4), d["obs"])
+    assert_same(tag + " dir", _np(dr).T, d["dir"])
+    assert_same(tag + " done", _np(dn).T.astype(np.uint8), d["done"])
+    assert_same(tag + " reward bits", bits(_np(r).T.copy()), bits(d["reward"]))
+    s = env.get_state()
+    assert_same(tag + " grid1", _np(s["grid"]), d["grid1"])
+    assert_same(tag + " aux1", _np(s["aux"]), d["aux1"])
+    assert_same(tag + " agent1", _np(s["agent"]), d["agent1"])
+    assert_same(tag + " carrying1", _np(s["carrying"]), d["carrying1"])
+    env.check_errors()
+
+
+@pytest.mark.parametrize("env_id", HEADLINE + ["MiniGrid-DoorKey-5x5-v0", "MiniGrid-Dynamic-Obstacles-Random-6x6-v0",
+                                               "MiniGrid-KeyCorridorS3R3-v0", "MiniGrid-Empty-Random-6x6-v0"])
+def test_cuda_matches_oracle_batch(env_id):
+    """thousands of envs (ragged tail group included), auto-reset on, TMA store path,
+    against the oracle on the same seeded inputs; then the full state."""
+    from oracle.oracle import OracleVec
+    mgb = _mgb()
+    cfg = _oracle_cfg(env_id)
+    N, T, seed, base = 2048 + 32 * 3 + 7, 160, 99, 1000003
+    rs = np.random.RandomState(5)
+    actions = rs.randint(0, cfg["n_actions"], size=(T, N)).astype(np.uint8)
+    env = mgb.make(env_id, num_envs=N, seed=seed, env_id_base=base)
+    orc = OracleVec(cfg, N, seed=seed, env0=base)
+    o0 = env.reset()
+    ro0, rd0 = orc.reset()
+    assert_same(env_id + " reset obs", _np(o0["image"]), ro0)
+    assert_same(env_id + " reset dir", _np(o0["direction"]), rd0)
+    half = T // 2
+    got = [env.rollout(torch.as_tensor(actions[:half]))]
+    # second half through T single-step launches
+    obs_l, r_l, d_l, dir_l = [], [], [], []
+    for t in range(half, T):
+        ob, r, dn, _ = env.step(torch.as_tensor(actions[t]))
+        obs_l.append(_np(ob["image"]).copy()); r_l.append(_np(r).copy()); d_l.append(_np(dn).copy()); dir_l.append(_np(ob["direction"]).copy())
+    want = orc.rollout(actions, autoreset=True)
+    o, r, dn, dr = got[0]
+    o = np.concatenate([_np(o), np.stack(obs_l)]); r = np.concatenate([_np(r), np.stack(r_l)])
+    dn = np.concatenate([_np(dn), np.stack(d_l)]); dr = np.concatenate([_np(dr), np.stack(dir_l)])
+    assert_same(env_id + " done", dn.astype(np.uint8), want[2])
+    assert_same(env_id + " obs", o, want[0])
+    assert_same(env_id + " dir", dr, want[3])
+    assert_same(env_id + " reward bits", bits(r), bits(want[1]))
+    s, so = env.get_state(), orc.get_state()
+    for key in ("grid", "aux", "agent", "carrying", "target"):
+        assert_same(env_id + " state." + key, _np(s[key]), so[key])
+    nob = cfg["n_obstacles"]
+    assert_same(env_id + " state.obstacles", _np(s["obstacles"])[:, :nob], so["obstacles"][:, :nob])
+    assert_same(env_id + " state.rng", _np(s["rng"]).view(np.uint32), so["rng"])
+    env.check_errors()
+
+
+def test_reward_formula_every_step_count():
+    """_reward() = 1 - 0.9*(step_count/max_steps) for EVERY step count of every max_steps in the
+    registry, against the values the reference itself computed (tests/golden/reward_table.npz)."""
+    mgb = _mgb()
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reward_table.npz"))
+    for env_id in ("MiniGrid-Empty-8x8-v0", "MiniGrid-FourRooms-v0", "MiniGrid-DoorKey-16x16-v0", "MiniGrid-KeyCorridorS6R3-v0"):
+        cfg = mgb.spec(env_id)["config"]
+        ms, W, H = cfg["max_steps"], cfg["width"], cfg["height"]
+        want = z["r_%d" % ms]                      # want[k] = reward when step_count == k after the step
+        n = ms + 40                                # beyond max_steps too (stepping past done)
+        grid = np.zeros((n, W, H, 3), np.uint8)
+        grid[..., 0] = 1
+        grid[:, 0, :, :] = grid[:, W - 1, :, :] = (2, 5, 0)
+        grid[:, :, 0, :] = grid[:, :, H - 1, :] = (2, 5, 0)
+        grid[:, 2, 1, :] = (8, 1, 0)
+        aux = np.zeros((n, W, H), np.uint8)
+        aux[:, 2, 1] = 1                           # Goal(toggletimes=0): overlap=True
+        agent = np.zeros((n, 4), np.int32)
+        agent[:, 0] = 1; agent[:, 1] = 1; agent[:, 2] = 0
+        agent[:, 3] = np.arange(n)                 # step_count before the step
+        env = mgb.make(env_id, num_envs=n, autoreset=False)
+        env.set_state(dict(grid=grid, aux=aux, agent=agent))
+        _, r, dn, _ = env.step(torch.full((n,), 2, dtype=torch.uint8))
+        assert bool(dn.all())
+        assert_same(env_id + " reward bits", bits(_np(r)), bits(want[1:n + 1]))
+        env.check_errors()
+
+
+def test_step_host_matches_step():
+    mgb = _mgb()
+    N = 32 * 1100 + 5                               # > 1024 groups: the chunked 3-stream pipeline is exercised
+    a = np.random.RandomState(3).randint(0, 7, size=(6, N)).astype(np.uint8)
+    e1 = mgb.make("MiniGrid-DoorKey-8x8-v0", num_envs=N, seed=11)
+    e2 = mgb.make("MiniGrid-DoorKey-8x8-v0", num_envs=N, seed=11)
+    e1.reset(); e2.reset()
+    for t in range(a.shape[0]):
+        o1, r1, d1, _ = e1.step(torch.as_tensor(a[t]))
+        o2, r2, d2, _ = e2.step_host(torch.as_tensor(a[t]).pin_memory())
+        assert_same("obs", _np(o1["image"]), o2["image"].numpy())
+        assert_same("dir", _np(o1["direction"]), o2["direction"].numpy())
+        assert_same("reward", bits(_np(r1)), bits(r2.numpy()))
+        assert_same("done", _np(d1), d2.numpy())
+
+
+def test_sharding_invariance():
+    """(e) multi-GPU: env batches shard by global env id with no collective; two half-size handles
+    with the right env_id_base must reproduce one full-size handle exactly."""
+    mgb = _mgb()
+    N, T = 4096, 64
+    a = np.random.RandomState(8).randint(0, 3, size=(T, N)).astype(np.uint8)
+    full = mgb.make("MiniGrid-Dynamic-Obstacles-16x16-v0", num_envs=N, seed=5)
+    full.reset()
+    fo, fr, fd, fdir = full.rollout(torch.as_tensor(a))
+    for lo, hi in ((0, 1536), (1536, N)):
+        part = mgb.make("MiniGrid-Dynamic-Obstacles-16x16-v0", num_envs=hi - lo, seed=5, env_id_base=lo)
+        part.reset()
+        po, pr, pd, pdir = part.rollout(torch.as_tensor(a[:, lo:hi].copy()))
+        assert torch.equal(po, fo[:, lo:hi]) and torch.equal(pd, fd[:, lo:hi])
+        assert torch.equal(pr.view(torch.int64), fr[:, lo:hi].contiguous().view(torch.int64))
+        assert torch.equal(pdir, fdir[:, lo:hi])
+
+
+def test_full_obs_and_invalid_action_flag():
+    mgb = _mgb()
+    env = mgb.make("MiniGrid-Empty-8x8-v0", num_envs=40)
+    env.reset()
+    f = _np(env.full_obs())
+    s = env.get_state()
+    g = _np(s["grid"]).copy()
+    ag = _np(s["agent"])
+    for i in range(40):
+        g[i, ag[i, 0], ag[i, 1]] = (10, 0, ag[i, 2])      # wrappers.py:327-333
+    assert_same("full_obs", f, g)
+    env.step(torch.full((40,), 7, dtype=torch.uint8))      # reference: assert False, "unknown action"
+    with pytest.raises(Exception, match="unknown action"):
+        env.check_errors()
+    env.check_errors()                                       # flags are cleared once reported
+
+
+def test_seed_reproducible_and_reseed():
+    mgb = _mgb()
+    a = torch.as_tensor(np.random.RandomState(1).randint(0, 7, size=(50, 300)).astype(np.uint8))
+    outs = []
+    for _ in range(2):
+        env = mgb.make("MiniGrid-FourRooms-v0", num_envs=300, seed=42)
+        env.reset()
+        outs.append(env.rollout(a)[0])
+    assert torch.equal(outs[0], outs[1])
+    env.seed(42)
+    env.reset()
+    assert torch.equal(env.rollout(a)[0], outs[0])
+    env.seed(43)
+    env.reset()
+    assert not torch.equal(env.rollout(a)[0], outs[0])
+
+
+def test_full_size_invariants():
+    """BASELINE-size batch (2^20 envs): properties that need no oracle (run_tests.py:48-62 invariants):
+    agent stays in bounds, the cell under the agent is empty-or-carried, rewards in range, the image
+    only contains valid codes, and two launches with different step partitioning agree bit for bit."""
+    mgb = _mgb()
+    N, T = 1 << 20, 8
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    a = torch.randint(0, 7, (T, N), dtype=torch.uint8, device="cuda", generator=g)
+    env = mgb.make("MiniGrid-Empty-8x8-v0", num_envs=N, seed=0)
+    env.reset()
+    o, r, d, dr = env.rollout(a)
+    env2 = mgb.make("MiniGrid-Empty-8x8-v0", num_envs=N, seed=0)
+    env2.reset()
+    o2 = torch.stack([env2.step(a[t])[0]["image"].clone() for t in range(T)])
+    assert torch.equal(o, o2)
+    assert int(o[..., 0].max()) <= 10 and int(o[..., 1].max()) <= 6 and int(o[..., 2].max()) <= 2
+    assert bool((o[:, :, 3, 6, 0] == 1).all())               # nothing carried in Empty: agent cell shows 'empty'
+    assert float(r.min()) >= 0.0 and float(r.max()) <= 1.0
+    ag = env.get_state(("agent",))["agent"]
+    assert bool(((ag[:, 0] >= 1) & (ag[:, 0] <= 6) & (ag[:, 1] >= 1) & (ag[:, 1] <= 6)).all())
+    assert bool((ag[:, 3] == T).all())
+    env.check_errors()
