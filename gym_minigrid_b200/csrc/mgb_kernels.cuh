@@ -645,10 +645,12 @@ struct StateIO {
 };
 
 __device__ __forceinline__ int encode_cell(int t, int c, int s, int auxbits, uint32_t &err) {
-    if (t == T_UNSEEN) t = T_EMPTY;                       // both decode to None (minigrid.py:124-125)
     if (t > T_LAVA || c > 6 || s > 2) { err |= ERR_CODE; return CODE_EMPTY; }
+    // 'unseen' and 'empty' both decode to None (minigrid.py:124-125).  Written as one range test on
+    // purpose: the `if (t==0) t=1; ... if (t==1)` form made ptxas 12.9 emit VIMNMX.U16x2 with a
+    // predicate output whose sense came out inverted on sm_100a (every cell decoded as empty).
+    if (t <= T_EMPTY) return CODE_EMPTY;
     if (t != T_DOOR) s = 0;                               // WorldObj.decode ignores state for non-doors
-    if (t == T_EMPTY) return CODE_EMPTY;
     if (t == T_GOAL && (auxbits & 1)) return CODE_TGOAL0 + c;
     return code_of(t, c, s);
 }

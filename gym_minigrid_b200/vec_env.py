@@ -248,7 +248,10 @@ class VecMiniGridEnv:
             self._tape = None
             _lib.check(self._L.mgb_set_rng_tape(self._h, None, None))
             return
-        d = torch.as_tensor(np.ascontiguousarray(draws, dtype=np.int32)).to(self.device)
+        draws = np.ascontiguousarray(draws, dtype=np.int32)
+        if draws.size == 0:
+            draws = np.zeros(1, np.int32)          # Empty-8x8 draws nothing; keep the pointer non-NULL
+        d = torch.as_tensor(draws).to(self.device)
         o = torch.as_tensor(np.ascontiguousarray(offsets, dtype=np.int64)).to(self.device)
         assert o.shape == (self.num_envs + 1,)
         self._tape = (d, o)
