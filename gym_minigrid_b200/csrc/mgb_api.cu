@@ -69,10 +69,10 @@ static rollout_fn pick_kernel(const mgb_config &c) {
 }
 
 // static part of each layout (walls + fixed goal) as packed cell codes, x-major like Grid.encode
-static std::vector<uint32_t> build_template(const mgb_config &c, int GW) {
+static std::vector<uint32_t> build_template(const mgb_config &c, int GW, int HP) {
     const int W = c.width, H = c.height;
     std::vector<uint8_t> g((size_t)GW * 4, (uint8_t)CODE_EMPTY);
-    auto set = [&](int x, int y, int code) { g[(size_t)x * H + y] = (uint8_t)code; };
+    auto set = [&](int x, int y, int code) { g[(size_t)x * HP + y] = (uint8_t)code; };
     auto wall_rect = [&](int x0, int y0, int w, int h) {   // Grid.wall_rect minigrid.py:433-437
         for (int i = 0; i < w; ++i) { set(x0 + i, y0, CODE_WALL); set(x0 + i, y0 + h - 1, CODE_WALL); }
         for (int j = 0; j < h; ++j) { set(x0, y0 + j, CODE_WALL); set(x0 + w - 1, y0 + j, CODE_WALL); }
@@ -136,10 +136,11 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     d.gen = c.gen; d.W = c.width; d.H = c.height; d.max_steps = c.max_steps; d.see_through = c.see_through;
     d.n_actions = c.n_actions; d.n_obst = c.n_obstacles; d.room_size = c.room_size; d.num_rows = c.num_rows;
     d.random_start = c.random_start; d.lava_v1 = c.lava_v1;
-    d.GW = (c.width * c.height + 3) / 4;
+    d.HP = (c.height + 3) / 4 * 4;
+    d.GW = c.width * d.HP / 4;
     d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0);
     h->sm_count = prop.multiProcessorCount;
-    h->smem_bytes = 1024 + (size_t)WARPS_PER_BLOCK * (STAGE_BYTES + (size_t)d.S * 32 * 4);
+    h->smem_bytes = 1024 + (size_t)WARPS_PER_BLOCK * (STAGE_BYTES + (size_t)(d.S + 1) * 32 * 4);
 
     auto cleanup = [&](int rc) { mgb_destroy(h); return rc; };
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess)
@@ -149,7 +150,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     const size_t state_bytes = (size_t)h->n_groups * d.S * 32 * 4;
     if (cudaMalloc(&h->state, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: cudaMalloc(%zu) for env state failed", state_bytes));
     if (cudaMemset(h->state, 0, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: memset failed"));
-    std::vector<uint32_t> t = build_template(c, d.GW);
+    std::vector<uint32_t> t = build_template(c, d.GW, d.HP);
     if (cudaMalloc(&h->tmpl, t.size() * 4) != cudaSuccess || cudaMemcpy(h->tmpl, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
         return cleanup(fail("mgb_create: template upload failed"));
     if (cudaMalloc(&h->err, 4) != cudaSuccess || cudaMemset(h->err, 0, 4) != cudaSuccess) return cleanup(fail("mgb_create: err flag alloc failed"));

@@ -72,7 +72,8 @@ __host__ __device__ inline uint32_t lut_entry(int code) {
 
 struct DevCfg {
     int32_t gen, W, H, max_steps, see_through, n_actions, n_obst, room_size, num_rows, random_start, lava_v1;
-    int32_t GW;   // grid words per env = ceil(W*H/4)
+    int32_t HP;   // grid column pitch in cells: H rounded up to a multiple of 4 (one column = HP/4 words)
+    int32_t GW;   // grid words per env = W*HP/4; cell (x,y) = byte (y&3) of word x*HP/4 + (y>>2)
     int32_t S;    // state words per env
 };
 
@@ -167,7 +168,7 @@ constexpr int HARD_TRY_CAP = 1 << 16;   // the reference would spin forever; we 
 __device__ __forceinline__ bool place_obj(Env &e, Rng &rg, const RolloutParams &p, int code, int topx, int topy,
                                           int sx, int sy, bool reject_next_to, int max_tries,
                                           bool check_agent, int &ox, int &oy) {
-    const int W = p.cfg.W, H = p.cfg.H;
+    const int W = p.cfg.W, H = p.cfg.H, HP = p.cfg.HP;
     topx = max(topx, 0); topy = max(topy, 0);
     const int hx = min(topx + sx, W), hy = min(topy + sy, H);
     int tries = 0, x, y;
@@ -177,12 +178,12 @@ __device__ __forceinline__ bool place_obj(Env &e, Rng &rg, const RolloutParams &
         x = rand_int(rg, p, topx, hx);
         y = rand_int(rg, p, topy, hy);
         if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) return false;
-        if (cell_rd(e.st, x * H + y) != CODE_EMPTY) continue;
+        if (cell_rd(e.st, x * HP + y) != CODE_EMPTY) continue;
         if (check_agent && x == e.ax && y == e.ay) continue;
         if (reject_next_to && (abs(e.ax - x) + abs(e.ay - y) < 2)) continue;   // roomgrid.py:3-12
         break;
     }
-    if (code != CODE_EMPTY) { cell_wr(e.st, x * H + y, (uint32_t)code); e.dirty = true; }
+    if (code != CODE_EMPTY) { cell_wr(e.st, x * HP + y, (uint32_t)code); e.dirty = true; }
     ox = x; oy = y;
     return true;
 }
@@ -231,7 +232,7 @@ __device__ __forceinline__ int room_nb(int r, int k, int rows) {   // right, dow
 __device__ __forceinline__ void add_door(Env &e, const DevCfg &c, Rooms &R, int r, int k, int color, bool locked) {
     // roomgrid.py:212-246 with door_idx, colour and locked given
     R.locked[r] = locked;
-    cell_wr(e.st, R.dpx[r][k] * c.H + R.dpy[r][k], (uint32_t)code_of(T_DOOR, color, locked ? 2 : 1));
+    cell_wr(e.st, R.dpx[r][k] * c.HP + R.dpy[r][k], (uint32_t)code_of(T_DOOR, color, locked ? 2 : 1));
     R.doors[r][k] = 1;
     R.doors[room_nb(r, k, c.num_rows)][(k + 2) & 3] = 1;
 }
@@ -239,7 +240,7 @@ __device__ __forceinline__ void add_door(Env &e, const DevCfg &c, Rooms &R, int 
 template <int GEN>
 __device__ __noinline__ void generate(Env &e, Rng &rg, const RolloutParams &p) {
     const DevCfg &c = p.cfg;
-    const int W = c.W, H = c.H;
+    const int W = c.W, H = c.H, HP = c.HP;
     // Grid(width,height) + static walls/goal
     for (int k = 0; k < c.GW; ++k) e.st[k * 32] = __ldg(&p.tmpl[k]);
     e.dirty = true;
@@ -254,18 +255,18 @@ __device__ __noinline__ void generate(Env &e, Rng &rg, const RolloutParams &p) {
         else ok = place_agent(e, rg, p, 0, 0, W, H, -1);
     } else if (GEN == GEN_DOORKEY) {                     // envs/doorkey.py:15-44
         const int split = rand_int(rg, p, 2, W - 2);
-        for (int j = 0; j < H; ++j) cell_wr(e.st, split * H + j, CODE_WALL);
+        for (int j = 0; j < H; ++j) cell_wr(e.st, split * HP + j, CODE_WALL);
         ok = place_agent(e, rg, p, 0, 0, split, H, -1);
         const int door = rand_int(rg, p, 1, W - 2);
-        cell_wr(e.st, split * H + door, code_of(T_DOOR, C_YELLOW, 2));
+        cell_wr(e.st, split * HP + door, code_of(T_DOOR, C_YELLOW, 2));
         ok = ok && place_obj(e, rg, p, code_of(T_KEY, C_YELLOW, 0), 0, 0, split, H, false, -1, true, x, y);
     } else if (GEN == GEN_FOURROOMS) {                   // envs/fourrooms.py:19-69
         const int rw = W / 2, rh = H / 2;
         // walls are in the template; gaps in reference draw order (j,i) = (0,0),(0,1),(1,0)
-        const int g1 = rand_int(rg, p, 1, rh);            cell_wr(e.st, rw * H + g1, CODE_EMPTY);
-        const int g2 = rand_int(rg, p, 1, rw);            cell_wr(e.st, g2 * H + rh, CODE_EMPTY);
-        const int g3 = rand_int(rg, p, rw + 1, 2 * rw);   cell_wr(e.st, g3 * H + rh, CODE_EMPTY);
-        const int g4 = rand_int(rg, p, rh + 1, 2 * rh);   cell_wr(e.st, rw * H + g4, CODE_EMPTY);
+        const int g1 = rand_int(rg, p, 1, rh);            cell_wr(e.st, rw * HP + g1, CODE_EMPTY);
+        const int g2 = rand_int(rg, p, 1, rw);            cell_wr(e.st, g2 * HP + rh, CODE_EMPTY);
+        const int g3 = rand_int(rg, p, rw + 1, 2 * rw);   cell_wr(e.st, g3 * HP + rh, CODE_EMPTY);
+        const int g4 = rand_int(rg, p, rh + 1, 2 * rh);   cell_wr(e.st, rw * HP + g4, CODE_EMPTY);
         ok = place_agent(e, rg, p, 0, 0, W, H, -1);
         ok = ok && place_obj(e, rg, p, CODE_GOAL, 0, 0, W, H, false, -1, true, x, y);
     } else if (GEN == GEN_DYNOBS) {                      // envs/dynamicobstacles.py:35-58
@@ -295,7 +296,7 @@ __device__ __noinline__ void generate(Env &e, Rng &rg, const RolloutParams &p) {
         // remove_wall(1, j, 3) (roomgrid.py:248-282)
         for (int j = 1; j < rows; ++j) {
             const int r = j * 3 + 1, tx = rs - 1, ty = j * (rs - 1);
-            for (int m = 1; m < rs - 1; ++m) cell_wr(e.st, (tx + m) * H + ty, CODE_EMPTY);
+            for (int m = 1; m < rs - 1; ++m) cell_wr(e.st, (tx + m) * HP + ty, CODE_EMPTY);
             R.doors[r][3] = 1; R.doors[r - 3][1] = 1;
         }
         const int room_idx = rand_int(rg, p, 0, rows);
@@ -310,7 +311,7 @@ __device__ __noinline__ void generate(Env &e, Rng &rg, const RolloutParams &p) {
             ok = place_agent(e, rg, p, rs - 1, (rows / 2) * (rs - 1), rs, rs, 1000);
             if (!ok) break;
             const int dx = (e.dir & 1) ? 0 : 1 - e.dir, dy = (e.dir & 1) ? 2 - e.dir : 0;
-            const uint32_t f = cell_rd(e.st, (e.ax + dx) * H + (e.ay + dy));
+            const uint32_t f = cell_rd(e.st, (e.ax + dx) * HP + (e.ay + dy));
             if (f == CODE_EMPTY || f / 21 == T_WALL) break;
         }
         // connect_all (roomgrid.py:305-359)
@@ -357,7 +358,7 @@ template <int GEN>
 __device__ __forceinline__ void transition(Env &e, Rng &rg, const RolloutParams &p, const uint32_t *lut, int action,
                                            double &reward, bool &done) {
     const DevCfg &c = p.cfg;
-    const int W = c.W, H = c.H;
+    const int W = c.W, H = c.H, HP = c.HP;
     reward = 0.0; done = false;
     bool not_clear = false;
     if (GEN == GEN_DYNOBS) {                             // envs/dynamicobstacles.py:60-78
@@ -365,15 +366,15 @@ __device__ __forceinline__ void transition(Env &e, Rng &rg, const RolloutParams 
         const int dx0 = (e.dir & 1) ? 0 : 1 - e.dir, dy0 = (e.dir & 1) ? 2 - e.dir : 0;
         const int fx0 = e.ax + dx0, fy0 = e.ay + dy0;
         uint32_t front = CODE_WALL;
-        if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(e.st, fx0 * H + fy0);
+        if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(e.st, fx0 * HP + fy0);
         not_clear = front != CODE_EMPTY && (lut[front] & 0xFF) != T_GOAL;
         for (int k = 0; k < c.n_obst; ++k) {
             int ox, oy, nx, ny;
             obst_get(e, c, k, ox, oy);
-            const uint32_t ball = cell_rd(e.st, ox * H + oy);
+            const uint32_t ball = cell_rd(e.st, ox * HP + oy);
             if (place_obj(e, rg, p, (int)ball, ox - 1, oy - 1, 3, 3, false, 100, true, nx, ny)) {
                 obst_set(e, c, k, nx, ny);
-                cell_wr(e.st, ox * H + oy, CODE_EMPTY);
+                cell_wr(e.st, ox * HP + oy, CODE_EMPTY);
             }
         }
     } else if (action >= c.n_actions) {
@@ -384,7 +385,7 @@ __device__ __forceinline__ void transition(Env &e, Rng &rg, const RolloutParams 
     const int dx = (e.dir & 1) ? 0 : 1 - e.dir, dy = (e.dir & 1) ? 2 - e.dir : 0;
     const int fx = e.ax + dx, fy = e.ay + dy;
     uint32_t fc = CODE_WALL;
-    const int fidx = fx * H + fy;
+    const int fidx = fx * HP + fy;
     const bool f_in = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
     if (f_in) fc = cell_rd(e.st, fidx); else rg.err |= ERR_BOUNDS;
     const uint32_t fw = lut[fc];
@@ -442,66 +443,123 @@ __device__ __forceinline__ void put3(int sh, uint32_t &a, uint32_t &b, uint32_t 
     else { a = __byte_perm(a, x, 0x4210); b = __byte_perm(b, x, 0x3265); }
 }
 
+// Shared-memory byte offset (relative to the lane's column) of grid cell coordinate v along x
+// (isx) or along y; out-of-grid coordinates map to `wall`, the offset of a pad word that holds
+// CODE_WALL: the offset of cell (x,y) is offx(x) + offy(y), any out-of-grid sum is >= wall and
+// one min() clamps it onto the pad -- no per-cell bounds test (minigrid.py:465-469).
+__device__ __forceinline__ int axis_off(int v, int ma, int mb, int bound, int wall) {
+    const int off = v * ma + (v >> 2) * mb;
+    return ((unsigned)v < (unsigned)bound) ? off : wall;
+}
+
+// realign + store one 32-bit word of the 147-byte record (see observe)
+struct Stitch {
+    uint32_t prev, first, w36, w37;
+};
+
 template <bool SEE>
 __device__ __forceinline__ void observe(const Env &e, const DevCfg &c, const uint32_t *lut,
                                         uint32_t *stage_w, int lane) {
-    const int W = c.W, H = c.H;
-    const int dx = (e.dir & 1) ? 0 : 1 - e.dir, dy = (e.dir & 1) ? 2 - e.dir : 0;
-    const int rx = -dy, ry = dx;
-    uint32_t acc[38];
+    const uint8_t *sb = reinterpret_cast<const uint8_t *>(e.st);
+    const int odd = e.dir & 1;
+    const int sgn = 1 - (e.dir & 2);                 // +1 for dir 0/1, -1 for dir 2/3
+    const int wall = c.S * 128;                       // pad word (index S of the smem column)
+    const int colstride = c.HP * 32;                  // bytes between grid columns: (HP/4 words) * 128
+    // world(vx,vy) = agent + d*(6-vy) + r*(vx-3), d = DIR_TO_VEC[dir], r = (-d.y, d.x)   
+    //   even dir: x = ax + sgn*(6-vy) (rows)    y = ay + sgn*(vx-3) (columns)
+    //   odd  dir: x = ax - sgn*(vx-3) (columns) y = ay + sgn*(6-vy) (rows)
+    // coordinate -> offset is x*colstride for x and (y>>2)*128 + (y&3) = y + (y>>2)*124 for y
+    const int pma = odd ? colstride : 1, pmb = odd ? 0 : 124, pbound = odd ? c.W : c.H;
+    const int qma = odd ? 1 : colstride, qmb = odd ? 124 : 0, qbound = odd ? c.H : c.W;
+    const int p0 = odd ? e.ax + 3 * sgn : e.ay - 3 * sgn, pstep = odd ? -sgn : sgn;
+    const int q6 = odd ? e.ay : e.ax;                 // row vy = 6 is the agent's own row
+    int P[VIEW], Q[VIEW];
 #pragma unroll
-    for (int i = 0; i < 38; ++i) acc[i] = 0;
-    uint32_t rowvis = 1u << 3;                              // mask[(3,6)] = True (minigrid.py:619)
-    const int dstep = rx * H + ry;
-#pragma unroll
-    for (int vy = VIEW - 1; vy >= 0; --vy) {
-        // world(vx,vy) = agent + d*(6-vy) + r*(vx-3)      
-        int wx = e.ax + dx * (6 - vy) - 3 * rx, wy = e.ay + dy * (6 - vy) - 3 * ry;
-        int idx = wx * H + wy;
-        uint32_t xs[VIEW];
-        uint32_t opaque = 0;
-#pragma unroll
-        for (int vx = 0; vx < VIEW; ++vx) {
-            uint32_t code = CODE_WALL;
-            if ((unsigned)wx < (unsigned)W && (unsigned)wy < (unsigned)H) code = cell_rd(e.st, idx);
-            const uint32_t x = lut[code];
-            xs[vx] = x;
-            if (!SEE) opaque |= ((x >> 24) & 1u) << vx;
-            wx += rx; wy += ry; idx += dstep;
-        }
-        uint32_t vis = 0x7F;
-        if (!SEE) {
-            const uint32_t t = ~opaque & 0x7Fu;
-            const uint32_t f = flood_up(rowvis, t);                       // forward sweep i = 0..5
-            vis = rev7(flood_up(rev7(f), rev7(t)));                        // reverse sweep i = 6..1
-            const uint32_t s = vis & t;
-            rowvis = (s | (s << 1) | (s >> 1)) & 0x7Fu;                    // seeds of row vy-1
-        }
-        if (vy == VIEW - 1) xs[3] = e.carry ? lut[e.carry] : (uint32_t)T_EMPTY;   // minigrid.py:1349-1356
-#pragma unroll
-        for (int vx = 0; vx < VIEW; ++vx) {
-            uint32_t x = xs[vx];
-            if (!SEE) x = ((vis >> vx) & 1u) ? x : 0u;
-            const int b = 3 * (vx * VIEW + vy);
-            put3(b & 3, acc[b >> 2], acc[(b >> 2) + 1], x);
-        }
+    for (int k = 0; k < VIEW; ++k) {
+        P[k] = axis_off(p0 + k * pstep, pma, pmb, pbound, wall);
+        Q[k] = axis_off(q6 + (6 - k) * sgn, qma, qmb, qbound, wall);
     }
-    acc[36] &= 0x00FFFFFFu;
-    acc[37] = 0;
-    // realign the 147-byte record to its byte offset lane*147 inside the warp's 4704-byte block
+    const uint32_t own = e.carry ? lut[e.carry] : (uint32_t)T_EMPTY;   // minigrid.py:1349-1356
+
+    // realignment of the record to byte offset lane*147 of the warp's 4704-byte block
     const int boff = lane * OBS_BYTES;
     const int q = boff >> 2;
     const uint32_t s8 = (boff & 3) * 8;
-    uint32_t prev = 0;
     uint32_t first = 0, w36 = 0, w37 = 0;
+
+    if (SEE) {
+        // no occlusion: stream cells in output order (vx-major), 4 cells -> 3 words, realign on the fly
+        uint32_t prev = 0;
 #pragma unroll
-    for (int j = 0; j < 38; ++j) {
-        const uint32_t o = __funnelshift_l(prev, acc[j], s8);
-        prev = acc[j];
-        if (j == 0) first = o;
-        else if (j < 36) stage_w[q + j] = o;
-        else if (j == 36) w36 = o;
-        else w37 = o;
+        for (int g = 0; g < 13; ++g) {
+            uint32_t x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ci = g * 4 + i;
+                x[i] = 0;
+                if (ci < VIEW * VIEW) {
+                    const int vx = ci / VIEW, vy = ci % VIEW;
+                    x[i] = (vx == 3 && vy == 6) ? own : lut[sb[min(P[vx] + Q[vy], wall)]];
+                }
+            }
+            uint32_t w[3];
+            w[0] = __byte_perm(x[0], x[1], 0x4210);        // x0.b0 x0.b1 x0.b2 x1.b0
+            w[1] = __byte_perm(x[1], x[2], 0x5421);        // x1.b1 x1.b2 x2.b0 x2.b1
+            w[2] = __byte_perm(x[2], x[3], 0x6542);        // x2.b2 x3.b0 x3.b1 x3.b2
+            if (g == 12) w[0] &= 0x00FFFFFFu;              // cell 48 is the last; byte 147 does not exist
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const int j = g * 3 + i;
+                if (j > 37) continue;
+                const uint32_t a = (j <= 36) ? w[i] : 0u;
+                const uint32_t o = __funnelshift_l(prev, a, s8);
+                prev = a;
+                if (j == 0) first = o;
+                else if (j < 36) stage_w[q + j] = o;
+                else if (j == 36) w36 = o;
+                else w37 = o;
+            }
+        }
+    } else {
+        uint32_t acc[38];
+#pragma unroll
+        for (int i = 0; i < 38; ++i) acc[i] = 0;
+        uint32_t rowvis = 1u << 3;                          // mask[(3,6)] = True (minigrid.py:619)
+#pragma unroll
+        for (int vy = VIEW - 1; vy >= 0; --vy) {
+            uint32_t xs[VIEW];
+            uint32_t opaque = 0;
+#pragma unroll
+            for (int vx = 0; vx < VIEW; ++vx) {
+                const uint32_t x = lut[sb[min(P[vx] + Q[vy], wall)]];
+                xs[vx] = x;
+                opaque |= ((x >> 24) & 1u) << vx;
+            }
+            const uint32_t t = ~opaque & 0x7Fu;
+            const uint32_t f = flood_up(rowvis, t);                       // forward sweep i = 0..5
+            const uint32_t vis = rev7(flood_up(rev7(f), rev7(t)));        // reverse sweep i = 6..1
+            const uint32_t sv = vis & t;
+            rowvis = (sv | (sv << 1) | (sv >> 1)) & 0x7Fu;                // seeds of row vy-1
+            if (vy == VIEW - 1) xs[3] = own;
+#pragma unroll
+            for (int vx = 0; vx < VIEW; ++vx) {
+                const uint32_t x = ((vis >> vx) & 1u) ? xs[vx] : 0u;
+                const int b = 3 * (vx * VIEW + vy);
+                put3(b & 3, acc[b >> 2], acc[(b >> 2) + 1], x);
+            }
+        }
+        acc[36] &= 0x00FFFFFFu;
+        acc[37] = 0;
+        uint32_t prev = 0;
+#pragma unroll
+        for (int j = 0; j < 38; ++j) {
+            const uint32_t o = __funnelshift_l(prev, acc[j], s8);
+            prev = acc[j];
+            if (j == 0) first = o;
+            else if (j < 36) stage_w[q + j] = o;
+            else if (j == 36) w36 = o;
+            else w37 = o;
+        }
     }
     // the partial last word of lane t-1 shares a 32-bit word with the head of lane t
     const uint32_t tail = (s8 >= 16) ? w37 : w36;
@@ -541,7 +599,7 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
     uint8_t *stage_base = smem_raw + 1024;
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * STAGE_BYTES);
-    uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + WARPS_PER_BLOCK * STAGE_BYTES) + warp * (c.S * 32);
+    uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + WARPS_PER_BLOCK * STAGE_BYTES) + warp * ((c.S + 1) * 32);
     for (int i = threadIdx.x; i < 256; i += THREADS) lut[i] = lut_entry(i);
     __syncthreads();
 
@@ -552,6 +610,7 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
         uint32_t *gst = p.state + (size_t)group * S * 32 + lane;
         // ---- load the group's state block: S coalesced 128-byte rows -> bank == lane ----
         for (int k = 0; k < S; ++k) st_warp[k * 32 + lane] = gst[k * 32];
+        st_warp[S * 32 + lane] = (uint32_t)CODE_WALL * 0x01010101u;        // out-of-grid pad (minigrid.py:469)
         Env e;
         Rng rg;
         e.st = st_warp + lane;
@@ -666,15 +725,17 @@ __global__ void k_set_state(const StateIO io) {
     uint32_t *dst = io.state + ((env >> 5) * c.S + k) * 32 + (env & 31);
     uint32_t err = 0;
     const int cells = c.W * c.H;
+    const int HW = c.HP >> 2;
     if (k < c.GW) {
         if (!io.grid) return;
         uint32_t w = 0;
+        const int x = k / HW, y0 = (k % HW) * 4;
         for (int b = 0; b < 4; ++b) {
-            const int idx = k * 4 + b;
             int code = CODE_EMPTY;
-            if (idx < cells) {
-                const uint8_t *g = io.grid + ((size_t)n * cells + idx) * 3;
-                code = encode_cell(g[0], g[1], g[2], io.aux ? io.aux[(size_t)n * cells + idx] : 0, err);
+            if (y0 + b < c.H) {
+                const size_t idx = (size_t)n * cells + x * c.H + y0 + b;     // Grid.encode: [x][y]
+                const uint8_t *g = io.grid + idx * 3;
+                code = encode_cell(g[0], g[1], g[2], io.aux ? io.aux[idx] : 0, err);
             }
             w |= (uint32_t)code << (8 * b);
         }
@@ -726,6 +787,7 @@ __global__ void k_get_state(const StateIO io, int full_obs) {
     const uint32_t *base = io.state + (env >> 5) * c.S * 32 + (env & 31);
     const uint32_t w = base[k * 32];
     const int cells = c.W * c.H;
+    const int HW = c.HP >> 2;
     if (k < c.GW) {
         int aidx = -1, adir = 0;
         if (full_obs) {
@@ -733,9 +795,10 @@ __global__ void k_get_state(const StateIO io, int full_obs) {
             aidx = (int)(w0 & 0xFF) * c.H + (int)((w0 >> 8) & 0xFF);
             adir = (w0 >> 16) & 3;
         }
+        const int cx = k / HW, y0 = (k % HW) * 4;
         for (int b = 0; b < 4; ++b) {
-            const int idx = k * 4 + b;
-            if (idx >= cells) break;
+            if (y0 + b >= c.H) break;
+            const int idx = cx * c.H + y0 + b;                                // Grid.encode: [x][y]
             const uint32_t x = lut_entry((w >> (8 * b)) & 0xFF);
             if (io.grid) {
                 uint8_t *g = io.grid + ((size_t)n * cells + idx) * 3;
