@@ -104,7 +104,6 @@ struct RolloutParams {
 // per-thread environment context (registers) + shared-memory column
 // ------------------------------------------------------------------------------------------
 struct Env {                    // hot: stays in registers (its address never escapes)
-    uint32_t *st;               // &state_smem[0*32 + lane]; word k at st[k*32]
     int ax, ay, dir, carry, steps, target;
     bool dirty;                 // grid words modified since load
 };
@@ -165,7 +164,7 @@ constexpr int HARD_TRY_CAP = 1 << 16;   // the reference would spin forever; we 
 
 // MiniGridEnv.place_obj (minigrid.py:1003-1061).  max_tries < 0 == math.inf.
 // check_agent: "don't place the object where the agent is" (agent_pos may be None -> false).
-__device__ __forceinline__ bool place_obj(Env &e, Rng &rg, const RolloutParams &p, int code, int topx, int topy,
+__device__ __forceinline__ bool place_obj(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, int code, int topx, int topy,
                                           int sx, int sy, bool reject_next_to, int max_tries,
                                           bool check_agent, int &ox, int &oy) {
     const int W = p.cfg.W, H = p.cfg.H, HP = p.cfg.HP;
@@ -178,21 +177,21 @@ __device__ __forceinline__ bool place_obj(Env &e, Rng &rg, const RolloutParams &
         x = rand_int(rg, p, topx, hx);
         y = rand_int(rg, p, topy, hy);
         if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) return false;
-        if (cell_rd(e.st, x * HP + y) != CODE_EMPTY) continue;
+        if (cell_rd(st, x * HP + y) != CODE_EMPTY) continue;
         if (check_agent && x == e.ax && y == e.ay) continue;
         if (reject_next_to && (abs(e.ax - x) + abs(e.ay - y) < 2)) continue;   // roomgrid.py:3-12
         break;
     }
-    if (code != CODE_EMPTY) { cell_wr(e.st, x * HP + y, (uint32_t)code); e.dirty = true; }
+    if (code != CODE_EMPTY) { cell_wr(st, x * HP + y, (uint32_t)code); e.dirty = true; }
     ox = x; oy = y;
     return true;
 }
 
 // MiniGridEnv.place_agent (minigrid.py:1072-1090)
-__device__ __forceinline__ bool place_agent(Env &e, Rng &rg, const RolloutParams &p, int topx, int topy, int sx,
+__device__ __forceinline__ bool place_agent(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, int topx, int topy, int sx,
                                             int sy, int max_tries) {
     int x, y;
-    if (!place_obj(e, rg, p, CODE_EMPTY, topx, topy, sx, sy, false, max_tries, false, x, y)) return false;
+    if (!place_obj(st, e, rg, p, CODE_EMPTY, topx, topy, sx, sy, false, max_tries, false, x, y)) return false;
     e.ax = x; e.ay = y;
     e.dir = rand_int(rg, p, 0, 4);
     return true;
@@ -205,12 +204,12 @@ __device__ __forceinline__ int rand_color(Rng &rg, const RolloutParams &p) {
 }
 
 // obstacle k = byte pair (k&1)*2 of word GW+XWORDS+(k>>1)
-__device__ __forceinline__ void obst_get(const Env &e, const DevCfg &c, int k, int &x, int &y) {
-    const uint32_t w = e.st[(c.GW + XWORDS + (k >> 1)) * 32] >> ((k & 1) * 16);
+__device__ __forceinline__ void obst_get(const uint32_t *st, const DevCfg &c, int k, int &x, int &y) {
+    const uint32_t w = st[(c.GW + XWORDS + (k >> 1)) * 32] >> ((k & 1) * 16);
     x = w & 0xFF; y = (w >> 8) & 0xFF;
 }
-__device__ __forceinline__ void obst_set(Env &e, const DevCfg &c, int k, int x, int y) {
-    uint32_t *q = &e.st[(c.GW + XWORDS + (k >> 1)) * 32];
+__device__ __forceinline__ void obst_set(uint32_t *st, const DevCfg &c, int k, int x, int y) {
+    uint32_t *q = &st[(c.GW + XWORDS + (k >> 1)) * 32];
     const int sh = (k & 1) * 16;
     *q = (*q & ~(0xFFFFu << sh)) | ((uint32_t)(x | (y << 8)) << sh);
 }
@@ -229,20 +228,20 @@ __device__ __forceinline__ int room_nb(int r, int k, int rows) {   // right, dow
     if (k == 2) return i > 0 ? r - 1 : -1;
     return j > 0 ? r - 3 : -1;
 }
-__device__ __forceinline__ void add_door(Env &e, const DevCfg &c, Rooms &R, int r, int k, int color, bool locked) {
+__device__ __forceinline__ void add_door(uint32_t *st, const DevCfg &c, Rooms &R, int r, int k, int color, bool locked) {
     // roomgrid.py:212-246 with door_idx, colour and locked given
     R.locked[r] = locked;
-    cell_wr(e.st, R.dpx[r][k] * c.HP + R.dpy[r][k], (uint32_t)code_of(T_DOOR, color, locked ? 2 : 1));
+    cell_wr(st, R.dpx[r][k] * c.HP + R.dpy[r][k], (uint32_t)code_of(T_DOOR, color, locked ? 2 : 1));
     R.doors[r][k] = 1;
     R.doors[room_nb(r, k, c.num_rows)][(k + 2) & 3] = 1;
 }
 
 template <int GEN>
-__device__ __noinline__ void generate(Env &e, Rng &rg, const RolloutParams &p) {
+__device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p) {
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP;
     // Grid(width,height) + static walls/goal
-    for (int k = 0; k < c.GW; ++k) e.st[k * 32] = __ldg(&p.tmpl[k]);
+    for (int k = 0; k < c.GW; ++k) st[k * 32] = __ldg(&p.tmpl[k]);
     e.dirty = true;
     rg.episode++;
     if (!p.tape) rg.ndraws = 0;
@@ -252,29 +251,29 @@ __device__ __noinline__ void generate(Env &e, Rng &rg, const RolloutParams &p) {
     int x, y;
     if (GEN == GEN_EMPTY) {                              // envs/empty.py:30-57 (extra == 0)
         if (!c.random_start) { e.ax = 1; e.ay = 1; e.dir = 0; }
-        else ok = place_agent(e, rg, p, 0, 0, W, H, -1);
+        else ok = place_agent(st, e, rg, p, 0, 0, W, H, -1);
     } else if (GEN == GEN_DOORKEY) {                     // envs/doorkey.py:15-44
         const int split = rand_int(rg, p, 2, W - 2);
-        for (int j = 0; j < H; ++j) cell_wr(e.st, split * HP + j, CODE_WALL);
-        ok = place_agent(e, rg, p, 0, 0, split, H, -1);
+        for (int j = 0; j < H; ++j) cell_wr(st, split * HP + j, CODE_WALL);
+        ok = place_agent(st, e, rg, p, 0, 0, split, H, -1);
         const int door = rand_int(rg, p, 1, W - 2);
-        cell_wr(e.st, split * HP + door, code_of(T_DOOR, C_YELLOW, 2));
-        ok = ok && place_obj(e, rg, p, code_of(T_KEY, C_YELLOW, 0), 0, 0, split, H, false, -1, true, x, y);
+        cell_wr(st, split * HP + door, code_of(T_DOOR, C_YELLOW, 2));
+        ok = ok && place_obj(st, e, rg, p, code_of(T_KEY, C_YELLOW, 0), 0, 0, split, H, false, -1, true, x, y);
     } else if (GEN == GEN_FOURROOMS) {                   // envs/fourrooms.py:19-69
         const int rw = W / 2, rh = H / 2;
         // walls are in the template; gaps in reference draw order (j,i) = (0,0),(0,1),(1,0)
-        const int g1 = rand_int(rg, p, 1, rh);            cell_wr(e.st, rw * HP + g1, CODE_EMPTY);
-        const int g2 = rand_int(rg, p, 1, rw);            cell_wr(e.st, g2 * HP + rh, CODE_EMPTY);
-        const int g3 = rand_int(rg, p, rw + 1, 2 * rw);   cell_wr(e.st, g3 * HP + rh, CODE_EMPTY);
-        const int g4 = rand_int(rg, p, rh + 1, 2 * rh);   cell_wr(e.st, rw * HP + g4, CODE_EMPTY);
-        ok = place_agent(e, rg, p, 0, 0, W, H, -1);
-        ok = ok && place_obj(e, rg, p, CODE_GOAL, 0, 0, W, H, false, -1, true, x, y);
+        const int g1 = rand_int(rg, p, 1, rh);            cell_wr(st, rw * HP + g1, CODE_EMPTY);
+        const int g2 = rand_int(rg, p, 1, rw);            cell_wr(st, g2 * HP + rh, CODE_EMPTY);
+        const int g3 = rand_int(rg, p, rw + 1, 2 * rw);   cell_wr(st, g3 * HP + rh, CODE_EMPTY);
+        const int g4 = rand_int(rg, p, rh + 1, 2 * rh);   cell_wr(st, rw * HP + g4, CODE_EMPTY);
+        ok = place_agent(st, e, rg, p, 0, 0, W, H, -1);
+        ok = ok && place_obj(st, e, rg, p, CODE_GOAL, 0, 0, W, H, false, -1, true, x, y);
     } else if (GEN == GEN_DYNOBS) {                      // envs/dynamicobstacles.py:35-58
         if (!c.random_start) { e.ax = 1; e.ay = 1; e.dir = 0; }
-        else ok = place_agent(e, rg, p, 0, 0, W, H, -1);
+        else ok = place_agent(st, e, rg, p, 0, 0, W, H, -1);
         for (int k = 0; k < c.n_obst; ++k) {
-            ok = place_obj(e, rg, p, code_of(T_BALL, C_BLUE, 0), 0, 0, W, H, false, 100, true, x, y) && ok;
-            obst_set(e, c, k, x, y);
+            ok = place_obj(st, e, rg, p, code_of(T_BALL, C_BLUE, 0), 0, 0, W, H, false, 100, true, x, y) && ok;
+            obst_set(st, c, k, x, y);
         }
     } else if (GEN == GEN_KEYCORRIDOR) {                 // roomgrid.py:118-169 + envs/keycorridor.py:26-49
         Rooms R;
@@ -296,22 +295,22 @@ __device__ __noinline__ void generate(Env &e, Rng &rg, const RolloutParams &p) {
         // remove_wall(1, j, 3) (roomgrid.py:248-282)
         for (int j = 1; j < rows; ++j) {
             const int r = j * 3 + 1, tx = rs - 1, ty = j * (rs - 1);
-            for (int m = 1; m < rs - 1; ++m) cell_wr(e.st, (tx + m) * HP + ty, CODE_EMPTY);
+            for (int m = 1; m < rs - 1; ++m) cell_wr(st, (tx + m) * HP + ty, CODE_EMPTY);
             R.doors[r][3] = 1; R.doors[r - 3][1] = 1;
         }
         const int room_idx = rand_int(rg, p, 0, rows);
         const int door_color = rand_color(rg, p);                     // add_door(2, room_idx, 2, locked=True)
-        add_door(e, c, R, room_idx * 3 + 2, 2, door_color, true);
+        add_door(st, c, R, room_idx * 3 + 2, 2, door_color, true);
         const int obj_color = rand_color(rg, p);                      // add_object(2, room_idx, "ball")
-        ok = place_obj(e, rg, p, code_of(T_BALL, obj_color, 0), 2 * (rs - 1), room_idx * (rs - 1), rs, rs, true, 1000, true, x, y);
+        ok = place_obj(st, e, rg, p, code_of(T_BALL, obj_color, 0), 2 * (rs - 1), room_idx * (rs - 1), rs, rs, true, 1000, true, x, y);
         const int key_room = rand_int(rg, p, 0, rows);                // add_object(0, ri, "key", door.color)
-        ok = place_obj(e, rg, p, code_of(T_KEY, door_color, 0), 0, key_room * (rs - 1), rs, rs, true, 1000, true, x, y) && ok;
+        ok = place_obj(st, e, rg, p, code_of(T_KEY, door_color, 0), 0, key_room * (rs - 1), rs, rs, true, 1000, true, x, y) && ok;
         // RoomGrid.place_agent(1, rows//2) (roomgrid.py:284-303)
         for (int guard = 0; ok && guard < HARD_TRY_CAP; ++guard) {
-            ok = place_agent(e, rg, p, rs - 1, (rows / 2) * (rs - 1), rs, rs, 1000);
+            ok = place_agent(st, e, rg, p, rs - 1, (rows / 2) * (rs - 1), rs, rs, 1000);
             if (!ok) break;
             const int dx = (e.dir & 1) ? 0 : 1 - e.dir, dy = (e.dir & 1) ? 2 - e.dir : 0;
-            const uint32_t f = cell_rd(e.st, (e.ax + dx) * HP + (e.ay + dy));
+            const uint32_t f = cell_rd(st, (e.ax + dx) * HP + (e.ay + dy));
             if (f == CODE_EMPTY || f / 21 == T_WALL) break;
         }
         // connect_all (roomgrid.py:305-359)
@@ -338,7 +337,7 @@ __device__ __noinline__ void generate(Env &e, Rng &rg, const RolloutParams &p) {
             if (!R.has[r][k] || R.doors[r][k]) continue;
             if (R.locked[r] || R.locked[room_nb(r, k, rows)]) continue;
             const int color = rand_color(rg, p);
-            add_door(e, c, R, r, k, color, false);
+            add_door(st, c, R, r, k, color, false);
         }
         e.target = code_of(T_BALL, obj_color, 0);
     }
@@ -355,7 +354,7 @@ __device__ __forceinline__ double reward_formula(int steps, int max_steps) {
 }
 
 template <int GEN>
-__device__ __forceinline__ void transition(Env &e, Rng &rg, const RolloutParams &p, const uint32_t *lut, int action,
+__device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, const uint32_t *lut, int action,
                                            double &reward, bool &done) {
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP;
@@ -366,15 +365,15 @@ __device__ __forceinline__ void transition(Env &e, Rng &rg, const RolloutParams 
         const int dx0 = (e.dir & 1) ? 0 : 1 - e.dir, dy0 = (e.dir & 1) ? 2 - e.dir : 0;
         const int fx0 = e.ax + dx0, fy0 = e.ay + dy0;
         uint32_t front = CODE_WALL;
-        if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(e.st, fx0 * HP + fy0);
+        if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(st, fx0 * HP + fy0);
         not_clear = front != CODE_EMPTY && (lut[front] & 0xFF) != T_GOAL;
         for (int k = 0; k < c.n_obst; ++k) {
             int ox, oy, nx, ny;
-            obst_get(e, c, k, ox, oy);
-            const uint32_t ball = cell_rd(e.st, ox * HP + oy);
-            if (place_obj(e, rg, p, (int)ball, ox - 1, oy - 1, 3, 3, false, 100, true, nx, ny)) {
-                obst_set(e, c, k, nx, ny);
-                cell_wr(e.st, ox * HP + oy, CODE_EMPTY);
+            obst_get(st, c, k, ox, oy);
+            const uint32_t ball = cell_rd(st, ox * HP + oy);
+            if (place_obj(st, e, rg, p, (int)ball, ox - 1, oy - 1, 3, 3, false, 100, true, nx, ny)) {
+                obst_set(st, c, k, nx, ny);
+                cell_wr(st, ox * HP + oy, CODE_EMPTY);
             }
         }
     } else if (action >= c.n_actions) {
@@ -387,35 +386,37 @@ __device__ __forceinline__ void transition(Env &e, Rng &rg, const RolloutParams 
     uint32_t fc = CODE_WALL;
     const int fidx = fx * HP + fy;
     const bool f_in = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
-    if (f_in) fc = cell_rd(e.st, fidx); else rg.err |= ERR_BOUNDS;
+    if (f_in) fc = cell_rd(st, fidx); else rg.err |= ERR_BOUNDS;
     const uint32_t fw = lut[fc];
     const uint32_t ff = fw >> 24;
     const int ftype = fw & 0xFF;
-    if (action == A_LEFT) {
-        e.dir = (e.dir + 3) & 3;
-    } else if (action == A_RIGHT) {
-        e.dir = (e.dir + 1) & 3;
-    } else if (action == A_FORWARD) {
-        if (ff & F_OVERLAP) { e.ax = fx; e.ay = fy; }
-        if (ff & F_TGOAL) { done = true; reward = reward_formula(e.steps, c.max_steps); }
-        if (ff & F_LAVA) { if (c.lava_v1) { done = false; reward = -1.0; } else done = true; }
-    } else if (action == A_PICKUP) {
-        if ((ff & F_PICKUP) && e.carry == 0 && f_in) { e.carry = (int)fc; cell_wr(e.st, fidx, CODE_EMPTY); e.dirty = true; }
-    } else if (action == A_DROP) {
-        if (fc == CODE_EMPTY && e.carry != 0 && f_in) { cell_wr(e.st, fidx, (uint32_t)e.carry); e.carry = 0; e.dirty = true; }
-    } else if (action == A_TOGGLE) {
-        if (f_in) {
-            if (ftype == T_DOOR) {                       // Door.toggle minigrid.py:252-262
-                const int s = (fw >> 16) & 0xFF, col = (fw >> 8) & 0xFF;
-                int ns = s;
-                if (s == 2) { if (e.carry == code_of(T_KEY, col, 0)) ns = 0; }
-                else ns = s ^ 1;
-                if (ns != s) { cell_wr(e.st, fidx, fc - s + ns); e.dirty = true; }
-            } else if (ftype == T_BOX || (ftype == T_GOAL && !(ff & F_TGOAL))) {
-                // default Box (contains None) and default Goal (toggletimes 1) vanish: :171-177, :355-360
-                cell_wr(e.st, fidx, CODE_EMPTY); e.dirty = true;
-            }
-        }
+    // select form of the action switch (minigrid.py:1245-1318): one rarely-taken branch for grid edits
+    const int turn = action == A_LEFT ? 3 : (action == A_RIGHT ? 1 : 0);
+    e.dir = (e.dir + turn) & 3;
+    const bool fwd = action == A_FORWARD;
+    const bool move = fwd && (ff & F_OVERLAP);
+    e.ax = move ? fx : e.ax;
+    e.ay = move ? fy : e.ay;
+    const bool goal = fwd && (ff & F_TGOAL);                  // only Goal(toggletimes<=0) terminates (:157-160,:1259)
+    const bool lava = fwd && (ff & F_LAVA);
+    done = goal || (lava && !c.lava_v1);
+    if (lava && c.lava_v1) reward = -1.0;                     // 'v1' in class name (:1263-1266)
+    if (goal) reward = reward_formula(e.steps, c.max_steps);
+    const int ds = (fw >> 16) & 0xFF, dcol = (fw >> 8) & 0xFF;
+    const int ns = (ds == 2) ? ((e.carry == code_of(T_KEY, dcol, 0)) ? 0 : 2) : (ds ^ 1);   // Door.toggle :252-262
+    const bool tog = action == A_TOGGLE && f_in;
+    const bool tog_door = tog && ftype == T_DOOR && ns != ds;
+    // default Box (contains None) and default Goal (toggletimes 1) vanish when toggled (:171-177, :355-360)
+    const bool tog_vanish = tog && (ftype == T_BOX || (ftype == T_GOAL && !(ff & F_TGOAL)));
+    const bool pick = action == A_PICKUP && (ff & F_PICKUP) && e.carry == 0 && f_in;
+    const bool drop = action == A_DROP && fc == CODE_EMPTY && e.carry != 0 && f_in;
+    if (pick || drop || tog_door || tog_vanish) {
+        uint32_t nv = CODE_EMPTY;
+        if (drop) nv = (uint32_t)e.carry;
+        if (tog_door) nv = fc - ds + ns;
+        cell_wr(st, fidx, nv);
+        e.dirty = true;
+        e.carry = pick ? (int)fc : (drop ? 0 : e.carry);
     }
     if (e.steps >= c.max_steps) done = true;
     if (GEN == GEN_KEYCORRIDOR) {                        // envs/keycorridor.py:51-59
@@ -443,6 +444,24 @@ __device__ __forceinline__ void put3(int sh, uint32_t &a, uint32_t &b, uint32_t 
     else { a = __byte_perm(a, x, 0x4210); b = __byte_perm(b, x, 0x3265); }
 }
 
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+// code -> LUT word; the address is formed with a multiply-add so that it issues on the (idle) FMA
+// pipe instead of the ALU pipe that bounds this kernel
+__device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(code), "r"(lut_sa));
+    return lds_u32(a);
+}
+
 // Shared-memory byte offset (relative to the lane's column) of grid cell coordinate v along x
 // (isx) or along y; out-of-grid coordinates map to `wall`, the offset of a pad word that holds
 // CODE_WALL: the offset of cell (x,y) is offx(x) + offy(y), any out-of-grid sum is >= wall and
@@ -458,9 +477,10 @@ struct Stitch {
 };
 
 template <bool SEE>
-__device__ __forceinline__ void observe(const Env &e, const DevCfg &c, const uint32_t *lut,
+__device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const DevCfg &c, const uint32_t *lut,
                                         uint32_t *stage_w, int lane) {
-    const uint8_t *sb = reinterpret_cast<const uint8_t *>(e.st);
+    const uint32_t st_sa = (uint32_t)__cvta_generic_to_shared(st);     // 32-bit shared address of the lane's column
+    const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut);
     const int odd = e.dir & 1;
     const int sgn = 1 - (e.dir & 2);                 // +1 for dir 0/1, -1 for dir 2/3
     const int wall = c.S * 128;                       // pad word (index S of the smem column)
@@ -473,10 +493,11 @@ __device__ __forceinline__ void observe(const Env &e, const DevCfg &c, const uin
     const int qma = odd ? 1 : colstride, qmb = odd ? 124 : 0, qbound = odd ? c.H : c.W;
     const int p0 = odd ? e.ax + 3 * sgn : e.ay - 3 * sgn, pstep = odd ? -sgn : sgn;
     const int q6 = odd ? e.ay : e.ax;                 // row vy = 6 is the agent's own row
+    const int wall_sa = wall + (int)st_sa;            // address of the pad word; P carries the base address
     int P[VIEW], Q[VIEW];
 #pragma unroll
     for (int k = 0; k < VIEW; ++k) {
-        P[k] = axis_off(p0 + k * pstep, pma, pmb, pbound, wall);
+        P[k] = axis_off(p0 + k * pstep, pma, pmb, pbound, wall) + (int)st_sa;
         Q[k] = axis_off(q6 + (6 - k) * sgn, qma, qmb, qbound, wall);
     }
     const uint32_t own = e.carry ? lut[e.carry] : (uint32_t)T_EMPTY;   // minigrid.py:1349-1356
@@ -499,7 +520,7 @@ __device__ __forceinline__ void observe(const Env &e, const DevCfg &c, const uin
                 x[i] = 0;
                 if (ci < VIEW * VIEW) {
                     const int vx = ci / VIEW, vy = ci % VIEW;
-                    x[i] = (vx == 3 && vy == 6) ? own : lut[sb[min(P[vx] + Q[vy], wall)]];
+                    x[i] = (vx == 3 && vy == 6) ? own : lut_ld(lut_sa, lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa)));
                 }
             }
             uint32_t w[3];
@@ -531,7 +552,7 @@ __device__ __forceinline__ void observe(const Env &e, const DevCfg &c, const uin
             uint32_t opaque = 0;
 #pragma unroll
             for (int vx = 0; vx < VIEW; ++vx) {
-                const uint32_t x = lut[sb[min(P[vx] + Q[vy], wall)]];
+                const uint32_t x = lut_ld(lut_sa, lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa)));
                 xs[vx] = x;
                 opaque |= ((x >> 24) & 1u) << vx;
             }
@@ -613,16 +634,16 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
         st_warp[S * 32 + lane] = (uint32_t)CODE_WALL * 0x01010101u;        // out-of-grid pad (minigrid.py:469)
         Env e;
         Rng rg;
-        e.st = st_warp + lane;
+        uint32_t *const st = st_warp + lane;   // this lane's column: word k at st[k*32]; bank == lane
         rg.lid = (int64_t)group * 32 + lane;
         rg.gid = p.env_id_base + rg.lid;
         const int64_t lid = rg.lid;
         const bool valid = lid < p.n_envs;
         {
-            const uint32_t w0 = e.st[(GW + 0) * 32], w1 = e.st[(GW + 1) * 32];
+            const uint32_t w0 = st[(GW + 0) * 32], w1 = st[(GW + 1) * 32];
             e.ax = w0 & 0xFF; e.ay = (w0 >> 8) & 0xFF; e.dir = (w0 >> 16) & 3; e.carry = w0 >> 24;
             e.steps = w1 & 0xFFFF; e.target = (w1 >> 16) & 0xFF;
-            rg.episode = e.st[(GW + 2) * 32]; rg.ndraws = e.st[(GW + 3) * 32];
+            rg.episode = st[(GW + 2) * 32]; rg.ndraws = st[(GW + 3) * 32];
         }
         rg.rblk = 0xFFFFFFFFu; rg.err = 0; e.dirty = false;
         rg.rb0 = rg.rb1 = rg.rb2 = rg.rb3 = 0;
@@ -632,7 +653,7 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
 
         if (p.do_reset) {
             const bool m = valid && (!p.reset_mask || p.reset_mask[lid]);
-            if (m) { Env tmp = e; generate<GEN>(tmp, rg, p); e = tmp; }   // copy-in/out keeps `e` in registers
+            if (m) { Env tmp = e; generate<GEN>(st, tmp, rg, p); e = tmp; }   // copy-in/out keeps `e` in registers
         }
         const int nsteps = p.T > 0 ? p.T : 1;
         int a_next = 0;
@@ -643,15 +664,15 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
                 const int action = a_next;
                 if (t + 1 < p.T && valid) a_next = p.actions[(int64_t)(t + 1) * stride + lid];
                 if (valid) {
-                    transition<GEN>(e, rg, p, lut, action, reward, done);
-                    if (done && p.autoreset) { Env tmp = e; generate<GEN>(tmp, rg, p); e = tmp; }
+                    transition<GEN>(st, e, rg, p, lut, action, reward, done);
+                    if (done && p.autoreset) { Env tmp = e; generate<GEN>(st, tmp, rg, p); e = tmp; }
                 }
             }
             const int64_t o = (int64_t)t * stride + lid;
             if (p.obs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
                 __syncwarp();
-                observe<SEE>(e, c, lut, stage_w, lane);
+                observe<SEE>(st, e, c, lut, stage_w, lane);
                 uint8_t *gobs = p.obs + ((int64_t)t * stride + (int64_t)group * 32) * OBS_BYTES;
                 if (full && ((reinterpret_cast<uintptr_t>(gobs) & 15) == 0)) {
                     fence_proxy_async();
@@ -673,10 +694,10 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
             }
         }
         // ---- write the state back ----
-        e.st[(GW + 0) * 32] = (uint32_t)e.ax | ((uint32_t)e.ay << 8) | ((uint32_t)e.dir << 16) | ((uint32_t)e.carry << 24);
-        e.st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16);
-        e.st[(GW + 2) * 32] = rg.episode;
-        e.st[(GW + 3) * 32] = rg.ndraws;
+        st[(GW + 0) * 32] = (uint32_t)e.ax | ((uint32_t)e.ay << 8) | ((uint32_t)e.dir << 16) | ((uint32_t)e.carry << 24);
+        st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16);
+        st[(GW + 2) * 32] = rg.episode;
+        st[(GW + 3) * 32] = rg.ndraws;
         const bool any_dirty = __any_sync(0xFFFFFFFFu, e.dirty);
         __syncwarp();
         for (int k = any_dirty ? 0 : GW; k < S; ++k) gst[k * 32] = st_warp[k * 32 + lane];
