@@ -105,6 +105,7 @@ struct RolloutParams {
 // ------------------------------------------------------------------------------------------
 struct Env {                    // hot: stays in registers (its address never escapes)
     int ax, ay, dir, carry, steps, target;
+    int flags;                  // bit0: grid == template + obstacle balls only (Dynamic-Obstacles fast reset)
     bool dirty;                 // grid words modified since load
 };
 struct Rng {                    // cold: passed by reference to the out-of-line draw routine
@@ -140,7 +141,7 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 // MiniGridEnv._rand_int (minigrid.py:939-944): low + mulhi32(u32, high-low) on the stream
 // (seed, global env id, episode); or the next tape entry in RNG-tape mode.
-__device__ __noinline__ int rand_int(Rng &e, const RolloutParams &p, int low, int high) {
+__device__ __forceinline__ int rand_int_inl(Rng &e, const RolloutParams &p, int low, int high) {
     if (p.tape) {
         const int64_t off = p.tape_off[e.lid], len = p.tape_off[e.lid + 1] - off;
         if ((int64_t)e.ndraws >= len) { e.err |= ERR_TAPE_END; return low; }
@@ -159,11 +160,16 @@ __device__ __noinline__ int rand_int(Rng &e, const RolloutParams &p, int low, in
     e.ndraws++;
     return low + (int)__umulhi(u, (uint32_t)(high - low));
 }
+// out-of-line copy for the (cold) layout generators; the per-step obstacle moves inline the body
+__device__ __noinline__ int rand_int(Rng &e, const RolloutParams &p, int low, int high) {
+    return rand_int_inl(e, p, low, high);
+}
 
 constexpr int HARD_TRY_CAP = 1 << 16;   // the reference would spin forever; we flag ERR_SAMPLING
 
 // MiniGridEnv.place_obj (minigrid.py:1003-1061).  max_tries < 0 == math.inf.
 // check_agent: "don't place the object where the agent is" (agent_pos may be None -> false).
+template <bool INL = false>
 __device__ __forceinline__ bool place_obj(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, int code, int topx, int topy,
                                           int sx, int sy, bool reject_next_to, int max_tries,
                                           bool check_agent, int &ox, int &oy) {
@@ -174,8 +180,8 @@ __device__ __forceinline__ bool place_obj(uint32_t *st, Env &e, Rng &rg, const R
     for (;;) {
         if ((max_tries >= 0 && tries > max_tries) || tries > HARD_TRY_CAP) return false;
         tries++;
-        x = rand_int(rg, p, topx, hx);
-        y = rand_int(rg, p, topy, hy);
+        x = INL ? rand_int_inl(rg, p, topx, hx) : rand_int(rg, p, topx, hx);
+        y = INL ? rand_int_inl(rg, p, topy, hy) : rand_int(rg, p, topy, hy);
         if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) return false;
         if (cell_rd(st, x * HP + y) != CODE_EMPTY) continue;
         if (check_agent && x == e.ax && y == e.ay) continue;
@@ -241,7 +247,13 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP;
     // Grid(width,height) + static walls/goal
-    for (int k = 0; k < c.GW; ++k) st[k * 32] = __ldg(&p.tmpl[k]);
+    if (GEN == GEN_DYNOBS && (e.flags & 1)) {
+        // nothing but the balls ever changes in this env (actions >= 3 are clamped, dynamicobstacles.py:62-63):
+        // removing the old balls restores the template
+        for (int k = 0; k < c.n_obst; ++k) { int ox, oy; obst_get(st, c, k, ox, oy); cell_wr(st, ox * HP + oy, CODE_EMPTY); }
+    } else {
+        for (int k = 0; k < c.GW; ++k) st[k * 32] = __ldg(&p.tmpl[k]);
+    }
     e.dirty = true;
     rg.episode++;
     if (!p.tape) rg.ndraws = 0;
@@ -272,9 +284,10 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
         if (!c.random_start) { e.ax = 1; e.ay = 1; e.dir = 0; }
         else ok = place_agent(st, e, rg, p, 0, 0, W, H, -1);
         for (int k = 0; k < c.n_obst; ++k) {
-            ok = place_obj(st, e, rg, p, code_of(T_BALL, C_BLUE, 0), 0, 0, W, H, false, 100, true, x, y) && ok;
+            ok = place_obj<true>(st, e, rg, p, code_of(T_BALL, C_BLUE, 0), 0, 0, W, H, false, 100, true, x, y) && ok;   // resets are frequent here: inline Philox
             obst_set(st, c, k, x, y);
         }
+        e.flags |= 1;
     } else if (GEN == GEN_KEYCORRIDOR) {                 // roomgrid.py:118-169 + envs/keycorridor.py:26-49
         Rooms R;
         const int rs = c.room_size, rows = c.num_rows;
@@ -367,14 +380,31 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         uint32_t front = CODE_WALL;
         if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(st, fx0 * HP + fy0);
         not_clear = front != CODE_EMPTY && (lut[front] & 0xFF) != T_GOAL;
-        for (int k = 0; k < c.n_obst; ++k) {
-            int ox, oy, nx, ny;
-            obst_get(st, c, k, ox, oy);
-            const uint32_t ball = cell_rd(st, ox * HP + oy);
-            if (place_obj(st, e, rg, p, (int)ball, ox - 1, oy - 1, 3, 3, false, 100, true, nx, ny)) {
-                obst_set(st, c, k, nx, ny);
-                cell_wr(st, ox * HP + oy, CODE_EMPTY);
+        // Update obstacle positions: for each ball in list order, place_obj(top=old-(1,1), size=(3,3),
+        // max_tries=100) then clear the old cell; a failed placement (RecursionError, swallowed) leaves
+        // the ball where it is.  One loop iteration = one try of whichever ball the lane is on, so a
+        // warp runs max-over-lanes(total tries) iterations instead of sum-over-balls(max-over-lanes).
+        int k = 0, tries = 0, ox = 0, oy = 0, tx = 0, ty = 0, hx = 0, hy = 0;
+        uint32_t ball = 0;
+        const int nob = c.n_obst;
+        while (k < nob) {
+            if (tries == 0) {
+                obst_get(st, c, k, ox, oy);
+                ball = cell_rd(st, ox * HP + oy);
+                tx = max(ox - 1, 0); ty = max(oy - 1, 0);
+                hx = min(tx + 3, W); hy = min(ty + 3, H);
             }
+            if (tries > 100) { k++; tries = 0; continue; }
+            tries++;
+            const int x = rand_int_inl(rg, p, tx, hx);
+            const int y = rand_int_inl(rg, p, ty, hy);
+            if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) break;
+            if (cell_rd(st, x * HP + y) != CODE_EMPTY) continue;      // the ball's own cell counts: it must move
+            if (x == e.ax && y == e.ay) continue;
+            cell_wr(st, x * HP + y, ball);
+            obst_set(st, c, k, x, y);
+            cell_wr(st, ox * HP + oy, CODE_EMPTY);
+            k++; tries = 0;
         }
     } else if (action >= c.n_actions) {
         rg.err |= ERR_ACTION;                             // reference: assert False, "unknown action"
@@ -642,7 +672,7 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
         {
             const uint32_t w0 = st[(GW + 0) * 32], w1 = st[(GW + 1) * 32];
             e.ax = w0 & 0xFF; e.ay = (w0 >> 8) & 0xFF; e.dir = (w0 >> 16) & 3; e.carry = w0 >> 24;
-            e.steps = w1 & 0xFFFF; e.target = (w1 >> 16) & 0xFF;
+            e.steps = w1 & 0xFFFF; e.target = (w1 >> 16) & 0xFF; e.flags = w1 >> 24;
             rg.episode = st[(GW + 2) * 32]; rg.ndraws = st[(GW + 3) * 32];
         }
         rg.rblk = 0xFFFFFFFFu; rg.err = 0; e.dirty = false;
@@ -653,7 +683,7 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
 
         if (p.do_reset) {
             const bool m = valid && (!p.reset_mask || p.reset_mask[lid]);
-            if (m) { Env tmp = e; generate<GEN>(st, tmp, rg, p); e = tmp; }   // copy-in/out keeps `e` in registers
+            if (m) { Env te = e; Rng tr = rg; generate<GEN>(st, te, tr, p); e = te; rg = tr; }   // copy-in/out keeps e, rg in registers
         }
         const int nsteps = p.T > 0 ? p.T : 1;
         int a_next = 0;
@@ -665,7 +695,7 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
                 if (t + 1 < p.T && valid) a_next = p.actions[(int64_t)(t + 1) * stride + lid];
                 if (valid) {
                     transition<GEN>(st, e, rg, p, lut, action, reward, done);
-                    if (done && p.autoreset) { Env tmp = e; generate<GEN>(st, tmp, rg, p); e = tmp; }
+                    if (done && p.autoreset) { Env te = e; Rng tr = rg; generate<GEN>(st, te, tr, p); e = te; rg = tr; }
                 }
             }
             const int64_t o = (int64_t)t * stride + lid;
@@ -695,7 +725,7 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
         }
         // ---- write the state back ----
         st[(GW + 0) * 32] = (uint32_t)e.ax | ((uint32_t)e.ay << 8) | ((uint32_t)e.dir << 16) | ((uint32_t)e.carry << 24);
-        st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16);
+        st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16) | ((uint32_t)e.flags << 24);
         st[(GW + 2) * 32] = rg.episode;
         st[(GW + 3) * 32] = rg.ndraws;
         const bool any_dirty = __any_sync(0xFFFFFFFFu, e.dirty);
@@ -777,6 +807,7 @@ __global__ void k_set_state(const StateIO io) {
         *dst = w;
     } else if (k == c.GW + 1) {
         uint32_t w = *dst;
+        if (io.grid) w &= 0x00FFFFFFu;                      // flags: an uploaded grid is no longer 'template + balls'
         if (io.agent) w = (w & 0xFFFF0000u) | (uint32_t)(io.agent[n * 4 + 3] & 0xFFFF);
         if (io.target) {
             const uint8_t *q = io.target + n * 2;
