@@ -140,7 +140,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     d.GW = c.width * d.HP / 4;
     d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0);
     h->sm_count = prop.multiProcessorCount;
-    h->smem_bytes = 1024 + (size_t)WARPS_PER_BLOCK * (STAGE_BYTES + (size_t)(d.S + 1) * 32 * 4);
+    h->smem_bytes = TABLE_BYTES + (size_t)WARPS_PER_BLOCK * (STAGE_BYTES + (size_t)(d.S + 1) * 32 * 4);
 
     auto cleanup = [&](int rc) { mgb_destroy(h); return rc; };
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess)

@@ -32,6 +32,16 @@ constexpr int THREADS = WARPS_PER_BLOCK * 32;
 constexpr int MAX_OBST = 8;
 constexpr int XWORDS = 4;                        // agent, steps/target, episode, ndraws
 constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
+// CTA-shared tables at the start of dynamic shared memory:
+//   LUT: 256 entries at a 12-byte pitch.  The odd pitch is deliberate: code*12+base cannot be an LEA, so the
+//   address is an IMAD on the otherwise idle FMA pipe (the ALU pipe bounds this kernel); 3 is coprime with
+//   32, so 32 consecutive codes still hit 32 different banks.
+//   AXIS tables: shared-memory offset of grid coordinate v (index v+6) along x and along y, out-of-grid
+//   entries = offset of the wall pad word (see observe()).
+constexpr int LUT_PITCH_W = 3;
+constexpr int LUT_BYTES = 256 * LUT_PITCH_W * 4;                 // 3072
+constexpr int AXIS_ENTRIES = 80;                                 // v in [-6, 73]: grids up to 64 + view margin
+constexpr int TABLE_BYTES = LUT_BYTES + 2 * AXIS_ENTRIES * 4;    // 3712 = 29 * 128
 
 // minigrid.py:40-52 / 27-35 / 57-61
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
@@ -379,7 +389,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         const int fx0 = e.ax + dx0, fy0 = e.ay + dy0;
         uint32_t front = CODE_WALL;
         if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(st, fx0 * HP + fy0);
-        not_clear = front != CODE_EMPTY && (lut[front] & 0xFF) != T_GOAL;
+        not_clear = front != CODE_EMPTY && (lut[front * LUT_PITCH_W] & 0xFF) != T_GOAL;
         // Update obstacle positions: for each ball in list order, place_obj(top=old-(1,1), size=(3,3),
         // max_tries=100) then clear the old cell; a failed placement (RecursionError, swallowed) leaves
         // the ball where it is.  One loop iteration = one try of whichever ball the lane is on, so a
@@ -417,7 +427,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
     const int fidx = fx * HP + fy;
     const bool f_in = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
     if (f_in) fc = cell_rd(st, fidx); else rg.err |= ERR_BOUNDS;
-    const uint32_t fw = lut[fc];
+    const uint32_t fw = lut[fc * LUT_PITCH_W];
     const uint32_t ff = fw >> 24;
     const int ftype = fw & 0xFF;
     // select form of the action switch (minigrid.py:1245-1318): one rarely-taken branch for grid edits
@@ -488,18 +498,15 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 // pipe instead of the ALU pipe that bounds this kernel
 __device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
     uint32_t a;
-    asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(a) : "r"(code), "r"(lut_sa));
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_W * 4));
     return lds_u32(a);
 }
 
-// Shared-memory byte offset (relative to the lane's column) of grid cell coordinate v along x
-// (isx) or along y; out-of-grid coordinates map to `wall`, the offset of a pad word that holds
-// CODE_WALL: the offset of cell (x,y) is offx(x) + offy(y), any out-of-grid sum is >= wall and
-// one min() clamps it onto the pad -- no per-cell bounds test (minigrid.py:465-469).
-__device__ __forceinline__ int axis_off(int v, int ma, int mb, int bound, int wall) {
-    const int off = v * ma + (v >> 2) * mb;
-    return ((unsigned)v < (unsigned)bound) ? off : wall;
-}
+// Addressing of the view gather: the shared-memory offset of grid cell (x,y) inside a lane's column is
+// offx(x) + offy(y) with offx(x) = x*HP*32 and offy(y) = (y>>2)*128 + (y&3).  Out-of-grid coordinates map to
+// the offset of a pad word that holds CODE_WALL; any sum with an out-of-grid term is >= that offset, so one
+// min() clamps it onto the pad -- no per-cell bounds test (minigrid.py:465-469).  offx/offy are tabulated
+// once per CTA (axis tables).
 
 // realign + store one 32-bit word of the 147-byte record (see observe)
 struct Stitch {
@@ -513,24 +520,24 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
     const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut);
     const int odd = e.dir & 1;
     const int sgn = 1 - (e.dir & 2);                 // +1 for dir 0/1, -1 for dir 2/3
-    const int wall = c.S * 128;                       // pad word (index S of the smem column)
-    const int colstride = c.HP * 32;                  // bytes between grid columns: (HP/4 words) * 128
+    const int wall_sa = c.S * 128 + (int)st_sa;       // address of the pad word (index S of the lane's column)
     // world(vx,vy) = agent + d*(6-vy) + r*(vx-3), d = DIR_TO_VEC[dir], r = (-d.y, d.x)   
     //   even dir: x = ax + sgn*(6-vy) (rows)    y = ay + sgn*(vx-3) (columns)
     //   odd  dir: x = ax - sgn*(vx-3) (columns) y = ay + sgn*(6-vy) (rows)
-    // coordinate -> offset is x*colstride for x and (y>>2)*128 + (y&3) = y + (y>>2)*124 for y
-    const int pma = odd ? colstride : 1, pmb = odd ? 0 : 124, pbound = odd ? c.W : c.H;
-    const int qma = odd ? 1 : colstride, qmb = odd ? 124 : 0, qbound = odd ? c.H : c.W;
-    const int p0 = odd ? e.ax + 3 * sgn : e.ay - 3 * sgn, pstep = odd ? -sgn : sgn;
-    const int q6 = odd ? e.ay : e.ax;                 // row vy = 6 is the agent's own row
-    const int wall_sa = wall + (int)st_sa;            // address of the pad word; P carries the base address
+    // P[vx] / Q[vy] = shared-memory offsets of those coordinates, read from the CTA's axis tables
+    const uint32_t ax_sa = (uint32_t)__cvta_generic_to_shared(lut) + LUT_BYTES;      // table of x offsets
+    const uint32_t ay_sa = ax_sa + AXIS_ENTRIES * 4;                                 // table of y offsets
+    const int p0 = odd ? e.ax + 3 * sgn : e.ay - 3 * sgn, pstep4 = (odd ? -sgn : sgn) * 4;
+    const int q6 = odd ? e.ay : e.ax, qstep4 = sgn * 4;               // row vy = 6 is the agent's own row
+    const uint32_t pa = (odd ? ax_sa : ay_sa) + (uint32_t)(p0 + 6) * 4;
+    const uint32_t qa = (odd ? ay_sa : ax_sa) + (uint32_t)(q6 + 6) * 4;
     int P[VIEW], Q[VIEW];
 #pragma unroll
     for (int k = 0; k < VIEW; ++k) {
-        P[k] = axis_off(p0 + k * pstep, pma, pmb, pbound, wall) + (int)st_sa;
-        Q[k] = axis_off(q6 + (6 - k) * sgn, qma, qmb, qbound, wall);
+        P[k] = (int)lds_u32(pa + k * pstep4) + (int)st_sa;            // P carries the column base address
+        Q[k] = (int)lds_u32(qa + (6 - k) * qstep4);
     }
-    const uint32_t own = e.carry ? lut[e.carry] : (uint32_t)T_EMPTY;   // minigrid.py:1349-1356
+    const uint32_t own = e.carry ? lut[e.carry * LUT_PITCH_W] : (uint32_t)T_EMPTY;   // minigrid.py:1349-1356
 
     // realignment of the record to byte offset lane*147 of the warp's 4704-byte block
     const int boff = lane * OBS_BYTES;
@@ -648,10 +655,16 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
     const DevCfg &c = p.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
-    uint8_t *stage_base = smem_raw + 1024;
+    uint32_t *axis = lut + 256 * LUT_PITCH_W;                                       // [2][AXIS_ENTRIES]
+    uint8_t *stage_base = smem_raw + TABLE_BYTES;
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * STAGE_BYTES);
     uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + WARPS_PER_BLOCK * STAGE_BYTES) + warp * ((c.S + 1) * 32);
-    for (int i = threadIdx.x; i < 256; i += THREADS) lut[i] = lut_entry(i);
+    for (int i = threadIdx.x; i < 256; i += THREADS) lut[i * LUT_PITCH_W] = lut_entry(i);
+    for (int i = threadIdx.x; i < AXIS_ENTRIES; i += THREADS) {
+        const int v = i - 6, wall = c.S * 128;
+        axis[i] = ((unsigned)v < (unsigned)c.W) ? (uint32_t)(v * c.HP * 32) : (uint32_t)wall;                       // x: column pitch
+        axis[AXIS_ENTRIES + i] = ((unsigned)v < (unsigned)c.H) ? (uint32_t)(((v >> 2) << 7) + (v & 3)) : (uint32_t)wall;   // y: word + byte
+    }
     __syncthreads();
 
     const int S = c.S, GW = c.GW;
