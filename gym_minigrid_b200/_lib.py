@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmgb200.so")
+SO_PATH = os.environ.get("MGB_LIB") or os.path.join(_HERE, "libmgb200.so")   # MGB_LIB: kernel-variant experiments
 
 OBS_BYTES = 147
 MAX_OBSTACLES = 8

@@ -38,10 +38,12 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (e.g. defines=["MGB_STITCH_IMAD=1"]) next to the product .so"""
+    if not force and not needs_build() and not defines:
         return SO
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-o", SO] + SOURCES
+    target = out or SO
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-I", os.path.join(ROOT, "include"), "-o", target] + SOURCES
     env = dict(os.environ)
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
@@ -53,8 +55,10 @@ def build(force=False, verbose=False):
         print(r.stdout)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed (see %s)" % log)
-    return SO
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, defines=defs, out=outs[0] if outs else None))

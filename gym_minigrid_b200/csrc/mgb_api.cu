@@ -44,6 +44,7 @@ struct mgb_handle {
     const int64_t *tape_off = nullptr;
     int sm_count = 0;
     int blocks_per_sm = 0;
+    int warps_per_block = 4;
     size_t smem_bytes = 0;
     int64_t launches = 0;
     // host pipeline (mgb_step_host)
@@ -140,13 +141,22 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     d.GW = c.width * d.HP / 4;
     d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0);
     h->sm_count = prop.multiProcessorCount;
-    h->smem_bytes = TABLE_BYTES + (size_t)WARPS_PER_BLOCK * (STAGE_BYTES + (size_t)(d.S + 1) * 32 * 4);
 
     auto cleanup = [&](int rc) { mgb_destroy(h); return rc; };
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes) != cudaSuccess)
-        return cleanup(fail("mgb_create: %zu bytes of shared memory per block not available", h->smem_bytes));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, fn, THREADS, h->smem_bytes) != cudaSuccess || h->blocks_per_sm < 1)
-        return cleanup(fail("mgb_create: kernel does not fit on an SM"));
+    // warps per CTA: whatever keeps the most warps resident per SM (shared memory is the limiter for the
+    // larger grids: each warp needs its 32-env state block + a 4704-byte staging block)
+    const size_t per_warp = STAGE_BYTES + (size_t)(d.S + 1) * 32 * 4;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) != cudaSuccess)
+        return cleanup(fail("mgb_create: cannot opt in to %zu bytes of shared memory", (size_t)prop.sharedMemPerBlockOptin));
+    int best_warps = 0;
+    for (int wpb = MAX_WARPS_PER_BLOCK; wpb >= 2; --wpb) {
+        const size_t smem = TABLE_BYTES + (size_t)wpb * per_warp;
+        if (smem > prop.sharedMemPerBlockOptin) continue;
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, wpb * 32, smem) != cudaSuccess) continue;
+        if (nb * wpb > best_warps) { best_warps = nb * wpb; h->blocks_per_sm = nb; h->warps_per_block = wpb; h->smem_bytes = smem; }
+    }
+    if (best_warps < 1) return cleanup(fail("mgb_create: kernel does not fit on an SM (%zu bytes of shared memory per warp)", per_warp));
     const size_t state_bytes = (size_t)h->n_groups * d.S * 32 * 4;
     if (cudaMalloc(&h->state, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: cudaMalloc(%zu) for env state failed", state_bytes));
     if (cudaMemset(h->state, 0, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: memset failed"));
@@ -214,11 +224,12 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
     p.reset_mask = mask; p.actions = actions; p.obs = obs; p.reward = reward; p.done = done; p.dir = dir;
     p.stride = stride; p.seed = h->seed; p.env_id_base = h->env_id_base;
     p.tape = h->tape; p.tape_off = h->tape_off; p.err = h->err;
+    p.m0 = 1u; p.m1 = 1u; p.m2 = 2u; p.m8 = 1u << 8; p.m16 = 1u << 16; p.m24 = 1u << 24;
     rollout_fn fn = pick_kernel(h->cfg);
-    const int want = (ng + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const int want = (ng + h->warps_per_block - 1) / h->warps_per_block;
     const int grid = std::max(1, std::min(want, h->sm_count * h->blocks_per_sm));
     if (timed && h->timing) CUDA_OK(cudaEventRecord(h->ev0, stream));
-    fn<<<grid, THREADS, h->smem_bytes, stream>>>(p);
+    fn<<<grid, h->warps_per_block * 32, h->smem_bytes, stream>>>(p);
     CUDA_OK(cudaGetLastError());
     if (timed && h->timing) { CUDA_OK(cudaEventRecord(h->ev1, stream)); h->ev_valid = true; }
     h->launches++;

@@ -27,21 +27,31 @@ constexpr int VIEW = 7;
 constexpr int OBS_BYTES = 147;
 constexpr int GROUP = 32;
 constexpr int STAGE_BYTES = GROUP * OBS_BYTES;   // 4704 = 294 * 16
-constexpr int WARPS_PER_BLOCK = 4;
-constexpr int THREADS = WARPS_PER_BLOCK * 32;
+constexpr int MAX_WARPS_PER_BLOCK = 8;           // the host picks 2..8 warps per CTA to maximise resident warps/SM
+constexpr int MAX_THREADS = MAX_WARPS_PER_BLOCK * 32;
 constexpr int MAX_OBST = 8;
 constexpr int XWORDS = 4;                        // agent, steps/target, episode, ndraws
 constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 // CTA-shared tables at the start of dynamic shared memory:
-//   LUT: 256 entries at a 12-byte pitch.  The odd pitch is deliberate: code*12+base cannot be an LEA, so the
-//   address is an IMAD on the otherwise idle FMA pipe (the ALU pipe bounds this kernel); 3 is coprime with
-//   32, so 32 consecutive codes still hit 32 different banks.
+//   LUT: 256 entries at a 24-byte pitch: word0 = type|colour<<8|state<<16 (the 3 output bytes), word1 = opaque
+//   (0/1), word2 = word0|flags<<24 (transition).  The non-power-of-two pitch is deliberate: code*24+base cannot
+//   be an LEA, so the address is an IMAD on the otherwise idle FMA pipe (the ALU pipe bounds this kernel);
+//   8-byte alignment lets the occluded path fetch word0+word1 with one LDS.64.
 //   AXIS tables: shared-memory offset of grid coordinate v (index v+6) along x and along y, out-of-grid
 //   entries = offset of the wall pad word (see observe()).
-constexpr int LUT_PITCH_W = 3;
-constexpr int LUT_BYTES = 256 * LUT_PITCH_W * 4;                 // 3072
+#ifndef MGB_STITCH_IMAD
+#define MGB_STITCH_IMAD 0      // realign words with IMAD.WIDE (FMA pipe) instead of SHF funnel shifts (ALU pipe)
+#endif
+#ifndef MGB_PACK_IMAD_SEE
+#define MGB_PACK_IMAD_SEE 0    // see-through path: pack 4 cells -> 3 words with IMAD/IMAD.HI instead of PRMT
+#endif
+#ifndef MGB_PACK_IMAD_OCC
+#define MGB_PACK_IMAD_OCC 0    // occluded path: predicated IMAD accumulation instead of LOP3+SEL+PRMT (measured slower: 157 regs)
+#endif
+constexpr int LUT_PITCH_W = 6;
+constexpr int LUT_BYTES = 256 * LUT_PITCH_W * 4;                 // 6144
 constexpr int AXIS_ENTRIES = 80;                                 // v in [-6, 73]: grids up to 64 + view margin
-constexpr int TABLE_BYTES = LUT_BYTES + 2 * AXIS_ENTRIES * 4;    // 3712 = 29 * 128
+constexpr int TABLE_BYTES = LUT_BYTES + 2 * AXIS_ENTRIES * 4;    // 6784 = 53 * 128
 
 // minigrid.py:40-52 / 27-35 / 57-61
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
@@ -108,6 +118,10 @@ struct RolloutParams {
     const int32_t *tape;
     const int64_t *tape_off;
     uint32_t *err;
+    // run-time copies of 1, 1, 2, 2^8, 2^16, 2^24.  Multiplying by these (instead of literal shifts) keeps the
+    // byte packing / realignment on IMAD/IMAD.HI/IMAD.WIDE, i.e. on the FMA pipe: ptxas would turn a literal
+    // power of two back into SHF/LEA/PRMT on the ALU pipe, which is the pipe that bounds this kernel.
+    uint32_t m0, m1, m2, m8, m16, m24;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -389,7 +403,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         const int fx0 = e.ax + dx0, fy0 = e.ay + dy0;
         uint32_t front = CODE_WALL;
         if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(st, fx0 * HP + fy0);
-        not_clear = front != CODE_EMPTY && (lut[front * LUT_PITCH_W] & 0xFF) != T_GOAL;
+        not_clear = front != CODE_EMPTY && (lut[front * LUT_PITCH_W + 2] & 0xFF) != T_GOAL;
         // Update obstacle positions: for each ball in list order, place_obj(top=old-(1,1), size=(3,3),
         // max_tries=100) then clear the old cell; a failed placement (RecursionError, swallowed) leaves
         // the ball where it is.  One loop iteration = one try of whichever ball the lane is on, so a
@@ -427,7 +441,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
     const int fidx = fx * HP + fy;
     const bool f_in = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
     if (f_in) fc = cell_rd(st, fidx); else rg.err |= ERR_BOUNDS;
-    const uint32_t fw = lut[fc * LUT_PITCH_W];
+    const uint32_t fw = lut[fc * LUT_PITCH_W + 2];
     const uint32_t ff = fw >> 24;
     const int ftype = fw & 0xFF;
     // select form of the action switch (minigrid.py:1245-1318): one rarely-taken branch for grid edits
@@ -501,6 +515,12 @@ __device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
     asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_W * 4));
     return lds_u32(a);
 }
+// word0 (output bytes) and word1 (opaque) of a LUT entry with one LDS.64
+__device__ __forceinline__ void lut_ld2(uint32_t lut_sa, uint32_t code, uint32_t &x, uint32_t &opq) {
+    uint32_t a;
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_W * 4));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(opq) : "r"(a) : "memory");
+}
 
 // Addressing of the view gather: the shared-memory offset of grid cell (x,y) inside a lane's column is
 // offx(x) + offy(y) with offx(x) = x*HP*32 and offy(y) = (y>>2)*128 + (y&3).  Out-of-grid coordinates map to
@@ -514,8 +534,9 @@ struct Stitch {
 };
 
 template <bool SEE>
-__device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const DevCfg &c, const uint32_t *lut,
+__device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const RolloutParams &p, const uint32_t *lut,
                                         uint32_t *stage_w, int lane) {
+    const DevCfg &c = p.cfg;
     const uint32_t st_sa = (uint32_t)__cvta_generic_to_shared(st);     // 32-bit shared address of the lane's column
     const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut);
     const int odd = e.dir & 1;
@@ -537,17 +558,34 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
         P[k] = (int)lds_u32(pa + k * pstep4) + (int)st_sa;            // P carries the column base address
         Q[k] = (int)lds_u32(qa + (6 - k) * qstep4);
     }
-    const uint32_t own = e.carry ? lut[e.carry * LUT_PITCH_W] : (uint32_t)T_EMPTY;   // minigrid.py:1349-1356
+    const uint32_t own = e.carry ? lut[e.carry * LUT_PITCH_W] : (uint32_t)T_EMPTY;   // word0: 24-bit (type,colour,state)   // minigrid.py:1349-1356
 
-    // realignment of the record to byte offset lane*147 of the warp's 4704-byte block
+    // Realignment of the record to byte offset lane*147 of the warp's 4704-byte block: word j of the record
+    // times 2^s8 (one IMAD.WIDE) gives the bits that stay in block word q+j (low half) and the bits that
+    // spill into q+j+1 (high half, carried into the next multiply-add).
     const int boff = lane * OBS_BYTES;
     const int q = boff >> 2;
     const uint32_t s8 = (boff & 3) * 8;
-    uint32_t first = 0, w36 = 0, w37 = 0;
+    const uint32_t M = p.m1 << s8;
+    uint32_t first = 0, w36 = 0, w37 = 0, spill = 0;
+    auto emit = [&](int j, uint32_t a) {
+#if MGB_STITCH_IMAD
+        const uint64_t wide = (uint64_t)a * M + spill;
+        const uint32_t o = (uint32_t)wide;
+        spill = (uint32_t)(wide >> 32);
+#else
+        const uint32_t o = __funnelshift_l(spill, a, s8);      // spill holds the previous un-shifted word
+        spill = a;
+#endif
+        if (j == 0) first = o;
+        else if (j < 36) stage_w[q + j] = o;
+        else if (j == 36) w36 = o;
+        else w37 = o;
+    };
+    const uint32_t m0 = p.m0, m8 = p.m8, m16 = p.m16, m24 = p.m24;
 
     if (SEE) {
-        // no occlusion: stream cells in output order (vx-major), 4 cells -> 3 words, realign on the fly
-        uint32_t prev = 0;
+        // no occlusion: stream cells in output order (vx-major); 4 cells (3 bytes each) -> 3 words
 #pragma unroll
         for (int g = 0; g < 13; ++g) {
             uint32_t x[4];
@@ -560,23 +598,15 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
                     x[i] = (vx == 3 && vy == 6) ? own : lut_ld(lut_sa, lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa)));
                 }
             }
-            uint32_t w[3];
-            w[0] = __byte_perm(x[0], x[1], 0x4210);        // x0.b0 x0.b1 x0.b2 x1.b0
-            w[1] = __byte_perm(x[1], x[2], 0x5421);        // x1.b1 x1.b2 x2.b0 x2.b1
-            w[2] = __byte_perm(x[2], x[3], 0x6542);        // x2.b2 x3.b0 x3.b1 x3.b2
-            if (g == 12) w[0] &= 0x00FFFFFFu;              // cell 48 is the last; byte 147 does not exist
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const int j = g * 3 + i;
-                if (j > 37) continue;
-                const uint32_t a = (j <= 36) ? w[i] : 0u;
-                const uint32_t o = __funnelshift_l(prev, a, s8);
-                prev = a;
-                if (j == 0) first = o;
-                else if (j < 36) stage_w[q + j] = o;
-                else if (j == 36) w36 = o;
-                else w37 = o;
-            }
+#if MGB_PACK_IMAD_SEE
+            emit(g * 3, x[1] * m24 + x[0]);                                   // x0.b0 x0.b1 x0.b2 x1.b0
+            if (g * 3 + 1 <= 37) emit(g * 3 + 1, x[2] * m16 + __umulhi(x[1], m24));   // x1.b1 x1.b2 x2.b0 x2.b1
+            if (g * 3 + 2 <= 37) emit(g * 3 + 2, x[3] * m8 + __umulhi(x[2], m16));    // x2.b2 x3.b0 x3.b1 x3.b2
+#else
+            emit(g * 3, __byte_perm(x[0], x[1], 0x4210));                              // x0.b0 x0.b1 x0.b2 x1.b0
+            if (g * 3 + 1 <= 37) emit(g * 3 + 1, __byte_perm(x[1], x[2], 0x5421));     // x1.b1 x1.b2 x2.b0 x2.b1
+            if (g * 3 + 2 <= 37) emit(g * 3 + 2, __byte_perm(x[2], x[3], 0x6542));     // x2.b2 x3.b0 x3.b1 x3.b2
+#endif
         }
     } else {
         uint32_t acc[38];
@@ -588,10 +618,10 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
             uint32_t xs[VIEW];
             uint32_t opaque = 0;
 #pragma unroll
-            for (int vx = 0; vx < VIEW; ++vx) {
-                const uint32_t x = lut_ld(lut_sa, lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa)));
-                xs[vx] = x;
-                opaque |= ((x >> 24) & 1u) << vx;
+            for (int vx = VIEW - 1; vx >= 0; --vx) {                      // descending: Horner on the FMA pipe
+                uint32_t oq;
+                lut_ld2(lut_sa, lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa)), xs[vx], oq);
+                opaque = opaque * p.m2 + oq;
             }
             const uint32_t t = ~opaque & 0x7Fu;
             const uint32_t f = flood_up(rowvis, t);                       // forward sweep i = 0..5
@@ -601,23 +631,26 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
             if (vy == VIEW - 1) xs[3] = own;
 #pragma unroll
             for (int vx = 0; vx < VIEW; ++vx) {
-                const uint32_t x = ((vis >> vx) & 1u) ? xs[vx] : 0u;
-                const int b = 3 * (vx * VIEW + vy);
-                put3(b & 3, acc[b >> 2], acc[(b >> 2) + 1], x);
+#if MGB_PACK_IMAD_OCC
+                if ((vis >> vx) & 1u) {                                   // invisible cells stay (0,0,0)
+                    const uint32_t x = xs[vx];
+                    const int b = 3 * (vx * VIEW + vy), w = b >> 2, sh = b & 3;
+                    if (sh == 0) acc[w] = x * m0 + acc[w];
+                    else if (sh == 1) acc[w] = x * m8 + acc[w];
+                    else if (sh == 2) { acc[w] = x * m16 + acc[w]; acc[w + 1] = __umulhi(x, m16) + acc[w + 1]; }
+                    else { acc[w] = x * m24 + acc[w]; acc[w + 1] = __umulhi(x, m24) + acc[w + 1]; }
+                }
+#else
+                {
+                    const uint32_t x = ((vis >> vx) & 1u) ? xs[vx] : 0u;
+                    const int b = 3 * (vx * VIEW + vy);
+                    put3(b & 3, acc[b >> 2], acc[(b >> 2) + 1], x);
+                }
+#endif
             }
         }
-        acc[36] &= 0x00FFFFFFu;
-        acc[37] = 0;
-        uint32_t prev = 0;
 #pragma unroll
-        for (int j = 0; j < 38; ++j) {
-            const uint32_t o = __funnelshift_l(prev, acc[j], s8);
-            prev = acc[j];
-            if (j == 0) first = o;
-            else if (j < 36) stage_w[q + j] = o;
-            else if (j == 36) w36 = o;
-            else w37 = o;
-        }
+        for (int j = 0; j < 38; ++j) emit(j, acc[j]);
     }
     // the partial last word of lane t-1 shares a 32-bit word with the head of lane t
     const uint32_t tail = (s8 >= 16) ? w37 : w36;
@@ -649,18 +682,26 @@ __device__ __forceinline__ void fence_proxy_async() {
 // ------------------------------------------------------------------------------------------
 // the persistent rollout kernel (also serves reset and single step)
 // ------------------------------------------------------------------------------------------
+#ifndef MGB_MIN_BLOCKS
+#define MGB_MIN_BLOCKS 1
+#endif
 template <int GEN, bool SEE>
-__global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ RolloutParams p) {
+__global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS) k_rollout(const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const DevCfg &c = p.cfg;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
     uint32_t *axis = lut + 256 * LUT_PITCH_W;                                       // [2][AXIS_ENTRIES]
     uint8_t *stage_base = smem_raw + TABLE_BYTES;
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * STAGE_BYTES);
-    uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + WARPS_PER_BLOCK * STAGE_BYTES) + warp * ((c.S + 1) * 32);
-    for (int i = threadIdx.x; i < 256; i += THREADS) lut[i * LUT_PITCH_W] = lut_entry(i);
-    for (int i = threadIdx.x; i < AXIS_ENTRIES; i += THREADS) {
+    uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + wpb * STAGE_BYTES) + warp * ((c.S + 1) * 32);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const uint32_t le = lut_entry(i);
+        lut[i * LUT_PITCH_W] = le & 0x00FFFFFFu;
+        lut[i * LUT_PITCH_W + 1] = (le >> 24) & F_OPAQUE;
+        lut[i * LUT_PITCH_W + 2] = le;
+    }
+    for (int i = threadIdx.x; i < AXIS_ENTRIES; i += blockDim.x) {
         const int v = i - 6, wall = c.S * 128;
         axis[i] = ((unsigned)v < (unsigned)c.W) ? (uint32_t)(v * c.HP * 32) : (uint32_t)wall;                       // x: column pitch
         axis[AXIS_ENTRIES + i] = ((unsigned)v < (unsigned)c.H) ? (uint32_t)(((v >> 2) << 7) + (v & 3)) : (uint32_t)wall;   // y: word + byte
@@ -669,7 +710,7 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
 
     const int S = c.S, GW = c.GW;
     const int64_t stride = p.stride;
-    for (int g = blockIdx.x * WARPS_PER_BLOCK + warp; g < p.n_groups; g += gridDim.x * WARPS_PER_BLOCK) {
+    for (int g = blockIdx.x * wpb + warp; g < p.n_groups; g += gridDim.x * wpb) {
         const int group = p.group0 + g;
         uint32_t *gst = p.state + (size_t)group * S * 32 + lane;
         // ---- load the group's state block: S coalesced 128-byte rows -> bank == lane ----
@@ -715,7 +756,7 @@ __global__ void __launch_bounds__(THREADS) k_rollout(const __grid_constant__ Rol
             if (p.obs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
                 __syncwarp();
-                observe<SEE>(st, e, c, lut, stage_w, lane);
+                observe<SEE>(st, e, p, lut, stage_w, lane);
                 uint8_t *gobs = p.obs + ((int64_t)t * stride + (int64_t)group * 32) * OBS_BYTES;
                 if (full && ((reinterpret_cast<uintptr_t>(gobs) & 15) == 0)) {
                     fence_proxy_async();
