@@ -340,6 +340,39 @@ int mgb_full_obs(mgb_handle *h, uint8_t *out, void *stream) {
     return state_io(h, false, 1, 0, h ? h->n_envs : 0, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
+static int elementwise_grid(int64_t total) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (total + 255) / 256;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * 16));
+}
+
+int mgb_onehot(const uint8_t *cells, uint8_t *out, int64_t n_cells, const uint8_t *class_map, int32_t n_classes,
+               int32_t n_colors, int32_t n_states, void *stream) {
+    if (!cells || !out) return fail("mgb_onehot: null buffer");
+    if (n_cells < 0 || n_classes < 1 || n_classes > 16 || n_colors < 0 || n_colors > 8 || n_states < 1 || n_states > 8)
+        return fail("mgb_onehot: bad sizes");
+    if (n_cells == 0) return 0;
+    ClassMap cm;
+    for (int i = 0; i < 16; ++i) cm.m[i] = class_map && i < 11 ? class_map[i] : (uint8_t)i;
+    const int64_t total = n_cells * (n_classes + n_colors + n_states);
+    k_onehot<<<elementwise_grid(total), 256, 0, (cudaStream_t)stream>>>(cells, out, n_cells, cm, n_classes, n_colors, n_states);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mgb_flat_obs(const uint8_t *img, int32_t img_bytes, const float *mission_table, int32_t mission_len,
+                 const uint8_t *mission_idx, float *out, int64_t N, void *stream) {
+    if (!img || !mission_table || !out) return fail("mgb_flat_obs: null buffer");
+    if (img_bytes < 1 || mission_len < 0 || N < 0) return fail("mgb_flat_obs: bad sizes");
+    if (N == 0) return 0;
+    const int64_t total = N * ((int64_t)img_bytes + mission_len);
+    k_flat_obs<<<elementwise_grid(total), 256, 0, (cudaStream_t)stream>>>(img, img_bytes, mission_table, mission_len, mission_idx, out, N);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int mgb_error_flags(mgb_handle *h, void *stream, uint32_t *flags_host) {
     if (!h || !flags_host) return fail("null argument");
     CUDA_OK(cudaSetDevice(h->device));

@@ -682,11 +682,10 @@ __device__ __forceinline__ void fence_proxy_async() {
 // ------------------------------------------------------------------------------------------
 // the persistent rollout kernel (also serves reset and single step)
 // ------------------------------------------------------------------------------------------
-#ifndef MGB_MIN_BLOCKS
-#define MGB_MIN_BLOCKS 1
-#endif
+// NOTE: no minBlocksPerSM argument on purpose -- with it ptxas spends up to 157 registers/thread and the
+// occupancy loss costs more than it gains (measured: profiles/README.md, A/B table)
 template <int GEN, bool SEE>
-__global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS) k_rollout(const __grid_constant__ RolloutParams p) {
+__global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const DevCfg &c = p.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -937,6 +936,41 @@ __global__ void k_get_state(const StateIO io, int full_obs) {
         const int o = (k - c.GW - XWORDS) * 2;
         int16_t *q = io.obstacles + (n * MAX_OBST + o) * 2;
         q[0] = w & 0xFF; q[1] = (w >> 8) & 0xFF; q[2] = (w >> 16) & 0xFF; q[3] = (w >> 24) & 0xFF;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: observation-wrapper kernels (stateless, HBM-bound elementwise/gather)
+// ------------------------------------------------------------------------------------------
+struct ClassMap { uint8_t m[16]; };
+
+// one thread per output byte; out[cell][bit]
+__global__ void k_onehot(const uint8_t *__restrict__ cells, uint8_t *__restrict__ out, int64_t n_cells,
+                         ClassMap cm, int n_classes, int n_colors, int n_states) {
+    const int nbits = n_classes + n_colors + n_states;
+    const int64_t total = n_cells * nbits;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t cell = i / nbits;
+        const int bit = (int)(i - cell * nbits);
+        const uint8_t *q = cells + cell * 3;
+        const int t = cm.m[q[0] & 15], c = q[1], st = q[2];
+        const bool on = bit == t || (n_colors > 0 && bit == n_classes + c) || bit == n_classes + n_colors + st;
+        out[i] = on ? 1 : 0;
+    }
+}
+
+// one thread per output float; out[n][img_bytes + mission_len]
+__global__ void k_flat_obs(const uint8_t *__restrict__ img, int img_bytes, const float *__restrict__ table, int mlen,
+                           const uint8_t *__restrict__ midx, float *__restrict__ out, int64_t N) {
+    const int row = img_bytes + mlen;
+    const int64_t total = N * row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / row;
+        const int k = (int)(i - n * row);
+        float v;
+        if (k < img_bytes) v = (float)img[n * img_bytes + k];
+        else v = __ldg(&table[(size_t)(midx ? midx[n] : 0) * mlen + (k - img_bytes)]);
+        out[i] = v;
     }
 }
 

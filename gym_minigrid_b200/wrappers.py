@@ -1,0 +1,232 @@
+"""Batched observation wrappers: SURVEY §8(f) rank 1 -- the part of gym_minigrid/wrappers.py that
+the north star names as kept API surface.  Same class names and constructor arguments as the
+reference; they wrap a VecMiniGridEnv and transform whole batches on the GPU through libmgb200
+(mgb_full_obs / mgb_onehot / mgb_flat_obs).
+
+Built (with reference lines):      ReseedWrapper (wrappers.py:12-32), ImgObsWrapper (:156-166),
+    OneHotPartialObsWrapper (:203-243), FullyObsWrapper (:311-338), FullyObsOneHotWrapper (:340-415),
+    FlatObsWrapper (:528-577).
+Not built (out of the hot-path scope): RGBImg*Wrapper (rendering), ViewSizeWrapper
+    (needs a view-size template parameter in k_rollout), DACWrapper / ActionBonus / StateBonus /
+    AppendActionWrapper / GoalPolicyWrapper / AgentExtraInfoWrapper (bookkeeping on top of step).
+
+Reference quirks, kept or documented:
+  * OneHotPartialObsWrapper.observation reads `self.observation_space.shape` of a Dict space
+    (wrappers.py:228), which has no usable shape, so the reference class cannot actually run; the
+    intended (7, 7, 21) encoding of its loop body (:230-238) is what is implemented.
+  * FlatObsWrapper concatenates a uint8 image with a float32 one-hot, so the result is float32 and
+    1-D although its declared space is uint8 with shape (1, n) (wrappers.py:543-548,575).  Kept.
+  * FullyObsOneHotWrapper uses 4 state planes (wrappers.py:368) and expects an *array* observation
+    (e.g. ImgObsWrapper(FullyObsWrapper(env))).  Kept.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, spaces
+from .vec_env import COLOR_TO_IDX, OBJECT_TO_IDX, STATE_TO_IDX, IDX_TO_COLOR, IDX_TO_OBJECT
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Wrapper:
+    """gym.core.Wrapper for batched envs: forwards everything it does not override."""
+
+    def __init__(self, env):
+        self.env = env
+        self.action_space = env.action_space
+        self.observation_space = env.observation_space
+        self.reward_range = env.reward_range
+        self.metadata = getattr(env, "metadata", {})
+
+    def __getattr__(self, name):
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.env, name)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+    def reset(self, **kw):
+        return self.env.reset(**kw)
+
+    def step(self, action):
+        return self.env.step(action)
+
+    def seed(self, seed=None):
+        return self.env.seed(seed)
+
+    def close(self):
+        return self.env.close()
+
+
+class ObservationWrapper(Wrapper):
+    def reset(self, **kw):
+        return self.observation(self.env.reset(**kw))
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        return self.observation(obs), reward, done, info
+
+    def observation(self, obs):
+        raise NotImplementedError
+
+
+class ReseedWrapper(Wrapper):
+    """wrappers.py:12-32: every reset re-seeds with the next seed of the list, so the whole batch
+    regenerates the same layouts (per global env id) each time."""
+
+    def __init__(self, env, seeds=[0], seed_idx=0):
+        self.seeds = list(seeds)
+        self.seed_idx = seed_idx
+        super().__init__(env)
+
+    def reset(self, **kw):
+        seed = self.seeds[self.seed_idx]
+        self.seed_idx = (self.seed_idx + 1) % len(self.seeds)
+        self.env.seed(seed)
+        return self.env.reset(**kw)
+
+
+class ImgObsWrapper(ObservationWrapper):
+    """wrappers.py:156-166: the image is the only observation output."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = env.observation_space.spaces['image']
+
+    def observation(self, obs):
+        return obs['image']
+
+
+def _onehot(cells, n_classes, n_colors, n_states, class_map=None):
+    L = _lib.load()
+    cells = cells.contiguous()
+    assert cells.dtype == torch.uint8 and cells.shape[-1] == 3 and cells.is_cuda
+    nbits = n_classes + n_colors + n_states
+    out = torch.empty(cells.shape[:-1] + (nbits,), dtype=torch.uint8, device=cells.device)
+    cm = None
+    if class_map is not None:
+        cm = (C.c_uint8 * 11)(*class_map)
+    with torch.cuda.device(cells.device):
+        _lib.check(L.mgb_onehot(_ptr(cells), _ptr(out), cells.numel() // 3, cm, n_classes, n_colors, n_states,
+                                C.c_void_p(torch.cuda.current_stream(cells.device).cuda_stream)))
+    return out
+
+
+class OneHotPartialObsWrapper(ObservationWrapper):
+    """wrappers.py:203-243: 7x7x3 view -> 7x7x(11+7+3) one-hot planes."""
+
+    def __init__(self, env, tile_size=8):
+        super().__init__(env)
+        self.tile_size = tile_size
+        shape = env.observation_space['image'].shape
+        self.num_bits = len(OBJECT_TO_IDX) + len(COLOR_TO_IDX) + len(STATE_TO_IDX)
+        self.observation_space = spaces.Dict(dict(env.observation_space.spaces))
+        self.observation_space.spaces["image"] = spaces.Box(0, 255, (shape[0], shape[1], self.num_bits), 'uint8')
+
+    def observation(self, obs):
+        out = _onehot(obs['image'], len(OBJECT_TO_IDX), len(COLOR_TO_IDX), len(STATE_TO_IDX))
+        return {'mission': obs['mission'], 'image': out}
+
+
+class FullyObsWrapper(ObservationWrapper):
+    """wrappers.py:311-338: full grid encoding with the agent drawn as (10, 0, dir)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Dict(dict(env.observation_space.spaces))
+        self.observation_space.spaces["image"] = spaces.Box(0, 255, (self.env.width, self.env.height, 3), 'uint8')
+
+    def observation(self, obs):
+        return {'mission': obs['mission'], 'image': self.unwrapped.full_obs()}
+
+
+class FullyObsOneHotWrapper(ObservationWrapper):
+    """wrappers.py:340-415.  Expects an array observation, e.g. ImgObsWrapper(FullyObsWrapper(env))."""
+
+    def __init__(self, env, drop_color=False, keep_classes=None, flatten=True):
+        super().__init__(env)
+        if not keep_classes:
+            keep_classes = list(OBJECT_TO_IDX.keys())
+        keep_classes.sort(key=lambda x: OBJECT_TO_IDX[x])
+        self.num_classes = len(keep_classes)
+        self.object_to_new_idx = {OBJECT_TO_IDX[k]: i for i, k in enumerate(keep_classes)}
+        self.num_colors = 0 if drop_color else len(COLOR_TO_IDX)
+        self.num_states = 4
+        self.N = self.num_classes + self.num_colors + self.num_states
+        o = self.env.observation_space
+        try:
+            shp = o['image'].shape
+        except Exception:
+            shp = o.shape
+        self._cells_shape = tuple(shp[:2])
+        self.flatten = flatten
+        n = int(np.prod(self._cells_shape))
+        shape = (n * self.N,) if flatten else self._cells_shape + (self.N,)
+        self.obsshape = n
+        self.observation_space = spaces.Box(0, 1, shape, 'uint8')
+        # types that are not kept have no plane: the reference would raise KeyError; map them to an
+        # out-of-range index so that no class bit is set
+        self._class_map = [self.object_to_new_idx.get(t, 255) for t in range(11)]
+
+    def observation(self, obs):
+        out = _onehot(obs, self.num_classes, self.num_colors, self.num_states, self._class_map)
+        n = out.shape[0]
+        return out.reshape(n, -1) if self.flatten else out.reshape((n,) + self._cells_shape + (self.N,))
+
+
+class FlatObsWrapper(ObservationWrapper):
+    """wrappers.py:528-577: image.flatten() ++ 27x96 one-hot of the lower-cased mission, float32."""
+
+    def __init__(self, env, maxStrLen=96):
+        super().__init__(env)
+        self.maxStrLen = maxStrLen
+        self.numCharCodes = 27
+        img = env.observation_space.spaces['image']
+        self._img_bytes = int(np.prod(img.shape))
+        self.observation_space = spaces.Box(0, 255, (1, self._img_bytes + self.numCharCodes * self.maxStrLen), 'uint8')
+        u = env.unwrapped
+        tmpl = u._mission
+        # every mission string this env can produce: one for the static ones, one per target colour for
+        # KeyCorridor ("pick up the <colour> ball", keycorridor.py:49); row index = colour id
+        if "%s" in tmpl:
+            self._per_colour = True
+            missions = [tmpl % (IDX_TO_COLOR[c], IDX_TO_OBJECT[6]) for c in range(len(COLOR_TO_IDX))]
+        else:
+            self._per_colour = False
+            missions = [tmpl]
+        table = np.stack([self._encode(m) for m in missions])
+        self._table = torch.as_tensor(table).to(u.device)
+
+    def _encode(self, mission):
+        assert len(mission) <= self.maxStrLen, 'mission string too long ({} chars)'.format(len(mission))
+        arr = np.zeros((self.maxStrLen, self.numCharCodes), dtype='float32')
+        chNo = 0
+        for idx, ch in enumerate(mission.lower()):
+            if 'a' <= ch <= 'z':
+                chNo = ord(ch) - ord('a')
+            elif ch == ' ':
+                chNo = ord('z') - ord('a') + 1
+            assert chNo < self.numCharCodes
+            arr[idx, chNo] = 1
+        return arr.reshape(-1)
+
+    def observation(self, obs):
+        L = _lib.load()
+        img = obs['image'].contiguous()
+        u = self.unwrapped
+        N = img.shape[0]
+        midx = None
+        if self._per_colour:
+            midx = u.get_state(("target",))["target"][:, 1].contiguous()
+        mlen = self._table.shape[1]
+        out = torch.empty((N, self._img_bytes + mlen), dtype=torch.float32, device=img.device)
+        with torch.cuda.device(img.device):
+            _lib.check(L.mgb_flat_obs(_ptr(img), self._img_bytes, _ptr(self._table), mlen, _ptr(midx), _ptr(out), N,
+                                      C.c_void_p(torch.cuda.current_stream(img.device).cuda_stream)))
+        return out

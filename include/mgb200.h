@@ -125,6 +125,21 @@ int mgb_set_rng_tape(mgb_handle *h, const int32_t *draws, const int64_t *offsets
  * to (10, 0, dir).  out [N][W][H][3]. */
 int mgb_full_obs(mgb_handle *h, uint8_t *out, void *stream);
 
+/* ---- observation wrappers: stateless batched kernels on the current device ---- */
+
+/* OneHotPartialObsWrapper.observation (wrappers.py:203-243) / FullyObsOneHotWrapper.observation
+ * (wrappers.py:340-415): cells [n_cells][3] (type, colour, state) -> out [n_cells][n_classes+n_colors+n_states]
+ * with out[type'] = out[n_classes+colour] = out[n_classes+n_colors+state] = 1.  class_map[11] maps type ->
+ * type' (NULL = identity; FullyObsOneHotWrapper's keep_classes); n_colors may be 0 (drop_color). */
+int mgb_onehot(const uint8_t *cells, uint8_t *out, int64_t n_cells, const uint8_t *class_map,
+               int32_t n_classes, int32_t n_colors, int32_t n_states, void *stream);
+
+/* FlatObsWrapper.observation (wrappers.py:528-577): out[n] = concat(float32(img[n]), mission_table[mission_idx[n]])
+ * img [N][img_bytes]; mission_table [M][mission_len] float32 (27 x maxStrLen one-hot, built on the host);
+ * mission_idx [N] (NULL = row 0 for every env); out [N][img_bytes + mission_len] float32. */
+int mgb_flat_obs(const uint8_t *img, int32_t img_bytes, const float *mission_table, int32_t mission_len,
+                 const uint8_t *mission_idx, float *out, int64_t N, void *stream);
+
 /* Synchronises `stream` and returns the sticky device error flags (then clears them):
  *   1 unknown action (reference: assert False, minigrid.py:1316-1318)   2 RNG tape exhausted
  *   4 tape value outside [low,high)    8 rejection sampling gave up (RecursionError in reset)

@@ -293,6 +293,46 @@ def main():
               dn, rw, time.time() - t0), flush=True)
 
 
+def wrapper_traces():
+    """observation wrappers: outputs of the reference's own wrapper classes
+    (FullyObsWrapper, FlatObsWrapper, FullyObsOneHotWrapper over ImgObsWrapper(FullyObsWrapper))
+    evaluated on Philox-injected trajectories."""
+    W = sys.modules["gym_minigrid.wrappers"]
+    seed = 4242
+    for env_id in ("MiniGrid-DoorKey-8x8-v0", "MiniGrid-KeyCorridorS3R3-v0", "MiniGrid-Empty-8x8-v0"):
+        idx, T = [3, 11], 40
+        full, flat, foh, acts, missions = [], [], [], [], []
+        for k, i in enumerate(idx):
+            env = R.make(env_id)
+            shim = R.PhiloxShim(seed, i, 0)
+            env.np_random = shim
+            obs = env.reset()
+            ep = 1
+            w_full = W.FullyObsWrapper(env)
+            w_flat = W.FlatObsWrapper(env)
+            w_foh = W.FullyObsOneHotWrapper(W.ImgObsWrapper(W.FullyObsWrapper(env)), flatten=True)
+            rs = np.random.RandomState(77 + k)
+            a = rs.randint(0, env.action_space.n, size=T).astype(np.uint8)
+            f1, f2, f3, ms = [], [], [], []
+            for t in range(T):
+                obs, r, d, _ = env.step(int(a[t]))
+                if d:
+                    shim.new_episode(ep)
+                    obs = env.reset()
+                    ep += 1
+                fo = w_full.observation(obs)["image"]
+                f1.append(fo.copy())
+                f2.append(np.asarray(w_flat.observation(obs)).copy())
+                f3.append(np.asarray(w_foh.observation(fo)).copy())
+                ms.append(obs["mission"])
+            full.append(np.stack(f1)); flat.append(np.stack(f2)); foh.append(np.stack(f3)); acts.append(a); missions.append(ms)
+        path = os.path.join(OUT, "wrappers_%s.npz" % short(env_id))
+        np.savez_compressed(path, env_id=env_id, seed=np.uint64(seed), env_indices=np.array(idx, np.int64),
+                            actions=np.stack(acts), full=np.stack(full), flat=np.stack(flat).astype(np.float32),
+                            full_onehot=np.stack(foh).astype(np.uint8), missions=np.array(missions))
+        print("%-50s %7.1f KB flat dtype %s" % (os.path.basename(path), os.path.getsize(path) / 1024, flat[0].dtype))
+
+
 def reward_table():
     """_reward() (minigrid.py:933-937) evaluated BY THE REFERENCE for every step_count of every
     max_steps in the registry (and 50 beyond): r_<max_steps>[k] = reward at step_count == k."""
@@ -312,6 +352,8 @@ def reward_table():
 
 
 if __name__ == "__main__":
-    if "--reward-table-only" not in sys.argv:
+    R.load_reference()
+    if "--extras-only" not in sys.argv:
         main()
     reward_table()
+    wrapper_traces()
