@@ -189,6 +189,20 @@ __device__ __noinline__ int rand_int(Rng &e, const RolloutParams &p, int low, in
     return rand_int_inl(e, p, low, high);
 }
 
+// Dynamic-Obstacles consumes ~2 draws per ball try, ~20-60 draws per step.  Instead of computing a Philox
+// block inside the (divergent) try loop, a lane pre-computes DRAW_BLOCKS consecutive blocks of its stream
+// in straight-line code (all lanes active, independent chains -> ILP) into its column of the warp's
+// staging buffer, which is idle between two observations.  word i of the window at draws[i*32].
+constexpr int DRAW_BLOCKS = 9;                    // 36 draws = 18 tries; the staging column has 36 words per lane
+__device__ __noinline__ void prefetch_draws(uint32_t *draws, uint32_t first_block, uint32_t stream, int64_t gid, uint64_t seed) {
+#pragma unroll
+    for (int j = 0; j < DRAW_BLOCKS; ++j) {
+        uint32_t o0, o1, o2, o3;
+        philox4x32_10(first_block + j, stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1, o2, o3);
+        draws[(4 * j + 0) * 32] = o0; draws[(4 * j + 1) * 32] = o1; draws[(4 * j + 2) * 32] = o2; draws[(4 * j + 3) * 32] = o3;
+    }
+}
+
 constexpr int HARD_TRY_CAP = 1 << 16;   // the reference would spin forever; we flag ERR_SAMPLING
 
 // MiniGridEnv.place_obj (minigrid.py:1003-1061).  max_tries < 0 == math.inf.
@@ -392,7 +406,7 @@ __device__ __forceinline__ double reward_formula(int steps, int max_steps) {
 
 template <int GEN>
 __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, const uint32_t *lut, int action,
-                                           double &reward, bool &done) {
+                                           double &reward, bool &done, uint32_t *draws) {
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP;
     reward = 0.0; done = false;
@@ -411,6 +425,12 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         int k = 0, tries = 0, ox = 0, oy = 0, tx = 0, ty = 0, hx = 0, hy = 0;
         uint32_t ball = 0;
         const int nob = c.n_obst;
+        uint32_t wbase = 0;                                        // draw index of draws[0]
+        if (!p.tape) {
+            wbase = rg.ndraws & ~3u;
+            prefetch_draws(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
+            rg.rblk = 0xFFFFFFFFu;
+        }
         while (k < nob) {
             if (tries == 0) {
                 obst_get(st, c, k, ox, oy);
@@ -420,9 +440,21 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
             }
             if (tries > 100) { k++; tries = 0; continue; }
             tries++;
-            const int x = rand_int_inl(rg, p, tx, hx);
-            const int y = rand_int_inl(rg, p, ty, hy);
-            if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) break;
+            int x, y;
+            if (p.tape) {
+                x = rand_int_inl(rg, p, tx, hx);
+                y = rand_int_inl(rg, p, ty, hy);
+                if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) break;
+            } else {
+                if (rg.ndraws - wbase + 2 > 4 * DRAW_BLOCKS) {     // window exhausted (rare): slide it
+                    wbase = rg.ndraws & ~3u;
+                    prefetch_draws(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
+                }
+                const uint32_t i = rg.ndraws - wbase;
+                x = tx + (int)__umulhi(draws[i * 32], (uint32_t)(hx - tx));
+                y = ty + (int)__umulhi(draws[(i + 1) * 32], (uint32_t)(hy - ty));
+                rg.ndraws += 2;
+            }
             if (cell_rd(st, x * HP + y) != CODE_EMPTY) continue;      // the ball's own cell counts: it must move
             if (x == e.ax && y == e.ay) continue;
             cell_wr(st, x * HP + y, ball);
@@ -746,8 +778,12 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
             if (p.T > 0) {
                 const int action = a_next;
                 if (t + 1 < p.T && valid) a_next = p.actions[(int64_t)(t + 1) * stride + lid];
+                if (GEN == GEN_DYNOBS) {                        // the staging block doubles as the draw window
+                    if (lane == 0) bulk_store_wait_read();
+                    __syncwarp();
+                }
                 if (valid) {
-                    transition<GEN>(st, e, rg, p, lut, action, reward, done);
+                    transition<GEN>(st, e, rg, p, lut, action, reward, done, stage_w + lane);
                     if (done && p.autoreset) { Env te = e; Rng tr = rg; generate<GEN>(st, te, tr, p); e = te; rg = tr; }
                 }
             }
