@@ -45,11 +45,19 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #ifndef MGB_PACK_IMAD_SEE
 #define MGB_PACK_IMAD_SEE 0    // see-through path: pack 4 cells -> 3 words with IMAD/IMAD.HI instead of PRMT
 #endif
+#ifndef MGB_SEE_BATCH
+#define MGB_SEE_BATCH 1       // see-through path: groups of 4 cells whose loads are issued back to back
+#endif
 #ifndef MGB_PACK_IMAD_OCC
 #define MGB_PACK_IMAD_OCC 0    // occluded path: predicated IMAD accumulation instead of LOP3+SEL+PRMT (measured slower: 157 regs)
 #endif
-constexpr int LUT_PITCH_W = 6;
-constexpr int LUT_BYTES = 256 * LUT_PITCH_W * 4;                 // 6144
+constexpr int LUT_PITCH_OCC = 6;   // occluded kernels: [x24, opaque, x24|flags<<24, -, -, -]  (LDS.64 of the first two)
+constexpr int LUT_PITCH_SEE = 3;   // see-through kernels: [x24, x24|flags<<24, -]; odd pitch -> any 32 consecutive
+                                   // codes map to 32 different banks (pitch 6 makes codes 16 apart collide,
+                                   // e.g. grey wall 57 / green goal 169 -- the two objects of Empty-8x8)
+template <bool SEE> __host__ __device__ constexpr int lut_pitch() { return SEE ? LUT_PITCH_SEE : LUT_PITCH_OCC; }
+template <bool SEE> __host__ __device__ constexpr int lut_fw() { return SEE ? 1 : 2; }     // word index of the flags word
+constexpr int LUT_BYTES = 256 * LUT_PITCH_OCC * 4;               // 6144 (sized for the larger layout)
 constexpr int AXIS_ENTRIES = 80;                                 // v in [-6, 73]: grids up to 64 + view margin
 constexpr int TABLE_BYTES = LUT_BYTES + 2 * AXIS_ENTRIES * 4;    // 6784 = 53 * 128
 
@@ -404,7 +412,7 @@ __device__ __forceinline__ double reward_formula(int steps, int max_steps) {
     return __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)max_steps)));
 }
 
-template <int GEN>
+template <int GEN, bool SEE>
 __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, const uint32_t *lut, int action,
                                            double &reward, bool &done, uint32_t *draws) {
     const DevCfg &c = p.cfg;
@@ -417,7 +425,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         const int fx0 = e.ax + dx0, fy0 = e.ay + dy0;
         uint32_t front = CODE_WALL;
         if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(st, fx0 * HP + fy0);
-        not_clear = front != CODE_EMPTY && (lut[front * LUT_PITCH_W + 2] & 0xFF) != T_GOAL;
+        not_clear = front != CODE_EMPTY && (lut[front * lut_pitch<SEE>() + lut_fw<SEE>()] & 0xFF) != T_GOAL;
         // Update obstacle positions: for each ball in list order, place_obj(top=old-(1,1), size=(3,3),
         // max_tries=100) then clear the old cell; a failed placement (RecursionError, swallowed) leaves
         // the ball where it is.  One loop iteration = one try of whichever ball the lane is on, so a
@@ -473,7 +481,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
     const int fidx = fx * HP + fy;
     const bool f_in = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
     if (f_in) fc = cell_rd(st, fidx); else rg.err |= ERR_BOUNDS;
-    const uint32_t fw = lut[fc * LUT_PITCH_W + 2];
+    const uint32_t fw = lut[fc * lut_pitch<SEE>() + lut_fw<SEE>()];
     const uint32_t ff = fw >> 24;
     const int ftype = fw & 0xFF;
     // select form of the action switch (minigrid.py:1245-1318): one rarely-taken branch for grid edits
@@ -544,13 +552,13 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 // pipe instead of the ALU pipe that bounds this kernel
 __device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
     uint32_t a;
-    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_W * 4));
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_SEE * 4));
     return lds_u32(a);
 }
 // word0 (output bytes) and word1 (opaque) of a LUT entry with one LDS.64
 __device__ __forceinline__ void lut_ld2(uint32_t lut_sa, uint32_t code, uint32_t &x, uint32_t &opq) {
     uint32_t a;
-    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_W * 4));
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_OCC * 4));
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(opq) : "r"(a) : "memory");
 }
 
@@ -590,7 +598,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
         P[k] = (int)lds_u32(pa + k * pstep4) + (int)st_sa;            // P carries the column base address
         Q[k] = (int)lds_u32(qa + (6 - k) * qstep4);
     }
-    const uint32_t own = e.carry ? lut[e.carry * LUT_PITCH_W] : (uint32_t)T_EMPTY;   // word0: 24-bit (type,colour,state)   // minigrid.py:1349-1356
+    const uint32_t own = e.carry ? lut[e.carry * lut_pitch<SEE>()] : (uint32_t)T_EMPTY;   // word0: 24-bit (type,colour,state)   // minigrid.py:1349-1356
 
     // Realignment of the record to byte offset lane*147 of the warp's 4704-byte block: word j of the record
     // times 2^s8 (one IMAD.WIDE) gives the bits that stay in block word q+j (low half) and the bits that
@@ -617,28 +625,44 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
     const uint32_t m0 = p.m0, m8 = p.m8, m16 = p.m16, m24 = p.m24;
 
     if (SEE) {
-        // no occlusion: stream cells in output order (vx-major); 4 cells (3 bytes each) -> 3 words
+        // no occlusion: stream cells in output order (vx-major); 4 cells (3 bytes each) -> 3 words.
+        // Software-pipelined by hand: a warp issues in order, so the cell loads of a whole batch
+        // (MGB_SEE_BATCH groups of 4 cells) are issued before the first dependent LUT load, and all LUT loads
+        // before the first pack -- fewer exposed LDS latencies per step.
+        constexpr int GB = MGB_SEE_BATCH;
 #pragma unroll
-        for (int g = 0; g < 13; ++g) {
-            uint32_t x[4];
+        for (int g0 = 0; g0 < 13; g0 += GB) {
+            uint32_t code[GB * 4], x[GB * 4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int ci = g * 4 + i;
-                x[i] = 0;
-                if (ci < VIEW * VIEW) {
+            for (int i = 0; i < GB * 4; ++i) {
+                const int ci = g0 * 4 + i;
+                code[i] = 0;
+                if (ci < VIEW * VIEW && ci != 3 * VIEW + 6) {
                     const int vx = ci / VIEW, vy = ci % VIEW;
-                    x[i] = (vx == 3 && vy == 6) ? own : lut_ld(lut_sa, lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa)));
+                    code[i] = lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa));
                 }
             }
+#pragma unroll
+            for (int i = 0; i < GB * 4; ++i) {
+                const int ci = g0 * 4 + i;
+                x[i] = 0;
+                if (ci < VIEW * VIEW) x[i] = (ci == 3 * VIEW + 6) ? own : lut_ld(lut_sa, code[i]);
+            }
+#pragma unroll
+            for (int gg = 0; gg < GB; ++gg) {
+                const int g = g0 + gg;
+                if (g >= 13) continue;
+                const uint32_t *y = &x[gg * 4];
 #if MGB_PACK_IMAD_SEE
-            emit(g * 3, x[1] * m24 + x[0]);                                   // x0.b0 x0.b1 x0.b2 x1.b0
-            if (g * 3 + 1 <= 37) emit(g * 3 + 1, x[2] * m16 + __umulhi(x[1], m24));   // x1.b1 x1.b2 x2.b0 x2.b1
-            if (g * 3 + 2 <= 37) emit(g * 3 + 2, x[3] * m8 + __umulhi(x[2], m16));    // x2.b2 x3.b0 x3.b1 x3.b2
+                emit(g * 3, y[1] * m24 + y[0]);                                   // x0.b0 x0.b1 x0.b2 x1.b0
+                if (g * 3 + 1 <= 37) emit(g * 3 + 1, y[2] * m16 + __umulhi(y[1], m24));   // x1.b1 x1.b2 x2.b0 x2.b1
+                if (g * 3 + 2 <= 37) emit(g * 3 + 2, y[3] * m8 + __umulhi(y[2], m16));    // x2.b2 x3.b0 x3.b1 x3.b2
 #else
-            emit(g * 3, __byte_perm(x[0], x[1], 0x4210));                              // x0.b0 x0.b1 x0.b2 x1.b0
-            if (g * 3 + 1 <= 37) emit(g * 3 + 1, __byte_perm(x[1], x[2], 0x5421));     // x1.b1 x1.b2 x2.b0 x2.b1
-            if (g * 3 + 2 <= 37) emit(g * 3 + 2, __byte_perm(x[2], x[3], 0x6542));     // x2.b2 x3.b0 x3.b1 x3.b2
+                emit(g * 3, __byte_perm(y[0], y[1], 0x4210));                              // x0.b0 x0.b1 x0.b2 x1.b0
+                if (g * 3 + 1 <= 37) emit(g * 3 + 1, __byte_perm(y[1], y[2], 0x5421));     // x1.b1 x1.b2 x2.b0 x2.b1
+                if (g * 3 + 2 <= 37) emit(g * 3 + 2, __byte_perm(y[2], y[3], 0x6542));     // x2.b2 x3.b0 x3.b1 x3.b2
 #endif
+            }
         }
     } else {
         uint32_t acc[38];
@@ -722,15 +746,15 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
     const DevCfg &c = p.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
-    uint32_t *axis = lut + 256 * LUT_PITCH_W;                                       // [2][AXIS_ENTRIES]
+    uint32_t *axis = lut + LUT_BYTES / 4;                                           // [2][AXIS_ENTRIES]
     uint8_t *stage_base = smem_raw + TABLE_BYTES;
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * STAGE_BYTES);
     uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + wpb * STAGE_BYTES) + warp * ((c.S + 1) * 32);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const uint32_t le = lut_entry(i);
-        lut[i * LUT_PITCH_W] = le & 0x00FFFFFFu;
-        lut[i * LUT_PITCH_W + 1] = (le >> 24) & F_OPAQUE;
-        lut[i * LUT_PITCH_W + 2] = le;
+        lut[i * lut_pitch<SEE>()] = le & 0x00FFFFFFu;
+        if (!SEE) lut[i * lut_pitch<SEE>() + 1] = (le >> 24) & F_OPAQUE;
+        lut[i * lut_pitch<SEE>() + lut_fw<SEE>()] = le;
     }
     for (int i = threadIdx.x; i < AXIS_ENTRIES; i += blockDim.x) {
         const int v = i - 6, wall = c.S * 128;
@@ -783,7 +807,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
                     __syncwarp();
                 }
                 if (valid) {
-                    transition<GEN>(st, e, rg, p, lut, action, reward, done, stage_w + lane);
+                    transition<GEN, SEE>(st, e, rg, p, lut, action, reward, done, stage_w + lane);
                     if (done && p.autoreset) { Env te = e; Rng tr = rg; generate<GEN>(st, te, tr, p); e = te; rg = tr; }
                 }
             }
