@@ -16,6 +16,7 @@ ERROR_BITS = {
     8: "rejection sampling gave up (reference: RecursionError)",
     16: "agent / cell index out of bounds",
     32: "unsupported cell code in set_state",
+    64: "reset without a level pool",
 }
 
 
@@ -41,6 +42,7 @@ SIGNATURES = {
     "mgb_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mgb_set_state": (C.c_int, [_P, C.c_int64, C.c_int64] + [_P] * 8),
     "mgb_get_state": (C.c_int, [_P, C.c_int64, C.c_int64] + [_P] * 8),
+    "mgb_set_level_pool": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "mgb_set_rng_tape": (C.c_int, [_P, _P, _P]),
     "mgb_full_obs": (C.c_int, [_P, _P, _P]),
     "mgb_onehot": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -42,6 +42,8 @@ struct mgb_handle {
     uint32_t *err = nullptr;
     const int32_t *tape = nullptr;
     const int64_t *tape_off = nullptr;
+    uint32_t *pool = nullptr;
+    int32_t pool_n = 0;
     int sm_count = 0;
     int blocks_per_sm = 0;
     int warps_per_block = 4;
@@ -65,6 +67,7 @@ static rollout_fn pick_kernel(const mgb_config &c) {
     case MGB_GEN_FOURROOMS: return c.see_through ? nullptr : k_rollout<GEN_FOURROOMS, false>;
     case MGB_GEN_DYNOBS: return c.see_through ? k_rollout<GEN_DYNOBS, true> : nullptr;
     case MGB_GEN_KEYCORRIDOR: return c.see_through ? nullptr : k_rollout<GEN_KEYCORRIDOR, false>;
+    case MGB_GEN_POOL: return c.see_through ? k_rollout<GEN_POOL, true> : k_rollout<GEN_POOL, false>;
     }
     return nullptr;
 }
@@ -171,7 +174,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
 int mgb_destroy(mgb_handle *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
-    cudaFree(h->state); cudaFree(h->tmpl); cudaFree(h->err);
+    cudaFree(h->state); cudaFree(h->tmpl); cudaFree(h->err); cudaFree(h->pool);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_dir); cudaFree(h->d_reward);
     for (auto &s : h->pipe) if (s) cudaStreamDestroy(s);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -223,7 +226,7 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
     p.group0 = g0; p.n_groups = ng; p.T = T; p.do_reset = do_reset; p.autoreset = h->autoreset;
     p.reset_mask = mask; p.actions = actions; p.obs = obs; p.reward = reward; p.done = done; p.dir = dir;
     p.stride = stride; p.seed = h->seed; p.env_id_base = h->env_id_base;
-    p.tape = h->tape; p.tape_off = h->tape_off; p.err = h->err;
+    p.tape = h->tape; p.tape_off = h->tape_off; p.err = h->err; p.pool = h->pool; p.pool_n = h->pool_n;
     p.m0 = 1u; p.m1 = 1u; p.m2 = 2u; p.m8 = 1u << 8; p.m16 = 1u << 16; p.m24 = 1u << 24;
     rollout_fn fn = pick_kernel(h->cfg);
     const int want = (ng + h->warps_per_block - 1) / h->warps_per_block;
@@ -247,8 +250,28 @@ int mgb_seed(mgb_handle *h, uint64_t seed) {
     return 0;
 }
 
+int mgb_set_level_pool(mgb_handle *h, int32_t n_levels, const uint8_t *grid, const uint8_t *aux, const int32_t *agent, void *stream) {
+    if (!h) return fail("null handle");
+    if (h->cfg.gen != MGB_GEN_POOL) return fail("mgb_set_level_pool: handle was not created with MGB_GEN_POOL");
+    if (n_levels < 1 || !grid || !agent) return fail("mgb_set_level_pool: need at least one level, grid and agent");
+    CUDA_OK(cudaSetDevice(h->device));
+    const int PW = h->dc.GW + 1;
+    uint32_t *np = nullptr;
+    CUDA_OK(cudaMalloc(&np, (size_t)n_levels * PW * 4));
+    const int64_t threads = (int64_t)n_levels * PW;
+    k_pack_levels<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->dc, n_levels, grid, aux, agent, np, h->err);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { cudaFree(np); return fail("k_pack_levels: %s", cudaGetErrorString(e)); }
+    CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));      // the old pool may still be in use by earlier launches
+    cudaFree(h->pool);
+    h->pool = np; h->pool_n = n_levels;
+    h->launches++;
+    return 0;
+}
+
 int mgb_reset(mgb_handle *h, const uint8_t *mask, uint8_t *obs, uint8_t *dir, void *stream) {
     if (!h) return fail("null handle");
+    if (h->cfg.gen == MGB_GEN_POOL && h->pool_n < 1) return fail("mgb_reset: no level pool (call mgb_set_level_pool first)");
     CUDA_OK(cudaSetDevice(h->device));
     return launch(h, 0, h->n_groups, 0, 1, mask, nullptr, obs, nullptr, nullptr, dir, h->n_envs, (cudaStream_t)stream, false);
 }

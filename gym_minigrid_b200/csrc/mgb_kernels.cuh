@@ -66,8 +66,8 @@ enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_K
              T_BOX = 7, T_GOAL = 8, T_LAVA = 9, T_AGENT = 10 };
 enum : int { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5, C_WHITE = 6 };
 enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
-enum : int { GEN_EMPTY = 0, GEN_DOORKEY = 1, GEN_FOURROOMS = 2, GEN_DYNOBS = 3, GEN_KEYCORRIDOR = 4 };
-enum : uint32_t { ERR_ACTION = 1, ERR_TAPE_END = 2, ERR_TAPE_RANGE = 4, ERR_SAMPLING = 8, ERR_BOUNDS = 16, ERR_CODE = 32 };
+enum : int { GEN_EMPTY = 0, GEN_DOORKEY = 1, GEN_FOURROOMS = 2, GEN_DYNOBS = 3, GEN_KEYCORRIDOR = 4, GEN_POOL = 5 };
+enum : uint32_t { ERR_ACTION = 1, ERR_TAPE_END = 2, ERR_TAPE_RANGE = 4, ERR_SAMPLING = 8, ERR_BOUNDS = 16, ERR_CODE = 32, ERR_NO_POOL = 64 };
 
 __host__ __device__ constexpr int code_of(int t, int c, int s) { return t * 21 + c * 3 + s; }
 constexpr int CODE_EMPTY = code_of(T_EMPTY, 0, 0);            // 21
@@ -125,6 +125,8 @@ struct RolloutParams {
     int64_t env_id_base;
     const int32_t *tape;
     const int64_t *tape_off;
+    const uint32_t *pool;       // GEN_POOL: [pool_n][GW + 1] words (grid words, then x | y<<8 | dir<<16)
+    int32_t pool_n;
     uint32_t *err;
     // run-time copies of 1, 1, 2, 2^8, 2^16, 2^24.  Multiplying by these (instead of literal shifts) keeps the
     // byte packing / realignment on IMAD/IMAD.HI/IMAD.WIDE, i.e. on the FMA pipe: ptxas would turn a literal
@@ -292,6 +294,20 @@ template <int GEN>
 __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p) {
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP;
+    if (GEN == GEN_POOL) {
+        // no generator on the device: draw one of the uploaded reference layouts
+        rg.episode++;
+        if (!p.tape) rg.ndraws = 0;
+        rg.rblk = 0xFFFFFFFFu;
+        e.carry = 0; e.steps = 0; e.target = 0; e.dirty = true;
+        if (p.pool_n <= 0) { rg.err |= ERR_NO_POOL; return; }
+        const int lvl = rand_int(rg, p, 0, p.pool_n);
+        const uint32_t *src = p.pool + (size_t)lvl * (c.GW + 1);
+        for (int k = 0; k < c.GW; ++k) st[k * 32] = __ldg(&src[k]);
+        const uint32_t a = __ldg(&src[c.GW]);
+        e.ax = a & 0xFF; e.ay = (a >> 8) & 0xFF; e.dir = (a >> 16) & 3;
+        return;
+    }
     // Grid(width,height) + static walls/goal
     if (GEN == GEN_DYNOBS && (e.flags & 1)) {
         // nothing but the balls ever changes in this env (actions >= 3 are clamped, dynamicobstacles.py:62-63):
@@ -997,6 +1013,36 @@ __global__ void k_get_state(const StateIO io, int full_obs) {
         int16_t *q = io.obstacles + (n * MAX_OBST + o) * 2;
         q[0] = w & 0xFF; q[1] = (w >> 8) & 0xFF; q[2] = (w >> 16) & 0xFF; q[3] = (w >> 24) & 0xFF;
     }
+}
+
+// level pool upload: one thread per (level, pool word); same cell packing as k_set_state
+__global__ void k_pack_levels(DevCfg c, int n_levels, const uint8_t *__restrict__ grid, const uint8_t *__restrict__ aux,
+                              const int32_t *__restrict__ agent, uint32_t *__restrict__ pool, uint32_t *err_out) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int PW = c.GW + 1;
+    const int64_t lvl = tid / PW;
+    const int k = (int)(tid % PW);
+    if (lvl >= n_levels) return;
+    uint32_t err = 0, w = 0;
+    const int cells = c.W * c.H, HW = c.HP >> 2;
+    if (k < c.GW) {
+        const int x = k / HW, y0 = (k % HW) * 4;
+        for (int b = 0; b < 4; ++b) {
+            int code = CODE_EMPTY;
+            if (y0 + b < c.H) {
+                const size_t idx = (size_t)lvl * cells + x * c.H + y0 + b;
+                const uint8_t *g = grid + idx * 3;
+                code = encode_cell(g[0], g[1], g[2], aux ? aux[idx] : 0, err);
+            }
+            w |= (uint32_t)code << (8 * b);
+        }
+    } else {
+        const int32_t *a = agent + lvl * 3;
+        if (a[0] < 0 || a[0] >= c.W || a[1] < 0 || a[1] >= c.H || a[2] < 0 || a[2] > 3) err |= ERR_BOUNDS;
+        w = (uint32_t)(a[0] & 0xFF) | ((uint32_t)(a[1] & 0xFF) << 8) | ((uint32_t)(a[2] & 3) << 16);
+    }
+    pool[lvl * PW + k] = w;
+    if (err) atomicOr(err_out, err);
 }
 
 // ------------------------------------------------------------------------------------------

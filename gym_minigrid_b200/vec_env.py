@@ -46,6 +46,8 @@ class MissionBatch:
 
     def __getitem__(self, i):
         tmpl = self._env._mission
+        if self._env._pool_missions is not None:        # level-pool env with per-level mission strings
+            return self._env._pool_missions[int(self._env.level_index(i, 1)[0])]
         if "%s" not in tmpl:
             return tmpl
         if self._targets is None:          # KeyCorridor: "pick up the <colour> <type>" (keycorridor.py:49)
@@ -59,6 +61,18 @@ class MissionBatch:
 
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _philox4x32_10(ctr, key):
+    """host copy of the device RNG (Salmon et al., SC'11); only used to map envs to pool levels lazily"""
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    M = 0xFFFFFFFF
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c0, 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & M, p1 & M, ((p0 >> 32) ^ c3 ^ k1) & M, p0 & M
+        k0, k1 = (k0 + 0x9E3779B9) & M, (k1 + 0xBB67AE85) & M
+    return c0, c1, c2, c3
 
 
 class VecMiniGridEnv:
@@ -94,6 +108,9 @@ class VecMiniGridEnv:
                                       int(env_id_base), C.byref(h)))
         self._h = h
         self._seed = seed
+        self._env_id_base = int(env_id_base)
+        self._pool_n = 0
+        self._pool_missions = None
         if not autoreset:
             _lib.check(self._L.mgb_set_autoreset(self._h, 0))
         self._tape = None
@@ -241,6 +258,31 @@ class VecMiniGridEnv:
         _lib.check(self._L.mgb_set_state(self._h, first, count, *args, self._stream()))
         torch.cuda.current_stream(self.device).synchronize()     # ts goes out of scope
         self.check_errors()
+
+    def set_level_pool(self, grid, agent, aux=None, missions=None):
+        """Level-pool mode: upload K reference-generated layouts; reset / auto-reset of
+        env e in episode k picks level mulhi32(philox(seed, e, k).word0, K)."""
+        g = torch.as_tensor(np.ascontiguousarray(grid, dtype=np.uint8)).to(self.device)
+        K = g.shape[0]
+        assert tuple(g.shape[1:]) == (self.width, self.height, 3), g.shape
+        a = torch.as_tensor(np.ascontiguousarray(np.asarray(agent)[:, :3], dtype=np.int32)).to(self.device)
+        x = None if aux is None else torch.as_tensor(np.ascontiguousarray(aux, dtype=np.uint8)).to(self.device)
+        _lib.check(self._L.mgb_set_level_pool(self._h, K, _ptr(g), _ptr(x), _ptr(a), self._stream()))
+        self._pool_n = K
+        self._pool_missions = list(missions) if missions is not None else None
+        self.check_errors()
+
+    def level_index(self, first=0, count=None):
+        """which pool level each env is currently playing (recomputed from the Philox stream on the host)"""
+        rng = self.get_state(("rng",), first, count)["rng"].cpu().numpy().view(np.uint32)
+        seed = int(self._seed) & (2 ** 64 - 1)
+        out = np.zeros(len(rng), np.int64)
+        for i, (ep, _) in enumerate(rng):
+            gid = self._env_id_base + first + i
+            w0 = _philox4x32_10((0, (int(ep) - 1) & 0xFFFFFFFF, gid & 0xFFFFFFFF, (gid >> 32) & 0xFFFFFFFF),
+                                (seed & 0xFFFFFFFF, seed >> 32))[0]
+            out[i] = (w0 * self._pool_n) >> 32
+        return out
 
     def set_rng_tape(self, draws, offsets):
         """RNG-tape parity mode (SURVEY §8c mode 2)."""

@@ -37,7 +37,10 @@ enum {
     MGB_GEN_DOORKEY = 1,      /* envs/doorkey.py:15-44 */
     MGB_GEN_FOURROOMS = 2,    /* envs/fourrooms.py:19-69 */
     MGB_GEN_DYNOBS = 3,       /* envs/dynamicobstacles.py:35-89 */
-    MGB_GEN_KEYCORRIDOR = 4   /* roomgrid.py:118-359 + envs/keycorridor.py:26-59 */
+    MGB_GEN_KEYCORRIDOR = 4,  /* roomgrid.py:118-359 + envs/keycorridor.py:26-59 */
+    MGB_GEN_POOL = 5          /* no on-device generator: reset draws one of the uploaded levels (mgb_set_level_pool).
+                                 For envs whose step() is the base MiniGridEnv.step: envs/{crossing,lavagap,multiroom,
+                                 distshift,simpleroom}.py -- SURVEY §8(f) rank 2 */
 };
 
 /* static per-env-id configuration: what the reference bakes into constructor kwargs
@@ -116,6 +119,13 @@ int mgb_get_state(mgb_handle *h, int64_t first, int64_t count, uint8_t *grid, ui
                   int32_t *agent, uint8_t *carrying, int16_t *obstacles, uint8_t *target,
                   uint32_t *rng, void *stream);
 
+/* Level pool for MGB_GEN_POOL handles: n_levels layouts in the reference's encoding (e.g. snapshots of
+ * reference envs after reset()).  grid [K][W][H][3], aux [K][W][H] (may be NULL), agent [K][3] int32 = x,y,dir.
+ * Device pointers; the pool is copied, the buffers may be freed once `stream` has passed the call.
+ * reset / auto-reset of env e in episode k uses level  mulhi32(philox(seed, e, k).word0, K). */
+int mgb_set_level_pool(mgb_handle *h, int32_t n_levels, const uint8_t *grid, const uint8_t *aux,
+                       const int32_t *agent, void *stream);
+
 /* RNG-tape parity mode: env i consumes draws[offsets[i] ...) in order instead of Philox
  * (values are final randint results).  NULL switches back to Philox.  Device pointers,
  * offsets has N+1 entries. */
@@ -143,7 +153,7 @@ int mgb_flat_obs(const uint8_t *img, int32_t img_bytes, const float *mission_tab
 /* Synchronises `stream` and returns the sticky device error flags (then clears them):
  *   1 unknown action (reference: assert False, minigrid.py:1316-1318)   2 RNG tape exhausted
  *   4 tape value outside [low,high)    8 rejection sampling gave up (RecursionError in reset)
- *  16 agent/cell index out of bounds   32 unsupported cell code in set_state */
+ *  16 agent/cell index out of bounds   32 unsupported cell code in set_state   64 reset without a level pool */
 int mgb_error_flags(mgb_handle *h, void *stream, uint32_t *flags_host);
 
 /* number of kernels this handle has launched so far */

@@ -47,7 +47,11 @@ def config_of(env):
         if klass.__name__ in GEN_OF_CLASS:
             gen = GEN_OF_CLASS[klass.__name__]
             break
-    assert gen is not None, type(env)
+    if gen is None:
+        # no on-device generator for this class: level-pool mode, only legal when step() is the base step
+        mg = sys.modules["gym_minigrid.minigrid"]
+        assert type(env).step is mg.MiniGridEnv.step, "%s overrides step(): not a level-pool env" % type(env).__name__
+        gen = 5
     return dict(
         gen=gen, width=env.width, height=env.height, max_steps=env.max_steps,
         see_through=int(bool(env.see_through_walls)), n_actions=env.action_space.n,
@@ -333,6 +337,69 @@ def wrapper_traces():
         print("%-50s %7.1f KB flat dtype %s" % (os.path.basename(path), os.path.getsize(path) / 1024, flat[0].dtype))
 
 
+def pool_traces():
+    """Level-pool mode: envs whose step() is the base MiniGridEnv.step.  K layouts are
+    generated BY THE REFERENCE (its own _gen_grid and RNG); the trace restores the layout that the shared
+    Philox pick selects at every (auto-)reset and steps the unmodified reference."""
+    import copy
+    seed, K = 777, 6
+    for env_id, T, n_env in (("MiniGrid-LavaCrossingS9N2-v0", 700, 3), ("MiniGrid-SimpleCrossingS11N5-v0", 600, 2),
+                             ("MiniGrid-LavaGapS7-v1", 500, 3), ("MiniGrid-MultiRoom-N4-S5-v0", 400, 3),
+                             ("MiniGrid-DistShift2-v0", 500, 2), ("MiniGrid-SimpleRoom-v0", 300, 2)):
+        env = R.make(env_id)
+        cfg = config_of(env)
+        levels = []
+        for k in range(K):
+            env.seed(100 + k)
+            obs = env.reset()
+            s = R.snapshot(env)
+            levels.append(dict(grid=s["grid"], aux=s["aux"], agent=s["agent"][:3].copy(), mission=obs["mission"],
+                               obj=(copy.deepcopy(env.unwrapped.grid), tuple(int(v) for v in env.unwrapped.agent_pos), int(env.unwrapped.agent_dir))))
+
+        def restore(lvl):
+            u = env.unwrapped
+            env.reset()
+            g, pos, d = levels[lvl]["obj"]
+            u.grid = copy.deepcopy(g)
+            u.agent_pos = np.array(pos)
+            u.agent_dir = d
+            u.carrying = None
+            u.step_count = 0
+            return u.gen_obs()
+
+        idx = [4, 90, (1 << 33) + 5][:n_env]
+        tr = dict(obs=[], dir=[], reward=[], done=[], actions=[], obs0=[], dir0=[], lvl=[], grid_end=[], agent_end=[])
+        for k, i in enumerate(idx):
+            pick = R.PhiloxShim(seed, i, 0)
+            lv = [pick.randint(0, K)]
+            obs = restore(lv[-1])
+            rs = np.random.RandomState(500 + k)
+            a = rs.randint(0, 7, size=T).astype(np.uint8)
+            O, D, RW, DN = [obs["image"].copy()], [obs["direction"]], [], []
+            ep = 1
+            for t in range(T):
+                obs, r, d, _ = env.step(int(a[t]))
+                if d:
+                    pick.new_episode(ep)
+                    ep += 1
+                    lv.append(pick.randint(0, K))
+                    obs = restore(lv[-1])
+                O.append(obs["image"].copy()); D.append(obs["direction"]); RW.append(float(r)); DN.append(int(d))
+            s = R.snapshot(env)
+            tr["obs0"].append(O[0]); tr["dir0"].append(D[0]); tr["obs"].append(np.stack(O[1:])); tr["dir"].append(np.array(D[1:], np.uint8))
+            tr["reward"].append(np.array(RW)); tr["done"].append(np.array(DN, np.uint8)); tr["actions"].append(a)
+            tr["lvl"].append(np.array(lv + [-1] * (T + 1 - len(lv)), np.int32)); tr["grid_end"].append(s["grid"]); tr["agent_end"].append(s["agent"])
+        path = os.path.join(OUT, "pool_%s.npz" % short(env_id).replace("-v1", "_v1"))
+        np.savez_compressed(path, env_id=env_id, seed=np.uint64(seed), env_indices=np.array(idx, np.int64),
+                            cfg_keys=np.array(list(cfg.keys())), cfg_vals=np.array(list(cfg.values()), np.int32),
+                            level_grid=np.stack([l["grid"] for l in levels]), level_aux=np.stack([l["aux"] for l in levels]),
+                            level_agent=np.stack([l["agent"] for l in levels]).astype(np.int32),
+                            level_mission=np.array([l["mission"] for l in levels]),
+                            **{k: np.stack(v) for k, v in tr.items()})
+        print("%-50s %7.1f KB episodes=%s rewards=%d" % (os.path.basename(path), os.path.getsize(path) / 1024,
+              [int((l >= 0).sum()) for l in tr["lvl"]], sum(int((r != 0).sum()) for r in tr["reward"])))
+
+
 def reward_table():
     """_reward() (minigrid.py:933-937) evaluated BY THE REFERENCE for every step_count of every
     max_steps in the registry (and 50 beyond): r_<max_steps>[k] = reward at step_count == k."""
@@ -357,3 +424,4 @@ if __name__ == "__main__":
         main()
     reward_table()
     wrapper_traces()
+    pool_traces()

@@ -208,6 +208,7 @@ typedef struct {
 } Room;
 
 /* ---- MiniGridEnv (minigrid.py:720-1381) --------------------------------- */
+struct orc_vec;
 typedef struct {
     orc_config cfg;
     Grid grid;
@@ -222,6 +223,7 @@ typedef struct {
     const int32_t *tape; int64_t tape_len;
     int err;
     Room rooms[MAXR][MAXR];    /* room_grid[j][i] */
+    const struct orc_vec *owner;
 } Env;
 
 static int rand_int(Env *e, int low, int high) {   /* minigrid.py:939-944 */
@@ -468,6 +470,7 @@ static void gen_keycorridor(Env *e) {
     e->target_type = T_BALL; e->target_color = (uint8_t)obj_color;
 }
 
+static void gen_pool(Env *e);
 /* reset (minigrid.py:831-858) */
 static void gen_obs(Env *e, uint8_t *obs, uint8_t *dir);
 static void env_reset(Env *e, uint8_t *obs, uint8_t *dir) {
@@ -482,6 +485,7 @@ static void env_reset(Env *e, uint8_t *obs, uint8_t *dir) {
     case ORC_GEN_FOURROOMS: gen_fourrooms(e); break;
     case ORC_GEN_DYNOBS: gen_dynobs(e); break;
     case ORC_GEN_KEYCORRIDOR: gen_keycorridor(e); break;
+    case ORC_GEN_POOL: gen_pool(e); break;
     }
     e->carrying = NONE;
     e->step_count = 0;
@@ -617,7 +621,41 @@ struct orc_vec {
     int n;
     Env *envs;
     Obj *cells;
+    int pool_n;          /* ORC_GEN_POOL */
+    Obj *pool_cells;     /* [pool_n][W*H], index j*W+i like Grid */
+    int *pool_agent;     /* [pool_n][3] */
 };
+
+static void gen_pool(Env *e) {
+    const struct orc_vec *v = e->owner;
+    if (!v || v->pool_n < 1) { e->err |= 64; return; }
+    const int lvl = rand_int(e, 0, v->pool_n);
+    const size_t cells = (size_t)e->grid.w * e->grid.h;
+    memcpy(e->grid.c, v->pool_cells + (size_t)lvl * cells, cells * sizeof(Obj));
+    e->ax = v->pool_agent[lvl * 3]; e->ay = v->pool_agent[lvl * 3 + 1]; e->adir = v->pool_agent[lvl * 3 + 2];
+    e->has_agent = 1;
+}
+
+int orc_vec_set_level_pool(orc_vec *v, int32_t n_levels, const uint8_t *grid, const uint8_t *aux, const int32_t *agent) {
+    const int W = v->cfg.width, H = v->cfg.height;
+    const size_t cells = (size_t)W * H;
+    free(v->pool_cells); free(v->pool_agent);
+    v->pool_cells = (Obj *)calloc((size_t)n_levels * cells, sizeof(Obj));
+    v->pool_agent = (int *)calloc((size_t)n_levels * 3, sizeof(int));
+    v->pool_n = n_levels;
+    for (int l = 0; l < n_levels; l++) {
+        for (int i = 0; i < W; i++)
+            for (int j = 0; j < H; j++) {
+                const size_t ci = ((size_t)l * W + i) * H + j;
+                Obj o;
+                if (obj_decode(grid[ci * 3], grid[ci * 3 + 1], grid[ci * 3 + 2], &o)) { snprintf(g_err, sizeof g_err, "orc_vec_set_level_pool: bad cell code"); return -1; }
+                if (o.has && o.type == T_GOAL) { o.color = grid[ci * 3 + 1]; if (aux && (aux[ci] & 1)) { o.toggletimes = 0; o.overlap = 1; } }
+                v->pool_cells[(size_t)l * cells + (size_t)j * W + i] = o;
+            }
+        for (int k = 0; k < 3; k++) v->pool_agent[l * 3 + k] = agent[l * 3 + k];
+    }
+    return 0;
+}
 
 orc_vec *orc_vec_create(const orc_config *cfg, uint64_t seed, int64_t env0, int32_t n) {
     if (cfg->width < 3 || cfg->height < 3 || cfg->width > 64 || cfg->height > 64 || n < 0 ||
@@ -632,11 +670,11 @@ orc_vec *orc_vec_create(const orc_config *cfg, uint64_t seed, int64_t env0, int3
     for (int i = 0; i < n; i++) {
         Env *e = &v->envs[i];
         e->cfg = *cfg; e->grid.w = cfg->width; e->grid.h = cfg->height; e->grid.c = v->cells + (size_t)i * cells;
-        e->env_id = env0 + i; e->seed = seed;
+        e->env_id = env0 + i; e->seed = seed; e->owner = v;
     }
     return v;
 }
-void orc_vec_destroy(orc_vec *v) { if (!v) return; free(v->envs); free(v->cells); free(v); }
+void orc_vec_destroy(orc_vec *v) { if (!v) return; free(v->envs); free(v->cells); free(v->pool_cells); free(v->pool_agent); free(v); }
 
 int orc_vec_set_tape(orc_vec *v, const int32_t *draws, const int64_t *offsets) {
     for (int i = 0; i < v->n; i++) {

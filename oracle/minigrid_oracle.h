@@ -26,7 +26,8 @@ enum {
     ORC_GEN_DOORKEY = 1,     /* envs/doorkey.py:15-44        */
     ORC_GEN_FOURROOMS = 2,   /* envs/fourrooms.py:19-69      */
     ORC_GEN_DYNOBS = 3,      /* envs/dynamicobstacles.py:35-58 */
-    ORC_GEN_KEYCORRIDOR = 4  /* roomgrid.py:118-169 + envs/keycorridor.py:26-49 */
+    ORC_GEN_KEYCORRIDOR = 4, /* roomgrid.py:118-169 + envs/keycorridor.py:26-49 */
+    ORC_GEN_POOL = 5         /* reset = one of the uploaded reference layouts (base MiniGridEnv.step only) */
 };
 
 typedef struct {
@@ -51,6 +52,10 @@ typedef struct orc_vec orc_vec;
 orc_vec *orc_vec_create(const orc_config *cfg, uint64_t seed, int64_t env0, int32_t n);
 void orc_vec_destroy(orc_vec *v);
 void orc_set_threads(int nthreads);
+
+/* level pool for ORC_GEN_POOL: grid [K][W][H][3], aux [K][W][H] or NULL, agent [K][3] = x,y,dir.
+ * reset picks level rand_int(0, K) (first draw of the episode's stream). */
+int orc_vec_set_level_pool(orc_vec *v, int32_t n_levels, const uint8_t *grid, const uint8_t *aux, const int32_t *agent);
 
 /* RNG tape (parity mode 2): draws[offsets[i] .. offsets[i+1]) are the raw randint
  * results env i will consume, in order.  NULL disables. */

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libminigrid_oracle.so")
 
-GEN_EMPTY, GEN_DOORKEY, GEN_FOURROOMS, GEN_DYNOBS, GEN_KEYCORRIDOR = range(5)
+GEN_EMPTY, GEN_DOORKEY, GEN_FOURROOMS, GEN_DYNOBS, GEN_KEYCORRIDOR, GEN_POOL = range(6)
 OBS_BYTES = 147
 MAX_OBST = 8
 
@@ -43,6 +43,7 @@ def lib():
         L.orc_vec_destroy.argtypes = [C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_int]
         L.orc_vec_set_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_vec_set_level_pool.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_vec_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 3
         L.orc_vec_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.orc_vec_rollout.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int] + [C.c_void_p] * 4
@@ -93,6 +94,13 @@ class OracleVec:
     def set_tape(self, draws, offsets):
         self._tape = (np.ascontiguousarray(draws, np.int32), np.ascontiguousarray(offsets, np.int64))
         self._chk(self._L.orc_vec_set_tape(self._h, _p(self._tape[0]), _p(self._tape[1])))
+
+    def set_level_pool(self, grid, aux, agent):
+        g = np.ascontiguousarray(grid, np.uint8)
+        K = g.shape[0]
+        a = None if aux is None else np.ascontiguousarray(aux, np.uint8)
+        ag = np.ascontiguousarray(np.asarray(agent)[:, :3], np.int32)
+        self._chk(self._L.orc_vec_set_level_pool(self._h, K, _p(g), _p(a), _p(ag)))
 
     def reset(self, mask=None):
         obs = np.zeros((self.n, 7, 7, 3), np.uint8)

@@ -25,13 +25,14 @@ def header_functions():
 def test_registry_contract():
     for i in HEADLINE:
         assert i in mgb.env_list
-    assert len(mgb.env_list) == len(set(mgb.env_list)) == 24
+    assert len(mgb.env_list) == len(set(mgb.env_list)) == 46      # 24 with device generators + 22 level-pool ids
     with pytest.raises(AssertionError):            # register.py:12  id must start with "MiniGrid-"
         mgb.register("Foo-v0", "gym_minigrid.envs:EmptyEnv")
     with pytest.raises(AssertionError):            # register.py:13  ids are unique
         mgb.register("MiniGrid-Empty-8x8-v0", "gym_minigrid.envs:EmptyEnv")
     with pytest.raises(KeyError):
-        mgb.spec("MiniGrid-MultiRoom-N6-v0")       # out of scope: loud, not silent
+        mgb.spec("MiniGrid-Fetch-8x8-N3-v0")       # out of scope (custom step hook): loud, not silent
+    assert mgb.spec("MiniGrid-MultiRoom-N6-v0")["config"]["gen"] == 5     # level-pool id
     c = mgb.spec("MiniGrid-Dynamic-Obstacles-16x16-v0")["config"]
     assert (c["n_actions"], c["n_obstacles"], c["reward_range"], c["lava_v1"]) == (3, 8, (-1, 1), 1)
     assert mgb.spec("MiniGrid-KeyCorridorS6R3-v0")["config"]["max_steps"] == 1080
