@@ -44,6 +44,8 @@ struct mgb_handle {
     const int64_t *tape_off = nullptr;
     uint32_t *pool = nullptr;
     int32_t pool_n = 0;
+    int view = 7;
+    int obs_bytes = OBS_BYTES;
     int sm_count = 0;
     int blocks_per_sm = 0;
     int warps_per_block = 4;
@@ -60,14 +62,26 @@ struct mgb_handle {
 };
 
 typedef void (*rollout_fn)(const RolloutParams);
-static rollout_fn pick_kernel(const mgb_config &c) {
+template <int V>
+static rollout_fn pick_kernel_v(const mgb_config &c) {
     switch (c.gen) {
-    case MGB_GEN_EMPTY: return c.see_through ? k_rollout<GEN_EMPTY, true> : k_rollout<GEN_EMPTY, false>;
-    case MGB_GEN_DOORKEY: return c.see_through ? nullptr : k_rollout<GEN_DOORKEY, false>;
-    case MGB_GEN_FOURROOMS: return c.see_through ? nullptr : k_rollout<GEN_FOURROOMS, false>;
-    case MGB_GEN_DYNOBS: return c.see_through ? k_rollout<GEN_DYNOBS, true> : nullptr;
-    case MGB_GEN_KEYCORRIDOR: return c.see_through ? nullptr : k_rollout<GEN_KEYCORRIDOR, false>;
-    case MGB_GEN_POOL: return c.see_through ? k_rollout<GEN_POOL, true> : k_rollout<GEN_POOL, false>;
+    case MGB_GEN_EMPTY: return c.see_through ? k_rollout<GEN_EMPTY, true, V> : k_rollout<GEN_EMPTY, false, V>;
+    case MGB_GEN_DOORKEY: return c.see_through ? nullptr : k_rollout<GEN_DOORKEY, false, V>;
+    case MGB_GEN_FOURROOMS: return c.see_through ? nullptr : k_rollout<GEN_FOURROOMS, false, V>;
+    case MGB_GEN_DYNOBS: return c.see_through ? k_rollout<GEN_DYNOBS, true, V> : nullptr;
+    case MGB_GEN_KEYCORRIDOR: return c.see_through ? nullptr : k_rollout<GEN_KEYCORRIDOR, false, V>;
+    case MGB_GEN_POOL: return c.see_through ? k_rollout<GEN_POOL, true, V> : k_rollout<GEN_POOL, false, V>;
+    }
+    return nullptr;
+}
+static int view_of(const mgb_config &c) { return c.agent_view_size == 0 ? 7 : c.agent_view_size; }
+static rollout_fn pick_kernel(const mgb_config &c) {
+    switch (view_of(c)) {
+    case 3: return pick_kernel_v<3>(c);
+    case 5: return pick_kernel_v<5>(c);
+    case 7: return pick_kernel_v<7>(c);
+    case 9: return pick_kernel_v<9>(c);
+    case 11: return pick_kernel_v<11>(c);
     }
     return nullptr;
 }
@@ -122,6 +136,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     }
     if (c.gen == MGB_GEN_DYNOBS && c.n_actions != 3) return fail("mgb_create: Dynamic-Obstacles has 3 actions");
     if (c.gen != MGB_GEN_DYNOBS && c.n_actions != 7) return fail("mgb_create: n_actions must be 7");
+    { const int v = view_of(c); if (v != 3 && v != 5 && v != 7 && v != 9 && v != 11) return fail("mgb_create: agent_view_size %d not built (3, 5, 7, 9, 11)", v); }
     rollout_fn fn = pick_kernel(c);
     if (!fn) return fail("mgb_create: unsupported (gen=%d, see_through=%d) combination", c.gen, c.see_through);
     int ndev = 0;
@@ -136,6 +151,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     if (!h) return fail("mgb_create: out of host memory");
     h->cfg = c; h->device = device; h->n_envs = num_envs; h->seed = seed; h->env_id_base = env_id_base;
     h->n_groups = (int32_t)((num_envs + 31) / 32);
+    h->view = view_of(c); h->obs_bytes = obs_bytes(h->view);
     DevCfg &d = h->dc;
     d.gen = c.gen; d.W = c.width; d.H = c.height; d.max_steps = c.max_steps; d.see_through = c.see_through;
     d.n_actions = c.n_actions; d.n_obst = c.n_obstacles; d.room_size = c.room_size; d.num_rows = c.num_rows;
@@ -148,7 +164,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     auto cleanup = [&](int rc) { mgb_destroy(h); return rc; };
     // warps per CTA: whatever keeps the most warps resident per SM (shared memory is the limiter for the
     // larger grids: each warp needs its 32-env state block + a 4704-byte staging block)
-    const size_t per_warp = STAGE_BYTES + (size_t)(d.S + 1) * 32 * 4;
+    const size_t per_warp = (size_t)stage_bytes(h->view) + (size_t)(d.S + 1) * 32 * 4;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) != cudaSuccess)
         return cleanup(fail("mgb_create: cannot opt in to %zu bytes of shared memory", (size_t)prop.sharedMemPerBlockOptin));
     int best_warps = 0;
@@ -299,7 +315,7 @@ int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host,
     if (!h->pipe[0]) {
         for (auto &s : h->pipe) CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         CUDA_OK(cudaMalloc(&h->d_actions, N));
-        CUDA_OK(cudaMalloc(&h->d_obs, (size_t)N * OBS_BYTES));
+        CUDA_OK(cudaMalloc(&h->d_obs, (size_t)N * h->obs_bytes));
         CUDA_OK(cudaMalloc(&h->d_reward, (size_t)N * 8));
         CUDA_OK(cudaMalloc(&h->d_done, N));
         CUDA_OK(cudaMalloc(&h->d_dir, N));
@@ -316,7 +332,7 @@ int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host,
         CUDA_OK(cudaMemcpyAsync(h->d_actions + e0, actions_host + e0, ne, cudaMemcpyHostToDevice, s));
         if (launch(h, g0, ng, 1, 0, nullptr, h->d_actions, obs_host ? h->d_obs : nullptr, reward_host ? h->d_reward : nullptr,
                    done_host ? h->d_done : nullptr, dir_host ? h->d_dir : nullptr, N, s, false)) return -1;
-        if (obs_host) CUDA_OK(cudaMemcpyAsync(obs_host + e0 * OBS_BYTES, h->d_obs + e0 * OBS_BYTES, (size_t)ne * OBS_BYTES, cudaMemcpyDeviceToHost, s));
+        if (obs_host) CUDA_OK(cudaMemcpyAsync(obs_host + e0 * h->obs_bytes, h->d_obs + e0 * h->obs_bytes, (size_t)ne * h->obs_bytes, cudaMemcpyDeviceToHost, s));
         if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host + e0, h->d_reward + e0, (size_t)ne * 8, cudaMemcpyDeviceToHost, s));
         if (done_host) CUDA_OK(cudaMemcpyAsync(done_host + e0, h->d_done + e0, ne, cudaMemcpyDeviceToHost, s));
         if (dir_host) CUDA_OK(cudaMemcpyAsync(dir_host + e0, h->d_dir + e0, ne, cudaMemcpyDeviceToHost, s));

@@ -23,10 +23,13 @@
 
 namespace mgb {
 
-constexpr int VIEW = 7;
+constexpr int VIEW = 7;                           // default agent_view_size
 constexpr int OBS_BYTES = 147;
 constexpr int GROUP = 32;
 constexpr int STAGE_BYTES = GROUP * OBS_BYTES;   // 4704 = 294 * 16
+// the kernel is a template on the (odd) view size V: record = 3*V*V bytes, staging block = 32 records
+__host__ __device__ constexpr int obs_bytes(int V) { return 3 * V * V; }
+__host__ __device__ constexpr int stage_bytes(int V) { return GROUP * 3 * V * V; }      // multiple of 16 for every V
 constexpr int MAX_WARPS_PER_BLOCK = 8;           // the host picks 2..8 warps per CTA to maximise resident warps/SM
 constexpr int MAX_THREADS = MAX_WARPS_PER_BLOCK * 32;
 constexpr int MAX_OBST = 8;
@@ -58,8 +61,9 @@ constexpr int LUT_PITCH_SEE = 3;   // see-through kernels: [x24, x24|flags<<24, 
 template <bool SEE> __host__ __device__ constexpr int lut_pitch() { return SEE ? LUT_PITCH_SEE : LUT_PITCH_OCC; }
 template <bool SEE> __host__ __device__ constexpr int lut_fw() { return SEE ? 1 : 2; }     // word index of the flags word
 constexpr int LUT_BYTES = 256 * LUT_PITCH_OCC * 4;               // 6144 (sized for the larger layout)
-constexpr int AXIS_ENTRIES = 80;                                 // v in [-6, 73]: grids up to 64 + view margin
-constexpr int TABLE_BYTES = LUT_BYTES + 2 * AXIS_ENTRIES * 4;    // 6784 = 53 * 128
+constexpr int AXIS_ENTRIES = 88;                                 // v in [-(V-1), 64+V-2] for V <= 11: index v + AXIS_BIAS
+constexpr int AXIS_BIAS = 10;
+constexpr int TABLE_BYTES = LUT_BYTES + 2 * AXIS_ENTRIES * 4;    // 6848
 
 // minigrid.py:40-52 / 27-35 / 57-61
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
@@ -203,10 +207,12 @@ __device__ __noinline__ int rand_int(Rng &e, const RolloutParams &p, int low, in
 // block inside the (divergent) try loop, a lane pre-computes DRAW_BLOCKS consecutive blocks of its stream
 // in straight-line code (all lanes active, independent chains -> ILP) into its column of the warp's
 // staging buffer, which is idle between two observations.  word i of the window at draws[i*32].
-constexpr int DRAW_BLOCKS = 9;                    // 36 draws = 18 tries; the staging column has 36 words per lane
+// blocks that fit the staging column of a lane (3*V*V/4 words): 9 blocks = 36 draws = 18 tries for V = 7
+__host__ __device__ constexpr int draw_blocks(int V) { return (3 * V * V / 4) / 4 < 9 ? (3 * V * V / 4) / 4 : 9; }
+template <int NB>
 __device__ __noinline__ void prefetch_draws(uint32_t *draws, uint32_t first_block, uint32_t stream, int64_t gid, uint64_t seed) {
 #pragma unroll
-    for (int j = 0; j < DRAW_BLOCKS; ++j) {
+    for (int j = 0; j < NB; ++j) {
         uint32_t o0, o1, o2, o3;
         philox4x32_10(first_block + j, stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1, o2, o3);
         draws[(4 * j + 0) * 32] = o0; draws[(4 * j + 1) * 32] = o1; draws[(4 * j + 2) * 32] = o2; draws[(4 * j + 3) * 32] = o3;
@@ -428,7 +434,7 @@ __device__ __forceinline__ double reward_formula(int steps, int max_steps) {
     return __dsub_rn(1.0, __dmul_rn(0.9, __ddiv_rn((double)steps, (double)max_steps)));
 }
 
-template <int GEN, bool SEE>
+template <int GEN, bool SEE, int V>
 __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, const uint32_t *lut, int action,
                                            double &reward, bool &done, uint32_t *draws) {
     const DevCfg &c = p.cfg;
@@ -452,7 +458,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         uint32_t wbase = 0;                                        // draw index of draws[0]
         if (!p.tape) {
             wbase = rg.ndraws & ~3u;
-            prefetch_draws(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
+            prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
             rg.rblk = 0xFFFFFFFFu;
         }
         while (k < nob) {
@@ -470,9 +476,9 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
                 y = rand_int_inl(rg, p, ty, hy);
                 if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) break;
             } else {
-                if (rg.ndraws - wbase + 2 > 4 * DRAW_BLOCKS) {     // window exhausted (rare): slide it
+                if (rg.ndraws - wbase + 2 > 4 * draw_blocks(V)) {  // window exhausted (rare): slide it
                     wbase = rg.ndraws & ~3u;
-                    prefetch_draws(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
+                    prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
                 }
                 const uint32_t i = rg.ndraws - wbase;
                 x = tx + (int)__umulhi(draws[i * 32], (uint32_t)(hx - tx));
@@ -541,10 +547,10 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
 // ------------------------------------------------------------------------------------------
 // observation: gen_obs_grid + Grid.encode (minigrid.py:1327-1381, 571-594)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t rev7(uint32_t v) { return __brev(v) >> 25; }
+template <int V> __device__ __forceinline__ uint32_t revv(uint32_t v) { return __brev(v) >> (32 - V); }
 // cells reachable towards higher bits through runs of transparent cells (one sweep of
 // process_vis, minigrid.py:624-635) as a carry chain: ((v&t)+t)^t marks [lowest seed .. run end+1]
-__device__ __forceinline__ uint32_t flood_up(uint32_t v, uint32_t t) { return ((((v & t) + t) ^ t) | v) & 0x7Fu; }
+template <int V> __device__ __forceinline__ uint32_t flood_up(uint32_t v, uint32_t t) { return ((((v & t) + t) ^ t) | v) & ((1u << V) - 1u); }
 
 // insert the 3 low bytes of x at byte offset sh of the word pair (a, b); sh folds after unrolling
 __device__ __forceinline__ void put3(int sh, uint32_t &a, uint32_t &b, uint32_t x) {
@@ -589,37 +595,42 @@ struct Stitch {
     uint32_t prev, first, w36, w37;
 };
 
-template <bool SEE>
+template <bool SEE, int V>
 __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const RolloutParams &p, const uint32_t *lut,
                                         uint32_t *stage_w, int lane) {
     const DevCfg &c = p.cfg;
+    constexpr int R = 3 * V * V;            // record bytes (147)
+    constexpr int FW = R >> 2;              // full words of a record (36); word FW holds the last R&3 bytes
+    constexpr int NG = (V * V + 3) / 4;     // groups of 4 cells (13)
+    constexpr int AGENT_CI = (V / 2) * V + (V - 1);   // the agent's own cell (3,6) in output order
+    constexpr uint32_t VMASK = (1u << V) - 1u;
     const uint32_t st_sa = (uint32_t)__cvta_generic_to_shared(st);     // 32-bit shared address of the lane's column
     const uint32_t lut_sa = (uint32_t)__cvta_generic_to_shared(lut);
     const int odd = e.dir & 1;
     const int sgn = 1 - (e.dir & 2);                 // +1 for dir 0/1, -1 for dir 2/3
     const int wall_sa = c.S * 128 + (int)st_sa;       // address of the pad word (index S of the lane's column)
     // world(vx,vy) = agent + d*(6-vy) + r*(vx-3), d = DIR_TO_VEC[dir], r = (-d.y, d.x)   
-    //   even dir: x = ax + sgn*(6-vy) (rows)    y = ay + sgn*(vx-3) (columns)
-    //   odd  dir: x = ax - sgn*(vx-3) (columns) y = ay + sgn*(6-vy) (rows)
+    //   even dir: x = ax + sgn*(V-1-vy) (rows)    y = ay + sgn*(vx-V/2) (columns)
+    //   odd  dir: x = ax - sgn*(vx-V/2) (columns) y = ay + sgn*(V-1-vy) (rows)
     // P[vx] / Q[vy] = shared-memory offsets of those coordinates, read from the CTA's axis tables
     const uint32_t ax_sa = (uint32_t)__cvta_generic_to_shared(lut) + LUT_BYTES;      // table of x offsets
     const uint32_t ay_sa = ax_sa + AXIS_ENTRIES * 4;                                 // table of y offsets
-    const int p0 = odd ? e.ax + 3 * sgn : e.ay - 3 * sgn, pstep4 = (odd ? -sgn : sgn) * 4;
-    const int q6 = odd ? e.ay : e.ax, qstep4 = sgn * 4;               // row vy = 6 is the agent's own row
-    const uint32_t pa = (odd ? ax_sa : ay_sa) + (uint32_t)(p0 + 6) * 4;
-    const uint32_t qa = (odd ? ay_sa : ax_sa) + (uint32_t)(q6 + 6) * 4;
-    int P[VIEW], Q[VIEW];
+    const int p0 = odd ? e.ax + (V / 2) * sgn : e.ay - (V / 2) * sgn, pstep4 = (odd ? -sgn : sgn) * 4;
+    const int q6 = odd ? e.ay : e.ax, qstep4 = sgn * 4;               // row vy = V-1 is the agent's own row
+    const uint32_t pa = (odd ? ax_sa : ay_sa) + (uint32_t)(p0 + AXIS_BIAS) * 4;
+    const uint32_t qa = (odd ? ay_sa : ax_sa) + (uint32_t)(q6 + AXIS_BIAS) * 4;
+    int P[V], Q[V];
 #pragma unroll
-    for (int k = 0; k < VIEW; ++k) {
+    for (int k = 0; k < V; ++k) {
         P[k] = (int)lds_u32(pa + k * pstep4) + (int)st_sa;            // P carries the column base address
-        Q[k] = (int)lds_u32(qa + (6 - k) * qstep4);
+        Q[k] = (int)lds_u32(qa + (V - 1 - k) * qstep4);
     }
     const uint32_t own = e.carry ? lut[e.carry * lut_pitch<SEE>()] : (uint32_t)T_EMPTY;   // word0: 24-bit (type,colour,state)   // minigrid.py:1349-1356
 
     // Realignment of the record to byte offset lane*147 of the warp's 4704-byte block: word j of the record
     // times 2^s8 (one IMAD.WIDE) gives the bits that stay in block word q+j (low half) and the bits that
     // spill into q+j+1 (high half, carried into the next multiply-add).
-    const int boff = lane * OBS_BYTES;
+    const int boff = lane * R;
     const int q = boff >> 2;
     const uint32_t s8 = (boff & 3) * 8;
     const uint32_t M = p.m1 << s8;
@@ -634,8 +645,8 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
         spill = a;
 #endif
         if (j == 0) first = o;
-        else if (j < 36) stage_w[q + j] = o;
-        else if (j == 36) w36 = o;
+        else if (j < FW) stage_w[q + j] = o;
+        else if (j == FW) w36 = o;
         else w37 = o;
     };
     const uint32_t m0 = p.m0, m8 = p.m8, m16 = p.m16, m24 = p.m24;
@@ -647,14 +658,14 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
         // before the first pack -- fewer exposed LDS latencies per step.
         constexpr int GB = MGB_SEE_BATCH;
 #pragma unroll
-        for (int g0 = 0; g0 < 13; g0 += GB) {
+        for (int g0 = 0; g0 < NG; g0 += GB) {
             uint32_t code[GB * 4], x[GB * 4];
 #pragma unroll
             for (int i = 0; i < GB * 4; ++i) {
                 const int ci = g0 * 4 + i;
                 code[i] = 0;
-                if (ci < VIEW * VIEW && ci != 3 * VIEW + 6) {
-                    const int vx = ci / VIEW, vy = ci % VIEW;
+                if (ci < V * V && ci != AGENT_CI) {
+                    const int vx = ci / V, vy = ci % V;
                     code[i] = lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa));
                 }
             }
@@ -662,51 +673,51 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
             for (int i = 0; i < GB * 4; ++i) {
                 const int ci = g0 * 4 + i;
                 x[i] = 0;
-                if (ci < VIEW * VIEW) x[i] = (ci == 3 * VIEW + 6) ? own : lut_ld(lut_sa, code[i]);
+                if (ci < V * V) x[i] = (ci == AGENT_CI) ? own : lut_ld(lut_sa, code[i]);
             }
 #pragma unroll
             for (int gg = 0; gg < GB; ++gg) {
                 const int g = g0 + gg;
-                if (g >= 13) continue;
+                if (g >= NG) continue;
                 const uint32_t *y = &x[gg * 4];
 #if MGB_PACK_IMAD_SEE
                 emit(g * 3, y[1] * m24 + y[0]);                                   // x0.b0 x0.b1 x0.b2 x1.b0
-                if (g * 3 + 1 <= 37) emit(g * 3 + 1, y[2] * m16 + __umulhi(y[1], m24));   // x1.b1 x1.b2 x2.b0 x2.b1
-                if (g * 3 + 2 <= 37) emit(g * 3 + 2, y[3] * m8 + __umulhi(y[2], m16));    // x2.b2 x3.b0 x3.b1 x3.b2
+                if (g * 3 + 1 <= FW + 1) emit(g * 3 + 1, y[2] * m16 + __umulhi(y[1], m24));   // x1.b1 x1.b2 x2.b0 x2.b1
+                if (g * 3 + 2 <= FW + 1) emit(g * 3 + 2, y[3] * m8 + __umulhi(y[2], m16));    // x2.b2 x3.b0 x3.b1 x3.b2
 #else
                 emit(g * 3, __byte_perm(y[0], y[1], 0x4210));                              // x0.b0 x0.b1 x0.b2 x1.b0
-                if (g * 3 + 1 <= 37) emit(g * 3 + 1, __byte_perm(y[1], y[2], 0x5421));     // x1.b1 x1.b2 x2.b0 x2.b1
-                if (g * 3 + 2 <= 37) emit(g * 3 + 2, __byte_perm(y[2], y[3], 0x6542));     // x2.b2 x3.b0 x3.b1 x3.b2
+                if (g * 3 + 1 <= FW + 1) emit(g * 3 + 1, __byte_perm(y[1], y[2], 0x5421));     // x1.b1 x1.b2 x2.b0 x2.b1
+                if (g * 3 + 2 <= FW + 1) emit(g * 3 + 2, __byte_perm(y[2], y[3], 0x6542));     // x2.b2 x3.b0 x3.b1 x3.b2
 #endif
             }
         }
     } else {
-        uint32_t acc[38];
+        uint32_t acc[FW + 2];
 #pragma unroll
-        for (int i = 0; i < 38; ++i) acc[i] = 0;
-        uint32_t rowvis = 1u << 3;                          // mask[(3,6)] = True (minigrid.py:619)
+        for (int i = 0; i < FW + 2; ++i) acc[i] = 0;
+        uint32_t rowvis = 1u << (V / 2);                          // mask[(3,6)] = True (minigrid.py:619)
 #pragma unroll
-        for (int vy = VIEW - 1; vy >= 0; --vy) {
-            uint32_t xs[VIEW];
+        for (int vy = V - 1; vy >= 0; --vy) {
+            uint32_t xs[V];
             uint32_t opaque = 0;
 #pragma unroll
-            for (int vx = VIEW - 1; vx >= 0; --vx) {                      // descending: Horner on the FMA pipe
+            for (int vx = V - 1; vx >= 0; --vx) {                         // descending: Horner on the FMA pipe
                 uint32_t oq;
                 lut_ld2(lut_sa, lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa)), xs[vx], oq);
                 opaque = opaque * p.m2 + oq;
             }
-            const uint32_t t = ~opaque & 0x7Fu;
-            const uint32_t f = flood_up(rowvis, t);                       // forward sweep i = 0..5
-            const uint32_t vis = rev7(flood_up(rev7(f), rev7(t)));        // reverse sweep i = 6..1
+            const uint32_t t = ~opaque & VMASK;
+            const uint32_t f = flood_up<V>(rowvis, t);                       // forward sweep i = 0..5
+            const uint32_t vis = revv<V>(flood_up<V>(revv<V>(f), revv<V>(t)));        // reverse sweep i = 6..1
             const uint32_t sv = vis & t;
-            rowvis = (sv | (sv << 1) | (sv >> 1)) & 0x7Fu;                // seeds of row vy-1
-            if (vy == VIEW - 1) xs[3] = own;
+            rowvis = (sv | (sv << 1) | (sv >> 1)) & VMASK;                // seeds of row vy-1
+            if (vy == V - 1) xs[V / 2] = own;
 #pragma unroll
-            for (int vx = 0; vx < VIEW; ++vx) {
+            for (int vx = 0; vx < V; ++vx) {
 #if MGB_PACK_IMAD_OCC
                 if ((vis >> vx) & 1u) {                                   // invisible cells stay (0,0,0)
                     const uint32_t x = xs[vx];
-                    const int b = 3 * (vx * VIEW + vy), w = b >> 2, sh = b & 3;
+                    const int b = 3 * (vx * V + vy), w = b >> 2, sh = b & 3;
                     if (sh == 0) acc[w] = x * m0 + acc[w];
                     else if (sh == 1) acc[w] = x * m8 + acc[w];
                     else if (sh == 2) { acc[w] = x * m16 + acc[w]; acc[w + 1] = __umulhi(x, m16) + acc[w + 1]; }
@@ -715,21 +726,21 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
 #else
                 {
                     const uint32_t x = ((vis >> vx) & 1u) ? xs[vx] : 0u;
-                    const int b = 3 * (vx * VIEW + vy);
+                    const int b = 3 * (vx * V + vy);
                     put3(b & 3, acc[b >> 2], acc[(b >> 2) + 1], x);
                 }
 #endif
             }
         }
 #pragma unroll
-        for (int j = 0; j < 38; ++j) emit(j, acc[j]);
+        for (int j = 0; j < FW + 2; ++j) emit(j, acc[j]);
     }
     // the partial last word of lane t-1 shares a 32-bit word with the head of lane t
     const uint32_t tail = (s8 >= 16) ? w37 : w36;
     const uint32_t ptail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
     if (s8 != 0 && lane > 0) first |= ptail;
     stage_w[q] = first;
-    if (s8 != 0) stage_w[q + 36] = w36;
+    if (s8 != 0) stage_w[q + FW] = w36;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -756,7 +767,7 @@ __device__ __forceinline__ void fence_proxy_async() {
 // ------------------------------------------------------------------------------------------
 // NOTE: no minBlocksPerSM argument on purpose -- with it ptxas spends up to 157 registers/thread and the
 // occupancy loss costs more than it gains (measured: profiles/README.md, A/B table)
-template <int GEN, bool SEE>
+template <int GEN, bool SEE, int V>
 __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const DevCfg &c = p.cfg;
@@ -764,8 +775,9 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
     uint32_t *axis = lut + LUT_BYTES / 4;                                           // [2][AXIS_ENTRIES]
     uint8_t *stage_base = smem_raw + TABLE_BYTES;
-    uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * STAGE_BYTES);
-    uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + wpb * STAGE_BYTES) + warp * ((c.S + 1) * 32);
+    constexpr int SB = stage_bytes(V), OB = obs_bytes(V);
+    uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * SB);
+    uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + wpb * SB) + warp * ((c.S + 1) * 32);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const uint32_t le = lut_entry(i);
         lut[i * lut_pitch<SEE>()] = le & 0x00FFFFFFu;
@@ -773,7 +785,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
         lut[i * lut_pitch<SEE>() + lut_fw<SEE>()] = le;
     }
     for (int i = threadIdx.x; i < AXIS_ENTRIES; i += blockDim.x) {
-        const int v = i - 6, wall = c.S * 128;
+        const int v = i - AXIS_BIAS, wall = c.S * 128;
         axis[i] = ((unsigned)v < (unsigned)c.W) ? (uint32_t)(v * c.HP * 32) : (uint32_t)wall;                       // x: column pitch
         axis[AXIS_ENTRIES + i] = ((unsigned)v < (unsigned)c.H) ? (uint32_t)(((v >> 2) << 7) + (v & 3)) : (uint32_t)wall;   // y: word + byte
     }
@@ -823,7 +835,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
                     __syncwarp();
                 }
                 if (valid) {
-                    transition<GEN, SEE>(st, e, rg, p, lut, action, reward, done, stage_w + lane);
+                    transition<GEN, SEE, V>(st, e, rg, p, lut, action, reward, done, stage_w + lane);
                     if (done && p.autoreset) { Env te = e; Rng tr = rg; generate<GEN>(st, te, tr, p); e = te; rg = tr; }
                 }
             }
@@ -831,16 +843,16 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
             if (p.obs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
                 __syncwarp();
-                observe<SEE>(st, e, p, lut, stage_w, lane);
-                uint8_t *gobs = p.obs + ((int64_t)t * stride + (int64_t)group * 32) * OBS_BYTES;
+                observe<SEE, V>(st, e, p, lut, stage_w, lane);
+                uint8_t *gobs = p.obs + ((int64_t)t * stride + (int64_t)group * 32) * OB;
                 if (full && ((reinterpret_cast<uintptr_t>(gobs) & 15) == 0)) {
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) bulk_store(gobs, stage_w, STAGE_BYTES);
+                    if (lane == 0) bulk_store(gobs, stage_w, SB);
                 } else {                                         // ragged tail group / unaligned base
                     __syncwarp();
                     const uint8_t *sb = reinterpret_cast<const uint8_t *>(stage_w);
-                    for (int b = lane; b < nvalid * OBS_BYTES; b += 32) gobs[b] = sb[b];
+                    for (int b = lane; b < nvalid * OB; b += 32) gobs[b] = sb[b];
                     __syncwarp();
                 }
             }

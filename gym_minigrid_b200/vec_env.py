@@ -79,9 +79,11 @@ class VecMiniGridEnv:
     metadata = {'render.modes': [], 'video.frames_per_second': 10}
     Actions = Actions
 
-    def __init__(self, spec, num_envs=1, device=None, seed=1337, env_id_base=0, autoreset=True):
+    def __init__(self, spec, num_envs=1, device=None, seed=1337, env_id_base=0, autoreset=True, agent_view_size=7):
         self.spec = spec
-        cfg = spec["config"]
+        cfg = dict(spec["config"])
+        cfg["agent_view_size"] = int(agent_view_size)
+        self._ctor = dict(num_envs=num_envs, device=device, seed=seed, env_id_base=env_id_base, autoreset=autoreset)
         self._cfg = cfg
         self._L = _lib.load()                      # raises loudly when libmgb200.so is missing
         if not torch.cuda.is_available():
@@ -95,8 +97,8 @@ class VecMiniGridEnv:
         # reference attribute names (minigrid.py:785-819)
         self.actions = Actions
         self.action_space = spaces.Discrete(cfg["n_actions"])
-        self.agent_view_size = 7
-        self.observation_space = spaces.Dict({'image': spaces.Box(0, 255, (7, 7, 3), 'uint8')})
+        V = self.agent_view_size = int(agent_view_size)          # minigrid.py:776,795
+        self.observation_space = spaces.Dict({'image': spaces.Box(0, 255, (V, V, 3), 'uint8')})
         self.reward_range = cfg["reward_range"]
         self.width, self.height = cfg["width"], cfg["height"]
         self.max_steps = cfg["max_steps"]
@@ -116,7 +118,7 @@ class VecMiniGridEnv:
         self._tape = None
         N = self.num_envs
         with torch.cuda.device(self.device):
-            self._obs = torch.empty((N, 7, 7, 3), dtype=torch.uint8, device=self.device)
+            self._obs = torch.empty((N, V, V, 3), dtype=torch.uint8, device=self.device)
             self._dir = torch.empty((N,), dtype=torch.uint8, device=self.device)
             self._reward = torch.empty((N,), dtype=torch.float64, device=self.device)
             self._done = torch.empty((N,), dtype=torch.uint8, device=self.device)
@@ -139,6 +141,15 @@ class VecMiniGridEnv:
 
     def _obs_dict(self, image, direction):
         return {'image': image, 'direction': direction, 'mission': MissionBatch(self)}
+
+    def with_view_size(self, agent_view_size):
+        """ViewSizeWrapper support (wrappers.py:579-608): the view size is a compile-time parameter of the
+        kernel, so a new handle is created and the complete env state is carried over."""
+        if self._pool_n:
+            raise _lib.MgbError("change the view size before uploading the level pool (make(..., agent_view_size=V))")
+        new = VecMiniGridEnv(self.spec, agent_view_size=agent_view_size, **self._ctor)
+        new.set_state({k: v for k, v in self.get_state().items()})
+        return new
 
     def close(self):
         if getattr(self, "_h", None):
@@ -184,7 +195,8 @@ class VecMiniGridEnv:
         a = self._actions(actions, (T, self.num_envs))
         N = self.num_envs
         if out is None:
-            obs = torch.empty((T, N, 7, 7, 3), dtype=torch.uint8, device=self.device) if want_obs else None
+            V = self.agent_view_size
+            obs = torch.empty((T, N, V, V, 3), dtype=torch.uint8, device=self.device) if want_obs else None
             reward = torch.empty((T, N), dtype=torch.float64, device=self.device)
             done = torch.empty((T, N), dtype=torch.uint8, device=self.device)
             d = torch.empty((T, N), dtype=torch.uint8, device=self.device)
@@ -199,7 +211,7 @@ class VecMiniGridEnv:
         N = self.num_envs
         if self._host is None:
             self._host = dict(
-                obs=torch.empty((N, 7, 7, 3), dtype=torch.uint8).pin_memory(),
+                obs=torch.empty((N, self.agent_view_size, self.agent_view_size, 3), dtype=torch.uint8).pin_memory(),
                 reward=torch.empty((N,), dtype=torch.float64).pin_memory(),
                 done=torch.empty((N,), dtype=torch.uint8).pin_memory(),
                 dir=torch.empty((N,), dtype=torch.uint8).pin_memory())

@@ -6,8 +6,8 @@ reference; they wrap a VecMiniGridEnv and transform whole batches on the GPU thr
 Built (with reference lines):      ReseedWrapper (wrappers.py:12-32), ImgObsWrapper (:156-166),
     OneHotPartialObsWrapper (:203-243), FullyObsWrapper (:311-338), FullyObsOneHotWrapper (:340-415),
     FlatObsWrapper (:528-577).
-Not built (out of the hot-path scope): RGBImg*Wrapper (rendering), ViewSizeWrapper
-    (needs a view-size template parameter in k_rollout), DACWrapper / ActionBonus / StateBonus /
+    ViewSizeWrapper (:579-608; odd sizes 3..11, the kernel is a template on the view size).
+Not built (out of the hot-path scope): RGBImg*Wrapper (rendering), DACWrapper / ActionBonus / StateBonus /
     AppendActionWrapper / GoalPolicyWrapper / AgentExtraInfoWrapper (bookkeeping on top of step).
 
 Reference quirks, kept or documented:
@@ -230,3 +230,17 @@ class FlatObsWrapper(ObservationWrapper):
             _lib.check(L.mgb_flat_obs(_ptr(img), self._img_bytes, _ptr(self._table), mlen, _ptr(midx), _ptr(out), N,
                                       C.c_void_p(torch.cuda.current_stream(img.device).cuda_stream)))
         return out
+
+
+class ViewSizeWrapper(Wrapper):
+    """wrappers.py:579-608: customise the agent's field of view.  The reference mutates
+    `env.unwrapped.agent_view_size`; here the view size is a template parameter of the kernel, so the wrapped
+    env is rebuilt with the new size and its complete state (grids, agents, RNG positions) is carried over.
+    Odd sizes 3, 5, 7, 9, 11.  Like the reference, not to be combined with the fully-observable wrappers."""
+
+    def __init__(self, env, agent_view_size=7):
+        base = env.unwrapped.with_view_size(agent_view_size)
+        env.unwrapped.close()
+        super().__init__(base)
+        self.observation_space = spaces.Dict({
+            'image': spaces.Box(0, 255, (agent_view_size, agent_view_size, 3), 'uint8')})

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MGB_OBS_BYTES 147      /* 7*7*3 uint8, layout [vx][vy][c] = Grid.encode (minigrid.py:571-594) */
+#define MGB_OBS_BYTES 147      /* 7*7*3 uint8, layout [vx][vy][c] = Grid.encode (minigrid.py:571-594); 3*V*V for view size V */
 #define MGB_MAX_OBSTACLES 8
 
 /* layout generators, one per reference env file on the path */
@@ -56,6 +56,8 @@ typedef struct {
     int32_t num_rows;       /* RoomGrid (KeyCorridor); num_cols is 3 */
     int32_t random_start;   /* agent_start_pos=None variants (Empty-Random-*, Dynamic-Obstacles-Random-*) */
     int32_t lava_v1;        /* 'v1' in class name => lava gives reward -1, not done (minigrid.py:1263-1266) */
+    int32_t agent_view_size;/* minigrid.py:776,795 / ViewSizeWrapper (wrappers.py:579-608): 0 or 7 = default; 3, 5, 9, 11
+                               also built.  Every obs buffer is [..][V][V][3], i.e. 3*V*V bytes per env-step */
 } mgb_config;
 
 typedef struct mgb_handle mgb_handle;

@@ -400,6 +400,42 @@ def pool_traces():
               [int((l >= 0).sum()) for l in tr["lvl"]], sum(int((r != 0).sum()) for r in tr["reward"])))
 
 
+def viewsize_traces():
+    """ViewSizeWrapper(env, V) (wrappers.py:579-608) on Philox-injected trajectories, V in {3, 5, 9, 11}."""
+    W = sys.modules["gym_minigrid.wrappers"]
+    seed = 31337
+    for env_id, V in (("MiniGrid-DoorKey-8x8-v0", 5), ("MiniGrid-FourRooms-v0", 9), ("MiniGrid-Dynamic-Obstacles-8x8-v0", 5),
+                      ("MiniGrid-KeyCorridorS3R3-v0", 3), ("MiniGrid-Empty-16x16-v0", 11), ("MiniGrid-DoorKey-16x16-v0", 11)):
+        idx, T = [2, 40], 250
+        tr = dict(obs=[], dir=[], reward=[], done=[], actions=[], obs0=[])
+        for k, i in enumerate(idx):
+            env = W.ViewSizeWrapper(R.make(env_id), V)
+            assert env.observation_space.spaces["image"].shape == (V, V, 3)
+            shim = R.PhiloxShim(seed, i, 0)
+            env.unwrapped.np_random = shim
+            obs = env.reset()
+            ep = 1
+            n_act = env.unwrapped.action_space.n
+            a = np.random.RandomState(900 + k).randint(0, n_act, size=T).astype(np.uint8)
+            O, D, RW, DN = [obs["image"].copy()], [], [], []
+            for t in range(T):
+                obs, r, d, _ = env.step(int(a[t]))
+                if d:
+                    shim.new_episode(ep)
+                    ep += 1
+                    obs = env.reset()
+                O.append(obs["image"].copy()); D.append(obs["direction"]); RW.append(float(r)); DN.append(int(d))
+            tr["obs0"].append(O[0]); tr["obs"].append(np.stack(O[1:])); tr["dir"].append(np.array(D, np.uint8))
+            tr["reward"].append(np.array(RW)); tr["done"].append(np.array(DN, np.uint8)); tr["actions"].append(a)
+        cfg = config_of(env)
+        cfg["view_size"] = V
+        path = os.path.join(OUT, "viewsize%d_%s.npz" % (V, short(env_id)))
+        np.savez_compressed(path, env_id=env_id, seed=np.uint64(seed), env_indices=np.array(idx, np.int64), view=np.int32(V),
+                            cfg_keys=np.array(list(cfg.keys())), cfg_vals=np.array(list(cfg.values()), np.int32),
+                            **{k: np.stack(v) for k, v in tr.items()})
+        print("%-50s %7.1f KB" % (os.path.basename(path), os.path.getsize(path) / 1024))
+
+
 def reward_table():
     """_reward() (minigrid.py:933-937) evaluated BY THE REFERENCE for every step_count of every
     max_steps in the registry (and 50 beyond): r_<max_steps>[k] = reward at step_count == k."""
@@ -425,3 +461,4 @@ if __name__ == "__main__":
     reward_table()
     wrapper_traces()
     pool_traces()
+    viewsize_traces()

@@ -100,7 +100,7 @@ static int obj_decode(int t, int c, int s, Obj *out) {   /* :117-150 */
 }
 
 /* ---- Grid (minigrid.py:366-718) ---------------------------------------- */
-#define VIEW 7
+#define VIEW 11          /* maximum agent_view_size; the actual size is cfg.view_size */
 typedef struct { int w, h; Obj *c; } Grid;       /* c[j*w + i]  (:414) */
 typedef struct { int w, h; Obj c[VIEW * VIEW]; } VGrid;
 
@@ -494,7 +494,7 @@ static void env_reset(Env *e, uint8_t *obs, uint8_t *dir) {
 
 /* get_view_exts (minigrid.py:1162-1189) */
 static void get_view_exts(const Env *e, int *topX, int *topY) {
-    const int sz = VIEW;
+    const int sz = e->cfg.view_size;
     if (e->adir == 0) { *topX = e->ax; *topY = e->ay - sz / 2; }
     else if (e->adir == 1) { *topX = e->ax - sz / 2; *topY = e->ay; }
     else if (e->adir == 2) { *topX = e->ax - sz + 1; *topY = e->ay - sz / 2; }
@@ -505,10 +505,11 @@ static void gen_obs(Env *e, uint8_t *obs, uint8_t *dir) {
     int topX, topY;
     get_view_exts(e, &topX, &topY);
     VGrid a, b, *cur = &a, *nxt = &b;
-    grid_slice(&e->grid, topX, topY, VIEW, VIEW, cur);
+    const int V = e->cfg.view_size;
+    grid_slice(&e->grid, topX, topY, V, V, cur);
     for (int i = 0; i < e->adir + 1; i++) { rotate_left(cur, nxt); VGrid *t = cur; cur = nxt; nxt = t; }
     uint8_t mask[VIEW][VIEW];
-    if (!e->cfg.see_through) process_vis(cur, VIEW / 2, VIEW - 1, mask);
+    if (!e->cfg.see_through) process_vis(cur, V / 2, V - 1, mask);
     else memset(mask, 1, sizeof(mask));
     vset(cur, cur->w / 2, cur->h - 1, e->carrying.has ? e->carrying : NONE);
     vgrid_encode(cur, mask, obs);
@@ -658,18 +659,22 @@ int orc_vec_set_level_pool(orc_vec *v, int32_t n_levels, const uint8_t *grid, co
 }
 
 orc_vec *orc_vec_create(const orc_config *cfg, uint64_t seed, int64_t env0, int32_t n) {
+    if (cfg->view_size != 0 && (cfg->view_size < 3 || cfg->view_size > VIEW || cfg->view_size % 2 == 0)) {
+        snprintf(g_err, sizeof g_err, "orc_vec_create: view_size must be odd, 3..11"); return NULL;
+    }
     if (cfg->width < 3 || cfg->height < 3 || cfg->width > 64 || cfg->height > 64 || n < 0 ||
         cfg->n_obstacles > ORC_MAX_OBST || cfg->num_rows > MAXR) {
         snprintf(g_err, sizeof g_err, "orc_vec_create: bad config"); return NULL;
     }
     orc_vec *v = (orc_vec *)calloc(1, sizeof(*v));
     v->cfg = *cfg; v->n = n;
+    if (v->cfg.view_size == 0) v->cfg.view_size = 7;
     v->envs = (Env *)calloc((size_t)(n > 0 ? n : 1), sizeof(Env));
     size_t cells = (size_t)cfg->width * cfg->height;
     v->cells = (Obj *)calloc((size_t)(n > 0 ? n : 1) * cells, sizeof(Obj));
     for (int i = 0; i < n; i++) {
         Env *e = &v->envs[i];
-        e->cfg = *cfg; e->grid.w = cfg->width; e->grid.h = cfg->height; e->grid.c = v->cells + (size_t)i * cells;
+        e->cfg = v->cfg; e->grid.w = cfg->width; e->grid.h = cfg->height; e->grid.c = v->cells + (size_t)i * cells;
         e->env_id = env0 + i; e->seed = seed; e->owner = v;
     }
     return v;
@@ -721,7 +726,7 @@ static int reset_range(void *p, int lo, int hi) {
         if (c->mask && !c->mask[i]) continue;
         Env *e = &v->envs[i];
         g_oob = 0;
-        env_reset(e, c->obs ? c->obs + (size_t)i * ORC_OBS_BYTES : NULL, c->dir ? c->dir + i : NULL);
+        env_reset(e, c->obs ? c->obs + (size_t)i * (3 * v->cfg.view_size * v->cfg.view_size) : NULL, c->dir ? c->dir + i : NULL);
         bad |= e->err | (g_oob ? 16 : 0);
     }
     return bad;
@@ -745,12 +750,13 @@ static int rollout_range(void *p, int lo, int hi) {
     for (int i = lo; i < hi; i++) {
         Env *e = &v->envs[i];
         g_oob = 0;
-        uint8_t scratch[ORC_OBS_BYTES];
+        uint8_t scratch[3 * VIEW * VIEW];
+        const size_t ob = (size_t)3 * v->cfg.view_size * v->cfg.view_size;
         for (int t = 0; t < T; t++) {
             size_t o = (size_t)t * n + (size_t)i;
             double r; int d; uint8_t dd;
             if (env_step(e, actions[o], &r, &d)) bad |= 1;
-            uint8_t *op = obs ? obs + o * ORC_OBS_BYTES : scratch;
+            uint8_t *op = obs ? obs + o * ob : scratch;
             if (d && autoreset) env_reset(e, op, &dd);
             else gen_obs(e, op, &dd);
             if (reward) reward[o] = r;

@@ -41,6 +41,7 @@ typedef struct {
     int32_t num_rows;       /* KeyCorridor / RoomGrid (num_cols == 3) */
     int32_t random_start;   /* Empty-Random / DynObs-Random: agent_start_pos=None */
     int32_t lava_v1;        /* 'v1' in type(env).__name__ (minigrid.py:1263-1266): true for e.g. DoorKeyEn*v1*6x16 */
+    int32_t view_size;      /* agent_view_size (minigrid.py:776,795; ViewSizeWrapper wrappers.py:579-608); 0 = 7 */
 } orc_config;
 
 #define ORC_OBS_BYTES 147
@@ -61,7 +62,8 @@ int orc_vec_set_level_pool(orc_vec *v, int32_t n_levels, const uint8_t *grid, co
  * results env i will consume, in order.  NULL disables. */
 int orc_vec_set_tape(orc_vec *v, const int32_t *draws, const int64_t *offsets);
 
-/* reset envs where mask[i]!=0 (all if mask NULL): obs [n][147], dir [n] */
+/* obs records are view_size*view_size*3 bytes (147 for the default 7).
+ * reset envs where mask[i]!=0 (all if mask NULL): obs [n][147], dir [n] */
 int orc_vec_reset(orc_vec *v, const uint8_t *mask, uint8_t *obs, uint8_t *dir);
 
 /* one step; if autoreset, a done env is reset and obs/dir are those of the new episode */

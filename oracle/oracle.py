@@ -20,7 +20,7 @@ MAX_OBST = 8
 class OrcConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "gen", "width", "height", "max_steps", "see_through", "n_actions",
-        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1")]
+        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1", "view_size")]
 
 
 def build(force=False):
@@ -75,6 +75,7 @@ class OracleVec:
         c = OrcConfig(**{k: int(cfg.get(k, 0)) for k, _ in OrcConfig._fields_})
         self.n = int(n)
         self.W, self.H = c.width, c.height
+        self.V = c.view_size or 7
         self._L = lib()
         self._L.orc_set_threads(int(threads))
         self._h = self._L.orc_vec_create(C.byref(c), C.c_uint64(seed), C.c_int64(env0), self.n)
@@ -103,7 +104,7 @@ class OracleVec:
         self._chk(self._L.orc_vec_set_level_pool(self._h, K, _p(g), _p(a), _p(ag)))
 
     def reset(self, mask=None):
-        obs = np.zeros((self.n, 7, 7, 3), np.uint8)
+        obs = np.zeros((self.n, self.V, self.V, 3), np.uint8)
         d = np.zeros(self.n, np.uint8)
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         self._chk(self._L.orc_vec_reset(self._h, _p(m), _p(obs), _p(d)))
@@ -117,7 +118,7 @@ class OracleVec:
         a = np.ascontiguousarray(actions, np.uint8)
         T = a.shape[0]
         assert a.shape == (T, self.n)
-        obs = np.zeros((T, self.n, 7, 7, 3), np.uint8) if want_obs else None
+        obs = np.zeros((T, self.n, self.V, self.V, 3), np.uint8) if want_obs else None
         r = np.zeros((T, self.n), np.float64)
         dn = np.zeros((T, self.n), np.uint8)
         d = np.zeros((T, self.n), np.uint8)

@@ -55,7 +55,7 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.MgbError, match="no CPU fallback"):
         mgb.make("MiniGrid-Empty-8x8-v0", num_envs=4)
     lib = _lib.load()
-    cfg = _lib.MgbConfig(**{k: int(mgb.spec("MiniGrid-Empty-8x8-v0")["config"][k]) for k, _ in _lib.MgbConfig._fields_})
+    cfg = _lib.MgbConfig(**{k: int(mgb.spec("MiniGrid-Empty-8x8-v0")["config"].get(k, 0)) for k, _ in _lib.MgbConfig._fields_})
     h = C.c_void_p()
     assert lib.mgb_create(C.byref(cfg), 4, 0, 0, 0, C.byref(h)) != 0
     assert b"no CUDA device" in lib.mgb_last_error()
