@@ -23,7 +23,7 @@ ERROR_BITS = {
 class MgbConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "gen", "width", "height", "max_steps", "see_through", "n_actions",
-        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1", "agent_view_size")]
+        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1", "agent_view_size", "hook")]
 
 
 # name -> (restype, argtypes); the single source of truth checked against include/mgb200.h by the tests
@@ -42,7 +42,9 @@ SIGNATURES = {
     "mgb_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mgb_set_state": (C.c_int, [_P, C.c_int64, C.c_int64] + [_P] * 8),
     "mgb_get_state": (C.c_int, [_P, C.c_int64, C.c_int64] + [_P] * 8),
-    "mgb_set_level_pool": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
+    "mgb_set_level_pool": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P]),
+    "mgb_get_levels": (C.c_int, [_P, _P, _P]),
+    "mgb_set_levels": (C.c_int, [_P, _P, _P]),
     "mgb_set_rng_tape": (C.c_int, [_P, _P, _P]),
     "mgb_full_obs": (C.c_int, [_P, _P, _P]),
     "mgb_onehot": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -134,6 +134,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
         if (c.num_rows < 1 || c.num_rows > 3 || c.room_size < 3) return fail("mgb_create: bad RoomGrid shape");
         if (c.width != (c.room_size - 1) * 3 + 1 || c.height != (c.room_size - 1) * c.num_rows + 1) return fail("mgb_create: RoomGrid size mismatch (roomgrid.py:85-86)");
     }
+    if (c.hook < 0 || c.hook > MGB_HOOK_MEMORY || (c.hook != 0 && c.gen != MGB_GEN_POOL)) return fail("mgb_create: hook %d needs a level-pool handle (MGB_GEN_POOL)", c.hook);
     if (c.gen == MGB_GEN_DYNOBS && c.n_actions != 3) return fail("mgb_create: Dynamic-Obstacles has 3 actions");
     if (c.gen != MGB_GEN_DYNOBS && c.n_actions != 7) return fail("mgb_create: n_actions must be 7");
     { const int v = view_of(c); if (v != 3 && v != 5 && v != 7 && v != 9 && v != 11) return fail("mgb_create: agent_view_size %d not built (3, 5, 7, 9, 11)", v); }
@@ -155,10 +156,10 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     DevCfg &d = h->dc;
     d.gen = c.gen; d.W = c.width; d.H = c.height; d.max_steps = c.max_steps; d.see_through = c.see_through;
     d.n_actions = c.n_actions; d.n_obst = c.n_obstacles; d.room_size = c.room_size; d.num_rows = c.num_rows;
-    d.random_start = c.random_start; d.lava_v1 = c.lava_v1;
+    d.random_start = c.random_start; d.lava_v1 = c.lava_v1; d.hook = c.hook;
     d.HP = (c.height + 3) / 4 * 4;
     d.GW = c.width * d.HP / 4;
-    d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0);
+    d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0) + (c.gen == MGB_GEN_POOL ? 1 : 0);   // pool: + level word
     h->sm_count = prop.multiProcessorCount;
 
     auto cleanup = [&](int rc) { mgb_destroy(h); return rc; };
@@ -266,16 +267,18 @@ int mgb_seed(mgb_handle *h, uint64_t seed) {
     return 0;
 }
 
-int mgb_set_level_pool(mgb_handle *h, int32_t n_levels, const uint8_t *grid, const uint8_t *aux, const int32_t *agent, void *stream) {
+int mgb_set_level_pool(mgb_handle *h, int32_t n_levels, const uint8_t *grid, const uint8_t *aux, const int32_t *agent,
+                       const int32_t *hook_params, void *stream) {
     if (!h) return fail("null handle");
     if (h->cfg.gen != MGB_GEN_POOL) return fail("mgb_set_level_pool: handle was not created with MGB_GEN_POOL");
     if (n_levels < 1 || !grid || !agent) return fail("mgb_set_level_pool: need at least one level, grid and agent");
     CUDA_OK(cudaSetDevice(h->device));
-    const int PW = h->dc.GW + 1;
+    if (h->cfg.hook != 0 && !hook_params) return fail("mgb_set_level_pool: this handle has hook %d and needs hook_params", h->cfg.hook);
+    const int PW = h->dc.GW + POOL_XW;
     uint32_t *np = nullptr;
     CUDA_OK(cudaMalloc(&np, (size_t)n_levels * PW * 4));
     const int64_t threads = (int64_t)n_levels * PW;
-    k_pack_levels<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->dc, n_levels, grid, aux, agent, np, h->err);
+    k_pack_levels<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->dc, n_levels, grid, aux, agent, hook_params, np, h->err);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { cudaFree(np); return fail("k_pack_levels: %s", cudaGetErrorString(e)); }
     CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));      // the old pool may still be in use by earlier launches
@@ -284,6 +287,18 @@ int mgb_set_level_pool(mgb_handle *h, int32_t n_levels, const uint8_t *grid, con
     h->launches++;
     return 0;
 }
+
+static int levels_io(mgb_handle *h, int32_t *out, const int32_t *in, void *stream) {
+    if (!h) return fail("null handle");
+    if (h->cfg.gen != MGB_GEN_POOL) return fail("levels: handle was not created with MGB_GEN_POOL");
+    CUDA_OK(cudaSetDevice(h->device));
+    k_levels<<<(unsigned)((h->n_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->state, h->dc.S, h->dc.GW + XWORDS, h->n_envs, out, in);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+int mgb_get_levels(mgb_handle *h, int32_t *levels, void *stream) { return levels ? levels_io(h, levels, nullptr, stream) : fail("null buffer"); }
+int mgb_set_levels(mgb_handle *h, const int32_t *levels, void *stream) { return levels ? levels_io(h, nullptr, levels, stream) : fail("null buffer"); }
 
 int mgb_reset(mgb_handle *h, const uint8_t *mask, uint8_t *obs, uint8_t *dir, void *stream) {
     if (!h) return fail("null handle");

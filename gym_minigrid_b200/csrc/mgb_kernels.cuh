@@ -81,6 +81,9 @@ constexpr int CODE_TGOAL0 = 231;                               // + colour: Goal
 constexpr uint32_t EMPTY_WORD = 0x15151515u;                   // 4 x CODE_EMPTY
 static_assert(CODE_EMPTY == 0x15, "EMPTY_WORD");
 
+enum : int { HOOK_NONE = 0, HOOK_PICKUP_TARGET = 1, HOOK_UNLOCK = 2, HOOK_FETCH = 3, HOOK_GOTODOOR = 4, HOOK_GOTOOBJECT = 5,
+             HOOK_PUTNEAR = 6, HOOK_REDBLUEDOORS = 7, HOOK_MEMORY = 8 };
+constexpr int POOL_XW = 5;     // pool record = GW grid words + agent word + 4 hook-parameter words
 enum : uint32_t { F_OPAQUE = 1, F_OVERLAP = 2, F_PICKUP = 4, F_TGOAL = 8, F_LAVA = 16 };
 
 // code -> type | colour<<8 | state<<16 | flags<<24   (WorldObj.encode + the predicates
@@ -103,7 +106,7 @@ __host__ __device__ inline uint32_t lut_entry(int code) {
 }
 
 struct DevCfg {
-    int32_t gen, W, H, max_steps, see_through, n_actions, n_obst, room_size, num_rows, random_start, lava_v1;
+    int32_t gen, W, H, max_steps, see_through, n_actions, n_obst, room_size, num_rows, random_start, lava_v1, hook;
     int32_t HP;   // grid column pitch in cells: H rounded up to a multiple of 4 (one column = HP/4 words)
     int32_t GW;   // grid words per env = W*HP/4; cell (x,y) = byte (y&3) of word x*HP/4 + (y>>2)
     int32_t S;    // state words per env
@@ -129,7 +132,8 @@ struct RolloutParams {
     int64_t env_id_base;
     const int32_t *tape;
     const int64_t *tape_off;
-    const uint32_t *pool;       // GEN_POOL: [pool_n][GW + 1] words (grid words, then x | y<<8 | dir<<16)
+    const uint32_t *pool;       // GEN_POOL: [pool_n][GW + POOL_XW] words: grid, x|y<<8|dir<<16, then 4 hook words:
+                                //   tcode | mcode<<8 ; tx|ty<<8|A.x<<16|A.y<<24 ; B.x|B.y<<8|C.x<<16|C.y<<24 ; D.x|D.y<<8
     int32_t pool_n;
     uint32_t *err;
     // run-time copies of 1, 1, 2, 2^8, 2^16, 2^24.  Multiplying by these (instead of literal shifts) keeps the
@@ -145,6 +149,10 @@ struct Env {                    // hot: stays in registers (its address never es
     int ax, ay, dir, carry, steps, target;
     int flags;                  // bit0: grid == template + obstacle balls only (Dynamic-Obstacles fast reset)
     bool dirty;                 // grid words modified since load
+};
+struct PoolCtx {                // GEN_POOL kernels only: the level being played and its hook parameters
+    int level;
+    uint32_t hp0, hp1, hp2, hp3;
 };
 struct Rng {                    // cold: passed by reference to the out-of-line draw routine
     uint32_t episode, ndraws;
@@ -297,7 +305,7 @@ __device__ __forceinline__ void add_door(uint32_t *st, const DevCfg &c, Rooms &R
 }
 
 template <int GEN>
-__device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p) {
+__device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, PoolCtx *pc) {
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP;
     if (GEN == GEN_POOL) {
@@ -308,10 +316,12 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
         e.carry = 0; e.steps = 0; e.target = 0; e.dirty = true;
         if (p.pool_n <= 0) { rg.err |= ERR_NO_POOL; return; }
         const int lvl = rand_int(rg, p, 0, p.pool_n);
-        const uint32_t *src = p.pool + (size_t)lvl * (c.GW + 1);
+        const uint32_t *src = p.pool + (size_t)lvl * (c.GW + POOL_XW);
         for (int k = 0; k < c.GW; ++k) st[k * 32] = __ldg(&src[k]);
         const uint32_t a = __ldg(&src[c.GW]);
         e.ax = a & 0xFF; e.ay = (a >> 8) & 0xFF; e.dir = (a >> 16) & 3;
+        pc->level = lvl;
+        pc->hp0 = __ldg(&src[c.GW + 1]); pc->hp1 = __ldg(&src[c.GW + 2]); pc->hp2 = __ldg(&src[c.GW + 3]); pc->hp3 = __ldg(&src[c.GW + 4]);
         return;
     }
     // Grid(width,height) + static walls/goal
@@ -436,7 +446,7 @@ __device__ __forceinline__ double reward_formula(int steps, int max_steps) {
 
 template <int GEN, bool SEE, int V>
 __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, const uint32_t *lut, int action,
-                                           double &reward, bool &done, uint32_t *draws) {
+                                           double &reward, bool &done, uint32_t *draws, const PoolCtx &pc) {
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP;
     reward = 0.0; done = false;
@@ -496,6 +506,18 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         rg.err |= ERR_ACTION;                             // reference: assert False, "unknown action"
         action = A_DONE;
     }
+    // ---- subclass step() pre-hooks of the level-pool envs
+    const int pre_carry = e.carry;
+    bool red_before = false, blue_before = false;
+    if (GEN == GEN_POOL) {
+        if (c.hook == HOOK_MEMORY && action == A_PICKUP) action = A_TOGGLE;                  // memory.py:89-90
+        if (c.hook == HOOK_REDBLUEDOORS) {                                                     // redbluedoors.py:45-46
+            const uint32_t ra = lut[cell_rd(st, (int)((pc.hp1 >> 16) & 0xFF) * HP + (int)(pc.hp1 >> 24)) * lut_pitch<SEE>() + lut_fw<SEE>()];
+            const uint32_t rb = lut[cell_rd(st, (int)(pc.hp2 & 0xFF) * HP + (int)((pc.hp2 >> 8) & 0xFF)) * lut_pitch<SEE>() + lut_fw<SEE>()];
+            red_before = (ra & 0xFF) == T_DOOR && ((ra >> 16) & 0xFF) == 0;
+            blue_before = (rb & 0xFF) == T_DOOR && ((rb >> 16) & 0xFF) == 0;
+        }
+    }
     e.steps++;
     const int dx = (e.dir & 1) ? 0 : 1 - e.dir, dy = (e.dir & 1) ? 2 - e.dir : 0;
     const int fx = e.ax + dx, fy = e.ay + dy;
@@ -537,6 +559,59 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
     if (e.steps >= c.max_steps) done = true;
     if (GEN == GEN_KEYCORRIDOR) {                        // envs/keycorridor.py:51-59
         if (action == A_PICKUP && e.carry != 0 && e.carry == e.target) { reward = reward_formula(e.steps, c.max_steps); done = true; }
+    }
+    if (GEN == GEN_POOL && c.hook != HOOK_NONE) {        // step() post-hooks of the level-pool envs
+        const int tcode = pc.hp0 & 0xFF, mcode = (pc.hp0 >> 8) & 0xFF;
+        const int tx = pc.hp1 & 0xFF, ty = (pc.hp1 >> 8) & 0xFF;
+        const int Ax = (pc.hp1 >> 16) & 0xFF, Ay = pc.hp1 >> 24, Bx = pc.hp2 & 0xFF, By = (pc.hp2 >> 8) & 0xFF;
+        const int Cx = (pc.hp2 >> 16) & 0xFF, Cy = pc.hp2 >> 24, Dx = pc.hp3 & 0xFF, Dy = (pc.hp3 >> 8) & 0xFF;
+        auto adj4 = [&](int x, int y) { return (e.ax == x && abs(e.ay - y) == 1) || (e.ay == y && abs(e.ax - x) == 1); };
+        auto door_open = [&](int x, int y) {
+            const uint32_t w = lut[cell_rd(st, x * HP + y) * lut_pitch<SEE>() + lut_fw<SEE>()];
+            return (w & 0xFF) == T_DOOR && ((w >> 16) & 0xFF) == 0;
+        };
+        bool win = false;
+        switch (c.hook) {
+        case HOOK_PICKUP_TARGET:                          // unlockpickup.py:34-42, blockedunlockpickup.py:38-46
+            if (action == A_PICKUP && e.carry != 0 && e.carry == tcode) { win = true; done = true; }
+            break;
+        case HOOK_UNLOCK:                                 // unlock.py:33-41
+            if (action == A_TOGGLE && door_open(Ax, Ay)) { win = true; done = true; }
+            break;
+        case HOOK_FETCH:                                  // fetch.py:74-86
+            if (e.carry != 0) { if (e.carry == tcode) win = true; else reward = 0.0; done = true; }
+            break;
+        case HOOK_GOTODOOR:                               // gotodoor.py:72-93
+            if (action == A_DONE) {
+                if (adj4(tx, ty)) win = true;
+                if (adj4(Ax, Ay) || adj4(Bx, By) || adj4(Cx, Cy) || adj4(Dx, Dy)) done = true;
+            }
+            break;
+        case HOOK_GOTOOBJECT:                             // gotoobject.py:68-84
+            if (action == A_TOGGLE) done = true;
+            if (action == A_DONE) { if (abs(e.ax - tx) <= 1 && abs(e.ay - ty) <= 1) win = true; done = true; }
+            break;
+        case HOOK_PUTNEAR: {                              // putnear.py:91-112
+            if (action == A_PICKUP && e.carry != 0 && e.carry != mcode) done = true;
+            if (action == A_DROP && pre_carry != 0) {
+                const int ox = e.ax + dx, oy = e.ay + dy;                 // dir is unchanged by drop
+                if (e.carry == 0 && abs(ox - tx) <= 1 && abs(oy - ty) <= 1) win = true;   // dropped: the cell in front now holds it
+                done = true;
+            }
+            break;
+        }
+        case HOOK_REDBLUEDOORS: {                         // redbluedoors.py:44-66
+            const bool red_after = door_open(Ax, Ay), blue_after = door_open(Bx, By);
+            if (blue_after) { if (red_before) win = true; else reward = 0.0; done = true; }
+            else if (red_after) { if (blue_before) { reward = 0.0; done = true; } }
+            break;
+        }
+        case HOOK_MEMORY:                                 // memory.py:88-100
+            if (e.ax == Ax && e.ay == Ay) { win = true; done = true; }
+            if (e.ax == Bx && e.ay == By) { win = false; reward = 0.0; done = true; }
+            break;
+        }
+        if (win) reward = reward_formula(e.steps, c.max_steps);
     }
     if (GEN == GEN_DYNOBS) {                             // envs/dynamicobstacles.py:84-87
         e.dirty = true;
@@ -801,6 +876,8 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
         st_warp[S * 32 + lane] = (uint32_t)CODE_WALL * 0x01010101u;        // out-of-grid pad (minigrid.py:469)
         Env e;
         Rng rg;
+        PoolCtx pc;
+        pc.level = 0; pc.hp0 = pc.hp1 = pc.hp2 = pc.hp3 = 0;
         uint32_t *const st = st_warp + lane;   // this lane's column: word k at st[k*32]; bank == lane
         rg.lid = (int64_t)group * 32 + lane;
         rg.gid = p.env_id_base + rg.lid;
@@ -811,6 +888,13 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
             e.ax = w0 & 0xFF; e.ay = (w0 >> 8) & 0xFF; e.dir = (w0 >> 16) & 3; e.carry = w0 >> 24;
             e.steps = w1 & 0xFFFF; e.target = (w1 >> 16) & 0xFF; e.flags = w1 >> 24;
             rg.episode = st[(GW + 2) * 32]; rg.ndraws = st[(GW + 3) * 32];
+            if (GEN == GEN_POOL) {
+                pc.level = (int)st[(GW + XWORDS) * 32];
+                if (p.pool_n > 0 && (unsigned)pc.level < (unsigned)p.pool_n) {
+                    const uint32_t *src = p.pool + (size_t)pc.level * (GW + POOL_XW) + GW;
+                    pc.hp0 = __ldg(&src[1]); pc.hp1 = __ldg(&src[2]); pc.hp2 = __ldg(&src[3]); pc.hp3 = __ldg(&src[4]);
+                }
+            }
         }
         rg.rblk = 0xFFFFFFFFu; rg.err = 0; e.dirty = false;
         rg.rb0 = rg.rb1 = rg.rb2 = rg.rb3 = 0;
@@ -820,7 +904,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
 
         if (p.do_reset) {
             const bool m = valid && (!p.reset_mask || p.reset_mask[lid]);
-            if (m) { Env te = e; Rng tr = rg; generate<GEN>(st, te, tr, p); e = te; rg = tr; }   // copy-in/out keeps e, rg in registers
+            if (m) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }   // copy-in/out keeps e, rg in registers
         }
         const int nsteps = p.T > 0 ? p.T : 1;
         int a_next = 0;
@@ -835,8 +919,8 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
                     __syncwarp();
                 }
                 if (valid) {
-                    transition<GEN, SEE, V>(st, e, rg, p, lut, action, reward, done, stage_w + lane);
-                    if (done && p.autoreset) { Env te = e; Rng tr = rg; generate<GEN>(st, te, tr, p); e = te; rg = tr; }
+                    transition<GEN, SEE, V>(st, e, rg, p, lut, action, reward, done, stage_w + lane, pc);
+                    if (done && p.autoreset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
                 }
             }
             const int64_t o = (int64_t)t * stride + lid;
@@ -869,6 +953,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__
         st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16) | ((uint32_t)e.flags << 24);
         st[(GW + 2) * 32] = rg.episode;
         st[(GW + 3) * 32] = rg.ndraws;
+        if (GEN == GEN_POOL) st[(GW + XWORDS) * 32] = (uint32_t)pc.level;
         const bool any_dirty = __any_sync(0xFFFFFFFFu, e.dirty);
         __syncwarp();
         for (int k = any_dirty ? 0 : GW; k < S; ++k) gst[k * 32] = st_warp[k * 32 + lane];
@@ -1029,9 +1114,10 @@ __global__ void k_get_state(const StateIO io, int full_obs) {
 
 // level pool upload: one thread per (level, pool word); same cell packing as k_set_state
 __global__ void k_pack_levels(DevCfg c, int n_levels, const uint8_t *__restrict__ grid, const uint8_t *__restrict__ aux,
-                              const int32_t *__restrict__ agent, uint32_t *__restrict__ pool, uint32_t *err_out) {
+                              const int32_t *__restrict__ agent, const int32_t *__restrict__ hookp,
+                              uint32_t *__restrict__ pool, uint32_t *err_out) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int PW = c.GW + 1;
+    const int PW = c.GW + POOL_XW;
     const int64_t lvl = tid / PW;
     const int k = (int)(tid % PW);
     if (lvl >= n_levels) return;
@@ -1048,13 +1134,29 @@ __global__ void k_pack_levels(DevCfg c, int n_levels, const uint8_t *__restrict_
             }
             w |= (uint32_t)code << (8 * b);
         }
-    } else {
+    } else if (k == c.GW) {
         const int32_t *a = agent + lvl * 3;
         if (a[0] < 0 || a[0] >= c.W || a[1] < 0 || a[1] >= c.H || a[2] < 0 || a[2] > 3) err |= ERR_BOUNDS;
         w = (uint32_t)(a[0] & 0xFF) | ((uint32_t)(a[1] & 0xFF) << 8) | ((uint32_t)(a[2] & 3) << 16);
+    } else if (hookp) {
+        const int32_t *q = hookp + lvl * 16;
+        auto b = [&](int i) { return (uint32_t)(q[i] & 0xFF); };
+        const int j = k - c.GW;
+        if (j == 1) w = (q[0] ? (uint32_t)code_of(q[0], q[1], 0) : 0u) | ((q[2] ? (uint32_t)code_of(q[2], q[3], 0) : 0u) << 8);
+        else if (j == 2) w = b(4) | (b(5) << 8) | (b(6) << 16) | (b(7) << 24);
+        else if (j == 3) w = b(8) | (b(9) << 8) | (b(10) << 16) | (b(11) << 24);
+        else w = b(12) | (b(13) << 8);
     }
     pool[lvl * PW + k] = w;
     if (err) atomicOr(err_out, err);
+}
+
+__global__ void k_levels(uint32_t *state, int S, int word, int64_t n, int32_t *out, const int32_t *in) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t *w = state + ((i >> 5) * S + word) * 32 + (i & 31);
+    if (in) *w = (uint32_t)in[i];
+    if (out) out[i] = (int32_t)*w;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -271,7 +271,7 @@ class VecMiniGridEnv:
         torch.cuda.current_stream(self.device).synchronize()     # ts goes out of scope
         self.check_errors()
 
-    def set_level_pool(self, grid, agent, aux=None, missions=None):
+    def set_level_pool(self, grid, agent, aux=None, missions=None, hook_params=None):
         """Level-pool mode: upload K reference-generated layouts; reset / auto-reset of
         env e in episode k picks level mulhi32(philox(seed, e, k).word0, K)."""
         g = torch.as_tensor(np.ascontiguousarray(grid, dtype=np.uint8)).to(self.device)
@@ -279,22 +279,25 @@ class VecMiniGridEnv:
         assert tuple(g.shape[1:]) == (self.width, self.height, 3), g.shape
         a = torch.as_tensor(np.ascontiguousarray(np.asarray(agent)[:, :3], dtype=np.int32)).to(self.device)
         x = None if aux is None else torch.as_tensor(np.ascontiguousarray(aux, dtype=np.uint8)).to(self.device)
-        _lib.check(self._L.mgb_set_level_pool(self._h, K, _ptr(g), _ptr(x), _ptr(a), self._stream()))
+        hp = None if hook_params is None else torch.as_tensor(np.ascontiguousarray(hook_params, dtype=np.int32).reshape(K, 16)).to(self.device)
+        _lib.check(self._L.mgb_set_level_pool(self._h, K, _ptr(g), _ptr(x), _ptr(a), _ptr(hp), self._stream()))
         self._pool_n = K
         self._pool_missions = list(missions) if missions is not None else None
         self.check_errors()
 
     def level_index(self, first=0, count=None):
-        """which pool level each env is currently playing (recomputed from the Philox stream on the host)"""
-        rng = self.get_state(("rng",), first, count)["rng"].cpu().numpy().view(np.uint32)
-        seed = int(self._seed) & (2 ** 64 - 1)
-        out = np.zeros(len(rng), np.int64)
-        for i, (ep, _) in enumerate(rng):
-            gid = self._env_id_base + first + i
-            w0 = _philox4x32_10((0, (int(ep) - 1) & 0xFFFFFFFF, gid & 0xFFFFFFFF, (gid >> 32) & 0xFFFFFFFF),
-                                (seed & 0xFFFFFFFF, seed >> 32))[0]
-            out[i] = (w0 * self._pool_n) >> 32
-        return out
+        """which pool level each env is currently playing"""
+        lv = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)
+        _lib.check(self._L.mgb_get_levels(self._h, _ptr(lv), self._stream()))
+        count = self.num_envs - first if count is None else count
+        return lv[first:first + count].cpu().numpy().astype(np.int64)
+
+    def set_levels(self, levels):
+        """restore which level each env is playing (checkpoint restore, after set_state)"""
+        lv = torch.as_tensor(np.ascontiguousarray(levels, dtype=np.int32)).to(self.device)
+        assert lv.shape == (self.num_envs,)
+        _lib.check(self._L.mgb_set_levels(self._h, _ptr(lv), self._stream()))
+        torch.cuda.current_stream(self.device).synchronize()
 
     def set_rng_tape(self, draws, offsets):
         """RNG-tape parity mode (SURVEY §8c mode 2)."""

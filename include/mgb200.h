@@ -58,7 +58,24 @@ typedef struct {
     int32_t lava_v1;        /* 'v1' in class name => lava gives reward -1, not done (minigrid.py:1263-1266) */
     int32_t agent_view_size;/* minigrid.py:776,795 / ViewSizeWrapper (wrappers.py:579-608): 0 or 7 = default; 3, 5, 9, 11
                                also built.  Every obs buffer is [..][V][V][3], i.e. 3*V*V bytes per env-step */
+    int32_t hook;           /* MGB_HOOK_*: subclass step() post-hook for MGB_GEN_POOL handles (0 = base step only) */
 } mgb_config;
+
+/* step() post-hooks of the stock env files that only add a success/failure rule on top of MiniGridEnv.step.
+ * Per-level parameters come with the level pool (mgb_set_level_pool, `hook_params`). */
+enum {
+    MGB_HOOK_NONE = 0,
+    MGB_HOOK_PICKUP_TARGET = 1, /* unlockpickup.py:34-42, blockedunlockpickup.py:38-46 (= keycorridor.py:51-59): picking up `obj` */
+    MGB_HOOK_UNLOCK = 2,        /* unlock.py:33-41: toggle while the door (pos A) is open */
+    MGB_HOOK_FETCH = 3,         /* fetch.py:74-86: carrying anything ends the episode; reward iff it is the target */
+    MGB_HOOK_GOTODOOR = 4,      /* gotodoor.py:72-93: `done` next to the target door; done next to any door (A..D) */
+    MGB_HOOK_GOTOOBJECT = 5,    /* gotoobject.py:68-84: toggle ends; `done` within 1 cell of the target */
+    MGB_HOOK_PUTNEAR = 6,       /* putnear.py:91-112: wrong pickup ends; dropping the move object ends, reward iff near the target */
+    MGB_HOOK_REDBLUEDOORS = 7,  /* redbluedoors.py:44-66: red door = pos A, blue door = pos B */
+    MGB_HOOK_MEMORY = 8         /* memory.py:88-100: pickup acts as toggle; success pos A, failure pos B */
+};
+#define MGB_HOOK_PARAMS 16      /* int32 per level: target_type, target_color, move_type, move_color, target_x, target_y,
+                                   A.x, A.y, B.x, B.y, C.x, C.y, D.x, D.y, 0, 0 */
 
 typedef struct mgb_handle mgb_handle;
 
@@ -124,9 +141,13 @@ int mgb_get_state(mgb_handle *h, int64_t first, int64_t count, uint8_t *grid, ui
 /* Level pool for MGB_GEN_POOL handles: n_levels layouts in the reference's encoding (e.g. snapshots of
  * reference envs after reset()).  grid [K][W][H][3], aux [K][W][H] (may be NULL), agent [K][3] int32 = x,y,dir.
  * Device pointers; the pool is copied, the buffers may be freed once `stream` has passed the call.
- * reset / auto-reset of env e in episode k uses level  mulhi32(philox(seed, e, k).word0, K). */
+ * reset / auto-reset of env e in episode k uses level  mulhi32(philox(seed, e, k).word0, K).
+ * agent [K][3]; hook_params: per-level parameters of mgb_config.hook (positions in grid coordinates). */
 int mgb_set_level_pool(mgb_handle *h, int32_t n_levels, const uint8_t *grid, const uint8_t *aux,
-                       const int32_t *agent, void *stream);
+                       const int32_t *agent, const int32_t *hook_params /* [K][MGB_HOOK_PARAMS] or NULL */, void *stream);
+/* which level each env is playing: levels int32 [N] (device).  set: after mgb_set_state, to restore a checkpoint. */
+int mgb_get_levels(mgb_handle *h, int32_t *levels, void *stream);
+int mgb_set_levels(mgb_handle *h, const int32_t *levels, void *stream);
 
 /* RNG-tape parity mode: env i consumes draws[offsets[i] ...) in order instead of Philox
  * (values are final randint results).  NULL switches back to Philox.  Device pointers,

@@ -36,6 +36,8 @@ OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 MAX_OBST = 8
 SNAP_EVERY = 50
 
+HOOK_OF_CLASS = {"UnlockPickup": 1, "BlockedUnlockPickup": 1, "Unlock": 2, "FetchEnv": 3, "GoToDoorEnv": 4, "GoToObjectEnv": 5,
+                 "PutNearEnv": 6, "RedBlueDoorEnv": 7, "MemoryEnv": 8}
 GEN_OF_CLASS = {"EmptyEnv": 0, "DoorKeyEnv": 1, "FourRoomsEnv": 2, "DynamicObstaclesEnv": 3, "KeyCorridor": 4}
 
 
@@ -50,16 +52,20 @@ def config_of(env):
     if gen is None:
         # no on-device generator for this class: level-pool mode, only legal when step() is the base step
         mg = sys.modules["gym_minigrid.minigrid"]
-        assert type(env).step is mg.MiniGridEnv.step, "%s overrides step(): not a level-pool env" % type(env).__name__
+        names = [k.__name__ for k in type(env).__mro__]
+        assert type(env).step is mg.MiniGridEnv.step or any(n in HOOK_OF_CLASS for n in names) or \
+            any(n in ("LockedRoom", "PlaygroundV0") for n in names), \
+            "%s overrides step() with an unknown hook: not a level-pool env" % type(env).__name__
         gen = 5
-    return dict(
+    return dict(hook=HOOK_OF_CLASS.get(next((k.__name__ for k in type(env).__mro__ if k.__name__ in HOOK_OF_CLASS), ""), 0),
+        **dict(
         gen=gen, width=env.width, height=env.height, max_steps=env.max_steps,
         see_through=int(bool(env.see_through_walls)), n_actions=env.action_space.n,
         n_obstacles=getattr(env, "n_obstacles", 0) if gen == 3 else 0,
         room_size=getattr(env, "room_size", 0), num_rows=getattr(env, "num_rows", 0),
         random_start=int(gen in (0, 3) and getattr(env, "agent_start_pos", 1) is None),
         lava_v1=int("v1" in type(env).__name__),     # minigrid.py:1263 -- e.g. "DoorKeyEnv16x16" contains "v1"
-    )
+    ))
 
 
 def pad_obst(o):
@@ -436,6 +442,225 @@ def viewsize_traces():
         print("%-50s %7.1f KB" % (os.path.basename(path), os.path.getsize(path) / 1024))
 
 
+# ---------------------------------------------------------------------------
+# level-pool envs with step() hooks
+# ---------------------------------------------------------------------------
+def _find(u, pred):
+    for x in range(u.width):
+        for y in range(u.height):
+            c = u.grid.get(x, y)
+            if c is not None and pred(c):
+                return (x, y)
+    return None
+
+
+def hook_params_of(u, hook):
+    """the per-level attributes each hook reads, as the 16 int32 of MGB_HOOK_PARAMS"""
+    mg = sys.modules["gym_minigrid.minigrid"]
+    T, C = mg.OBJECT_TO_IDX, mg.COLOR_TO_IDX
+    hp = [0] * 16
+    if hook == 1:
+        hp[0], hp[1] = T[u.obj.type], C[u.obj.color]
+    elif hook == 2:
+        hp[6], hp[7] = _find(u, lambda c: c is u.door)
+    elif hook == 3:
+        hp[0], hp[1] = T[u.targetType], C[u.targetColor]
+    elif hook == 4:
+        hp[4], hp[5] = u.target_pos
+        for k, (x, y) in enumerate(u.doorPos):
+            hp[6 + 2 * k], hp[7 + 2 * k] = x, y
+    elif hook == 5:
+        hp[4], hp[5] = u.target_pos
+    elif hook == 6:
+        hp[2], hp[3] = T[u.move_type], C[u.moveColor]
+        hp[4], hp[5] = u.target_pos
+    elif hook == 7:
+        hp[6], hp[7] = _find(u, lambda c: c is u.red_door)
+        hp[8], hp[9] = _find(u, lambda c: c is u.blue_door)
+    elif hook == 8:
+        hp[6], hp[7] = u.success_pos
+        hp[8], hp[9] = u.failure_pos
+    return [int(v) for v in hp]
+
+
+def _face(u, P, rs):
+    """teleport the agent to an empty cell 4-adjacent to P, facing P; returns False if there is none"""
+    mg = sys.modules["gym_minigrid.minigrid"]
+    cand = []
+    for d, (dx, dy) in enumerate([(1, 0), (0, 1), (-1, 0), (0, -1)]):
+        x, y = P[0] - dx, P[1] - dy
+        if 0 < x < u.width - 1 and 0 < y < u.height - 1 and u.grid.get(x, y) is None:
+            cand.append((x, y, d))
+    if not cand:
+        return False
+    x, y, d = cand[rs.randint(len(cand))]
+    u.agent_pos = np.array([x, y])
+    u.agent_dir = d
+    return True
+
+
+def directed_scenarios(u0, hook, rs):
+    """(env copy, actions) pairs that drive each hook through its success AND failure branch"""
+    import copy
+    A = u0.actions
+    out = []
+
+    def fresh():
+        u = copy.deepcopy(u0)
+        u.step_count = int(rs.randint(0, u.max_steps - 5))
+        return u
+
+    tail = [int(v) for v in rs.randint(0, 7, size=3)]
+    if hook == 1:
+        u = fresh()
+        if _face(u, _find(u, lambda c: c is u.obj), rs):
+            out.append((u, [A.pickup] + tail))
+    elif hook == 2:
+        u = fresh()
+        key = _find(u, lambda c: c.type == "key" and c.color == u.door.color)
+        if key:
+            u.carrying = u.grid.get(*key)
+            u.grid.set(*key, None)
+            if _face(u, _find(u, lambda c: c is u.door), rs):
+                out.append((u, [A.toggle] + tail))
+                u2 = copy.deepcopy(u)
+                u2.carrying = None                       # no key: the toggle must not open it
+                out.append((u2, [A.toggle] + tail))
+    elif hook == 3:
+        for want in (True, False):
+            u = fresh()
+            P = _find(u, lambda c: c.can_pickup() and ((c.type == u.targetType and c.color == u.targetColor) == want))
+            if P and _face(u, P, rs):
+                out.append((u, [A.pickup] + tail))
+    elif hook == 4:
+        for k in range(4):
+            u = fresh()
+            if _face(u, u.doorPos[k], rs):
+                out.append((u, [A.done] + tail))
+    elif hook == 5:
+        u = fresh()
+        if _face(u, u.target_pos, rs):
+            out.append((u, [A.done] + tail))
+            u2 = copy.deepcopy(u)
+            out.append((u2, [A.toggle] + tail))
+        u3 = fresh()
+        out.append((u3, [A.done] + tail))                 # wherever the agent starts: done without reward (usually)
+    elif hook == 6:
+        for near in (True, False):
+            u = fresh()
+            mv = _find(u, lambda c: c.type == u.move_type and c.color == u.moveColor)
+            if not mv:
+                continue
+            u.carrying = u.grid.get(*mv)
+            u.grid.set(*mv, None)
+            tx, ty = u.target_pos
+            cells = [(x, y) for x in range(1, u.width - 1) for y in range(1, u.height - 1) if u.grid.get(x, y) is None
+                     and ((abs(x - tx) <= 1 and abs(y - ty) <= 1) == near)]
+            rs.shuffle(cells)
+            for F in cells:
+                if _face(u, F, rs):
+                    out.append((u, [A.drop] + tail))
+                    break
+        u = fresh()                                      # wrong pickup
+        P = _find(u, lambda c: c.can_pickup() and not (c.type == u.move_type and c.color == u.moveColor))
+        if P and _face(u, P, rs):
+            out.append((u, [A.pickup] + tail))
+    elif hook == 7:
+        for red_open in (True, False):
+            u = fresh()
+            u.red_door.is_open = red_open
+            if _face(u, _find(u, lambda c: c is u.blue_door), rs):
+                out.append((u, [A.toggle] + tail))
+        u = fresh()
+        u.blue_door.is_open = True                        # blue already open, then red
+        u.red_door.is_open = False
+        # (blue_after -> failure branch fires on any action)
+        out.append((u, [A.left] + tail))
+    elif hook == 8:
+        for P in (u0.success_pos, u0.failure_pos):
+            u = fresh()
+            if _face(u, P, rs):
+                out.append((u, [A.forward] + tail))
+        u = fresh()
+        out.append((u, [A.pickup, A.pickup] + tail))      # pickup acts as toggle
+    return out
+
+
+def hook_traces():
+    """SURVEY §8f rank 2, env files whose step() adds a success/failure rule (MGB_HOOK_*).  Levels and their
+    hook attributes come from the reference; random-action traces (pool restore by deepcopy of the reference
+    env) plus directed scenarios that force every hook branch."""
+    import copy
+    seed, K = 909, 6
+    for env_id, T in (("MiniGrid-Unlock-v0", 400), ("MiniGrid-UnlockPickup-v0", 300), ("MiniGrid-BlockedUnlockPickup-v0", 300),
+                      ("MiniGrid-Fetch-8x8-N3-v0", 500), ("MiniGrid-GoToDoor-6x6-v0", 500), ("MiniGrid-GoToObject-8x8-N2-v0", 400),
+                      ("MiniGrid-PutNear-8x8-N3-v0", 400), ("MiniGrid-RedBlueDoors-6x6-v0", 800), ("MiniGrid-MemoryS7-v0", 700),
+                      ("MiniGrid-MemoryS13Random-v0", 300), ("MiniGrid-LockedRoom-v0", 300), ("MiniGrid-Playground-v0", 250)):
+        env = R.make(env_id)
+        cfg = config_of(env)
+        hook = cfg["hook"]
+        levels = []
+        for k in range(K):
+            env.seed(200 + k)
+            obs = env.reset()
+            s = R.snapshot(env)
+            levels.append(dict(grid=s["grid"], aux=s["aux"], agent=s["agent"][:3].copy(), mission=obs["mission"],
+                               hp=hook_params_of(env.unwrapped, hook), env=copy.deepcopy(env.unwrapped)))
+        idx = [8, 123]
+        tr = dict(obs=[], dir=[], reward=[], done=[], actions=[], obs0=[], dir0=[], lvl=[], grid_end=[], agent_end=[])
+        for k, i in enumerate(idx):
+            pick = R.PhiloxShim(seed, i, 0)
+            lv = [pick.randint(0, K)]
+            u = copy.deepcopy(levels[lv[-1]]["env"])
+            obs = u.gen_obs()
+            a = np.random.RandomState(600 + k).randint(0, 7, size=T).astype(np.uint8)
+            O, D, RW, DN = [obs["image"].copy()], [obs["direction"]], [], []
+            ep = 1
+            for t in range(T):
+                obs, r, d, _ = u.step(int(a[t]))
+                if d:
+                    pick.new_episode(ep)
+                    ep += 1
+                    lv.append(pick.randint(0, K))
+                    u = copy.deepcopy(levels[lv[-1]]["env"])
+                    obs = u.gen_obs()
+                O.append(obs["image"].copy()); D.append(obs["direction"]); RW.append(float(r)); DN.append(int(d))
+            s = R.snapshot(u)
+            tr["obs0"].append(O[0]); tr["dir0"].append(D[0]); tr["obs"].append(np.stack(O[1:])); tr["dir"].append(np.array(D[1:], np.uint8))
+            tr["reward"].append(np.array(RW)); tr["done"].append(np.array(DN, np.uint8)); tr["actions"].append(a)
+            tr["lvl"].append(np.array(lv + [-1] * (T + 1 - len(lv)), np.int32)); tr["grid_end"].append(s["grid"]); tr["agent_end"].append(s["agent"])
+        # directed scenarios (state upload, no reset)
+        rs = np.random.RandomState(4321)
+        sc = dict(sc_level=[], sc_grid=[], sc_aux=[], sc_agent=[], sc_carrying=[], sc_actions=[], sc_obs=[], sc_dir=[], sc_reward=[], sc_done=[])
+        for li, L in enumerate(levels):
+            for u, acts in directed_scenarios(L["env"], hook, rs):
+                s0 = R.snapshot(u)
+                O, D, RW, DN = [], [], [], []
+                for a_ in acts:
+                    obs, r, d, _ = u.step(int(a_))
+                    O.append(obs["image"].copy()); D.append(obs["direction"]); RW.append(float(r)); DN.append(int(d))
+                sc["sc_level"].append(li); sc["sc_grid"].append(s0["grid"]); sc["sc_aux"].append(s0["aux"]); sc["sc_agent"].append(s0["agent"])
+                sc["sc_carrying"].append(s0["carrying"]); sc["sc_actions"].append(np.array(acts, np.uint8)); sc["sc_obs"].append(np.stack(O))
+                sc["sc_dir"].append(np.array(D, np.uint8)); sc["sc_reward"].append(np.array(RW)); sc["sc_done"].append(np.array(DN, np.uint8))
+        maxA = max([len(a_) for a_ in sc["sc_actions"]] + [1])
+        sc_len = np.array([len(a_) for a_ in sc["sc_actions"]], np.int32)        # true lengths (before padding)
+        for key in ("sc_actions", "sc_obs", "sc_dir", "sc_reward", "sc_done"):       # pad to a common length with action 6 (done = no-op for base)
+            sc[key] = [np.concatenate([v, np.repeat(v[-1:], maxA - len(v), axis=0)]) if len(v) < maxA else v for v in sc[key]]
+        path = os.path.join(OUT, "hook_%s.npz" % short(env_id))
+        extra = {k: (np.stack(v) if len(v) else np.zeros((0,))) for k, v in sc.items()}
+        np.savez_compressed(path, env_id=env_id, seed=np.uint64(seed), env_indices=np.array(idx, np.int64),
+                            cfg_keys=np.array(list(cfg.keys())), cfg_vals=np.array(list(cfg.values()), np.int32),
+                            level_grid=np.stack([l["grid"] for l in levels]), level_aux=np.stack([l["aux"] for l in levels]),
+                            level_agent=np.stack([l["agent"] for l in levels]).astype(np.int32),
+                            level_hook=np.array([l["hp"] for l in levels], np.int32),
+                            level_mission=np.array([l["mission"] for l in levels]), sc_len=sc_len,
+                            **{k: np.stack(v) for k, v in tr.items()}, **extra)
+        print("%-44s %6.1f KB hook=%d episodes=%s rewards(random)=%d scenarios=%d (reward>0: %d, done: %d)" % (
+            os.path.basename(path), os.path.getsize(path) / 1024, hook, [int((l >= 0).sum()) for l in tr["lvl"]],
+            sum(int((r != 0).sum()) for r in tr["reward"]), len(sc["sc_level"]),
+            sum(int((r[:1] > 0).sum()) for r in sc["sc_reward"]), sum(int(d[0]) for d in sc["sc_done"])))
+
+
 def reward_table():
     """_reward() (minigrid.py:933-937) evaluated BY THE REFERENCE for every step_count of every
     max_steps in the registry (and 50 beyond): r_<max_steps>[k] = reward at step_count == k."""
@@ -462,3 +687,4 @@ if __name__ == "__main__":
     wrapper_traces()
     pool_traces()
     viewsize_traces()
+    hook_traces()

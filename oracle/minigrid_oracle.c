@@ -224,7 +224,19 @@ typedef struct {
     int err;
     Room rooms[MAXR][MAXR];    /* room_grid[j][i] */
     const struct orc_vec *owner;
+    int level;                 /* ORC_GEN_POOL: level being played */
 } Env;
+
+struct orc_vec {
+    orc_config cfg;
+    int n;
+    Env *envs;
+    Obj *cells;
+    int pool_n;          /* ORC_GEN_POOL */
+    Obj *pool_cells;     /* [pool_n][W*H], index j*W+i like Grid */
+    int *pool_agent;     /* [pool_n][3] */
+    int *pool_hook;      /* [pool_n][16] or NULL */
+};
 
 static int rand_int(Env *e, int low, int high) {   /* minigrid.py:939-944 */
     if (e->tape) {
@@ -587,6 +599,71 @@ static int base_step(Env *e, int action, double *reward, int *done) {
     return bad ? -1 : 0;
 }
 
+static int door_is_open(Env *e, int x, int y) { Obj o = grid_get(&e->grid, x, y); return o.has && o.type == T_DOOR && o.is_open; }
+static int adj4(const Env *e, int x, int y) { return (e->ax == x && abs(e->ay - y) == 1) || (e->ay == y && abs(e->ax - x) == 1); }
+
+/* step() of the stock env files that add a success/failure rule around MiniGridEnv.step; the per-level
+ * attributes (self.obj, self.door, target_pos, ...) come with the level pool */
+static int pool_hook_step(Env *e, int action, double *reward, int *done) {
+    const struct orc_vec *v = e->owner;
+    const int *hp = v->pool_hook + (size_t)e->level * 16;
+    const int ttype = hp[0], tcol = hp[1], mtype = hp[2], mcol = hp[3], tx = hp[4], ty = hp[5];
+    const int Ax = hp[6], Ay = hp[7], Bx = hp[8], By = hp[9], Cx = hp[10], Cy = hp[11], Dx = hp[12], Dy = hp[13];
+    const Obj pre = e->carrying;
+    int red_before = 0, blue_before = 0;
+    if (e->cfg.hook == 8 && action == A_PICKUP) action = A_TOGGLE;                    /* memory.py:89-90 */
+    if (e->cfg.hook == 7) { red_before = door_is_open(e, Ax, Ay); blue_before = door_is_open(e, Bx, By); }
+    int rc = base_step(e, action, reward, done);
+    switch (e->cfg.hook) {
+    case 1:   /* unlockpickup.py:34-42, blockedunlockpickup.py:38-46: carrying == self.obj */
+        if (action == A_PICKUP && e->carrying.has && e->carrying.type == ttype && e->carrying.color == tcol) { *reward = reward_fn(e); *done = 1; }
+        break;
+    case 2:   /* unlock.py:33-41 */
+        if (action == A_TOGGLE && door_is_open(e, Ax, Ay)) { *reward = reward_fn(e); *done = 1; }
+        break;
+    case 3:   /* fetch.py:74-86 */
+        if (e->carrying.has) {
+            if (e->carrying.color == tcol && e->carrying.type == ttype) { *reward = reward_fn(e); *done = 1; }
+            else { *reward = 0; *done = 1; }
+        }
+        break;
+    case 4:   /* gotodoor.py:72-93 */
+        if (action == A_DONE) {
+            if (adj4(e, tx, ty)) *reward = reward_fn(e);
+            if (adj4(e, Ax, Ay) || adj4(e, Bx, By) || adj4(e, Cx, Cy) || adj4(e, Dx, Dy)) *done = 1;
+        }
+        break;
+    case 5:   /* gotoobject.py:68-84 */
+        if (action == A_TOGGLE) *done = 1;
+        if (action == A_DONE) { if (abs(e->ax - tx) <= 1 && abs(e->ay - ty) <= 1) *reward = reward_fn(e); *done = 1; }
+        break;
+    case 6: { /* putnear.py:91-112 */
+        const int ox = e->ax + DIRX[e->adir], oy = e->ay + DIRY[e->adir];
+        if (action == A_PICKUP && e->carrying.has)
+            if (e->carrying.type != mtype || e->carrying.color != mcol) *done = 1;
+        if (action == A_DROP && pre.has) {
+            Obj f = grid_get(&e->grid, ox, oy);
+            /* `self.grid.get(ox, oy) is preCarrying`: the drop happened this step */
+            if (!e->carrying.has && f.has && f.type == pre.type && f.color == pre.color)
+                if (abs(ox - tx) <= 1 && abs(oy - ty) <= 1) *reward = reward_fn(e);
+            *done = 1;
+        }
+        break;
+    }
+    case 7: { /* redbluedoors.py:44-66 */
+        const int red_after = door_is_open(e, Ax, Ay), blue_after = door_is_open(e, Bx, By);
+        if (blue_after) { if (red_before) { *reward = reward_fn(e); *done = 1; } else { *reward = 0; *done = 1; } }
+        else if (red_after) { if (blue_before) { *reward = 0; *done = 1; } }
+        break;
+    }
+    case 8:   /* memory.py:88-100 */
+        if (e->ax == Ax && e->ay == Ay) { *reward = reward_fn(e); *done = 1; }
+        if (e->ax == Bx && e->ay == By) { *reward = 0; *done = 1; }
+        break;
+    }
+    return rc;
+}
+
 /* env.step including the subclass hooks */
 static int env_step(Env *e, int action, double *reward, int *done) {
     int rc;
@@ -608,6 +685,7 @@ static int env_step(Env *e, int action, double *reward, int *done) {
         if (action == A_FORWARD && not_clear) { *reward = -1; *done = 1; }
         return rc;
     }
+    if (e->cfg.gen == ORC_GEN_POOL && e->cfg.hook) return pool_hook_step(e, action, reward, done);
     rc = base_step(e, action, reward, done);
     if (e->cfg.gen == ORC_GEN_KEYCORRIDOR) {        /* envs/keycorridor.py:51-59 */
         if (action == A_PICKUP)
@@ -617,15 +695,6 @@ static int env_step(Env *e, int action, double *reward, int *done) {
 }
 
 /* ---- vector front-end --------------------------------------------------- */
-struct orc_vec {
-    orc_config cfg;
-    int n;
-    Env *envs;
-    Obj *cells;
-    int pool_n;          /* ORC_GEN_POOL */
-    Obj *pool_cells;     /* [pool_n][W*H], index j*W+i like Grid */
-    int *pool_agent;     /* [pool_n][3] */
-};
 
 static void gen_pool(Env *e) {
     const struct orc_vec *v = e->owner;
@@ -635,12 +704,16 @@ static void gen_pool(Env *e) {
     memcpy(e->grid.c, v->pool_cells + (size_t)lvl * cells, cells * sizeof(Obj));
     e->ax = v->pool_agent[lvl * 3]; e->ay = v->pool_agent[lvl * 3 + 1]; e->adir = v->pool_agent[lvl * 3 + 2];
     e->has_agent = 1;
+    e->level = lvl;
 }
 
-int orc_vec_set_level_pool(orc_vec *v, int32_t n_levels, const uint8_t *grid, const uint8_t *aux, const int32_t *agent) {
+int orc_vec_set_level_pool(orc_vec *v, int32_t n_levels, const uint8_t *grid, const uint8_t *aux, const int32_t *agent,
+                           const int32_t *hook_params) {
     const int W = v->cfg.width, H = v->cfg.height;
     const size_t cells = (size_t)W * H;
-    free(v->pool_cells); free(v->pool_agent);
+    free(v->pool_cells); free(v->pool_agent); free(v->pool_hook);
+    v->pool_hook = NULL;
+    if (hook_params) { v->pool_hook = (int *)calloc((size_t)n_levels * 16, sizeof(int)); for (int i = 0; i < n_levels * 16; i++) v->pool_hook[i] = hook_params[i]; }
     v->pool_cells = (Obj *)calloc((size_t)n_levels * cells, sizeof(Obj));
     v->pool_agent = (int *)calloc((size_t)n_levels * 3, sizeof(int));
     v->pool_n = n_levels;
@@ -679,7 +752,9 @@ orc_vec *orc_vec_create(const orc_config *cfg, uint64_t seed, int64_t env0, int3
     }
     return v;
 }
-void orc_vec_destroy(orc_vec *v) { if (!v) return; free(v->envs); free(v->cells); free(v->pool_cells); free(v->pool_agent); free(v); }
+void orc_vec_destroy(orc_vec *v) { if (!v) return; free(v->envs); free(v->cells); free(v->pool_cells); free(v->pool_agent); free(v->pool_hook); free(v); }
+int orc_vec_get_levels(orc_vec *v, int32_t *levels) { for (int i = 0; i < v->n; i++) levels[i] = v->envs[i].level; return 0; }
+int orc_vec_set_levels(orc_vec *v, const int32_t *levels) { for (int i = 0; i < v->n; i++) v->envs[i].level = levels[i]; return 0; }
 
 int orc_vec_set_tape(orc_vec *v, const int32_t *draws, const int64_t *offsets) {
     for (int i = 0; i < v->n; i++) {

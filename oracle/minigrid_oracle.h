@@ -42,6 +42,9 @@ typedef struct {
     int32_t random_start;   /* Empty-Random / DynObs-Random: agent_start_pos=None */
     int32_t lava_v1;        /* 'v1' in type(env).__name__ (minigrid.py:1263-1266): true for e.g. DoorKeyEn*v1*6x16 */
     int32_t view_size;      /* agent_view_size (minigrid.py:776,795; ViewSizeWrapper wrappers.py:579-608); 0 = 7 */
+    int32_t hook;           /* ORC_GEN_POOL only: 1 pickup target (unlockpickup.py:34-42) 2 unlock (unlock.py:33-41)
+                               3 fetch (fetch.py:74-86) 4 gotodoor (gotodoor.py:72-93) 5 gotoobject (gotoobject.py:68-84)
+                               6 putnear (putnear.py:91-112) 7 redbluedoors (redbluedoors.py:44-66) 8 memory (memory.py:88-100) */
 } orc_config;
 
 #define ORC_OBS_BYTES 147
@@ -56,7 +59,12 @@ void orc_set_threads(int nthreads);
 
 /* level pool for ORC_GEN_POOL: grid [K][W][H][3], aux [K][W][H] or NULL, agent [K][3] = x,y,dir.
  * reset picks level rand_int(0, K) (first draw of the episode's stream). */
-int orc_vec_set_level_pool(orc_vec *v, int32_t n_levels, const uint8_t *grid, const uint8_t *aux, const int32_t *agent);
+/* hook_params [K][16] (NULL if hook == 0): target_type, target_color, move_type, move_color, target_x, target_y,
+ * A.x, A.y, B.x, B.y, C.x, C.y, D.x, D.y, 0, 0 */
+int orc_vec_set_level_pool(orc_vec *v, int32_t n_levels, const uint8_t *grid, const uint8_t *aux, const int32_t *agent,
+                           const int32_t *hook_params);
+int orc_vec_get_levels(orc_vec *v, int32_t *levels);
+int orc_vec_set_levels(orc_vec *v, const int32_t *levels);
 
 /* RNG tape (parity mode 2): draws[offsets[i] .. offsets[i+1]) are the raw randint
  * results env i will consume, in order.  NULL disables. */

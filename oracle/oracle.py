@@ -20,7 +20,7 @@ MAX_OBST = 8
 class OrcConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "gen", "width", "height", "max_steps", "see_through", "n_actions",
-        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1", "view_size")]
+        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1", "view_size", "hook")]
 
 
 def build(force=False):
@@ -43,7 +43,9 @@ def lib():
         L.orc_vec_destroy.argtypes = [C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_int]
         L.orc_vec_set_tape.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        L.orc_vec_set_level_pool.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_vec_set_level_pool.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_vec_get_levels.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_vec_set_levels.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_vec_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 3
         L.orc_vec_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.orc_vec_rollout.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int] + [C.c_void_p] * 4
@@ -96,12 +98,22 @@ class OracleVec:
         self._tape = (np.ascontiguousarray(draws, np.int32), np.ascontiguousarray(offsets, np.int64))
         self._chk(self._L.orc_vec_set_tape(self._h, _p(self._tape[0]), _p(self._tape[1])))
 
-    def set_level_pool(self, grid, aux, agent):
+    def set_level_pool(self, grid, aux, agent, hook_params=None):
         g = np.ascontiguousarray(grid, np.uint8)
         K = g.shape[0]
         a = None if aux is None else np.ascontiguousarray(aux, np.uint8)
         ag = np.ascontiguousarray(np.asarray(agent)[:, :3], np.int32)
-        self._chk(self._L.orc_vec_set_level_pool(self._h, K, _p(g), _p(a), _p(ag)))
+        hp = None if hook_params is None else np.ascontiguousarray(hook_params, np.int32).reshape(K, 16)
+        self._chk(self._L.orc_vec_set_level_pool(self._h, K, _p(g), _p(a), _p(ag), _p(hp)))
+
+    def get_levels(self):
+        out = np.zeros(self.n, np.int32)
+        self._chk(self._L.orc_vec_get_levels(self._h, _p(out)))
+        return out
+
+    def set_levels(self, levels):
+        lv = np.ascontiguousarray(levels, np.int32)
+        self._chk(self._L.orc_vec_set_levels(self._h, _p(lv)))
 
     def reset(self, mask=None):
         obs = np.zeros((self.n, self.V, self.V, 3), np.uint8)
