@@ -78,6 +78,7 @@ constexpr int CODE_EMPTY = code_of(T_EMPTY, 0, 0);            // 21
 constexpr int CODE_WALL = code_of(T_WALL, C_GREY, 0);          // out-of-grid cells (minigrid.py:469)
 constexpr int CODE_GOAL = code_of(T_GOAL, C_GREEN, 0);
 constexpr int CODE_TGOAL0 = 231;                               // + colour: Goal(toggletimes=0), overlap=True
+constexpr int CODE_KEYBOX0 = 238;                              // + key colour: grey Box(contains=Key(colour)) (obstructedmaze.py:68-73)
 constexpr uint32_t EMPTY_WORD = 0x15151515u;                   // 4 x CODE_EMPTY
 static_assert(CODE_EMPTY == 0x15, "EMPTY_WORD");
 
@@ -91,8 +92,10 @@ enum : uint32_t { F_OPAQUE = 1, F_OVERLAP = 2, F_PICKUP = 4, F_TGOAL = 8, F_LAVA
 __host__ __device__ inline uint32_t lut_entry(int code) {
     int t, c, s;
     uint32_t f = 0;
-    if (code >= CODE_TGOAL0) {
-        if (code >= CODE_TGOAL0 + 7) return 0;
+    if (code >= CODE_KEYBOX0) {
+        if (code >= CODE_KEYBOX0 + 7) return 0;
+        t = T_BOX; c = C_GREY; s = 0;                    // looks like any grey box; the key appears when it is toggled
+    } else if (code >= CODE_TGOAL0) {
         t = T_GOAL; c = code - CODE_TGOAL0; s = 0; f = F_TGOAL;
     } else {
         t = code / 21; c = (code % 21) / 3; s = code % 3;
@@ -552,6 +555,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         uint32_t nv = CODE_EMPTY;
         if (drop) nv = (uint32_t)e.carry;
         if (tog_door) nv = fc - ds + ns;
+        if (tog_vanish && fc >= CODE_KEYBOX0) nv = (uint32_t)code_of(T_KEY, (int)fc - CODE_KEYBOX0, 0);   // Box.toggle: cell := contents (:355-360)
         cell_wr(st, fidx, nv);
         e.dirty = true;
         e.carry = pick ? (int)fc : (drop ? 0 : e.carry);
@@ -988,6 +992,10 @@ __device__ __forceinline__ int encode_cell(int t, int c, int s, int auxbits, uin
     if (t <= T_EMPTY) return CODE_EMPTY;
     if (t != T_DOOR) s = 0;                               // WorldObj.decode ignores state for non-doors
     if (t == T_GOAL && (auxbits & 1)) return CODE_TGOAL0 + c;
+    if (t == T_BOX && ((auxbits >> 1) & 7)) {           // Box.contains = Key(colour k): aux bits 1-3 = k+1; only grey boxes
+        if (c != C_GREY || ((auxbits >> 1) & 7) > 7) { err |= ERR_CODE; return CODE_EMPTY; }
+        return CODE_KEYBOX0 + ((auxbits >> 1) & 7) - 1;
+    }
     return code_of(t, c, s);
 }
 
@@ -1027,7 +1035,7 @@ __global__ void k_set_state(const StateIO io) {
         if (io.carrying) {
             const uint8_t *q = io.carrying + n * 3;
             int code = 0;
-            if (q[0] != 0) { code = encode_cell(q[0], q[1], q[2], 0, err); if (code == CODE_EMPTY) code = 0; }
+            if (q[0] != 0) { code = encode_cell(q[0], q[1], q[0] == T_BOX ? 0 : q[2], q[0] == T_BOX ? q[2] : 0, err); if (code == CODE_EMPTY) code = 0; }
             w = (w & 0x00FFFFFFu) | ((uint32_t)code << 24);
         }
         *dst = w;
@@ -1083,7 +1091,8 @@ __global__ void k_get_state(const StateIO io, int full_obs) {
                 if (idx == aidx) { g[0] = T_AGENT; g[1] = 0; g[2] = (uint8_t)adir; }
                 else { g[0] = x & 0xFF; g[1] = (x >> 8) & 0xFF; g[2] = (x >> 16) & 0xFF; }
             }
-            if (io.aux) io.aux[(size_t)n * cells + idx] = ((x >> 24) & F_TGOAL) ? 1 : 0;
+            const uint32_t cc = (w >> (8 * b)) & 0xFF;
+            if (io.aux) io.aux[(size_t)n * cells + idx] = (((x >> 24) & F_TGOAL) ? 1 : 0) | (cc >= CODE_KEYBOX0 && cc < CODE_KEYBOX0 + 7 ? ((cc - CODE_KEYBOX0 + 1) << 1) : 0);
         }
     } else if (k == c.GW) {
         if (io.agent) { int32_t *a = io.agent + n * 4; a[0] = w & 0xFF; a[1] = (w >> 8) & 0xFF; a[2] = (w >> 16) & 3; }
@@ -1092,6 +1101,8 @@ __global__ void k_get_state(const StateIO io, int full_obs) {
             const uint32_t code = w >> 24;
             const uint32_t x = code ? lut_entry(code) : 0;
             q[0] = x & 0xFF; q[1] = (x >> 8) & 0xFF; q[2] = (x >> 16) & 0xFF;
+            // a carried box keeps its contents: the (otherwise always 0) state byte carries the aux bits
+            if (code >= CODE_KEYBOX0 && code < CODE_KEYBOX0 + 7) q[2] = (uint8_t)((code - CODE_KEYBOX0 + 1) << 1);
         }
     } else if (k == c.GW + 1) {
         if (io.agent) io.agent[n * 4 + 3] = w & 0xFFFF;

@@ -36,7 +36,7 @@ OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 MAX_OBST = 8
 SNAP_EVERY = 50
 
-HOOK_OF_CLASS = {"UnlockPickup": 1, "BlockedUnlockPickup": 1, "Unlock": 2, "FetchEnv": 3, "GoToDoorEnv": 4, "GoToObjectEnv": 5,
+HOOK_OF_CLASS = {"UnlockPickup": 1, "BlockedUnlockPickup": 1, "ObstructedMazeEnv": 1, "Unlock": 2, "FetchEnv": 3, "GoToDoorEnv": 4, "GoToObjectEnv": 5,
                  "PutNearEnv": 6, "RedBlueDoorEnv": 7, "MemoryEnv": 8}
 GEN_OF_CLASS = {"EmptyEnv": 0, "DoorKeyEnv": 1, "FourRoomsEnv": 2, "DynamicObstaclesEnv": 3, "KeyCorridor": 4}
 
@@ -515,6 +515,12 @@ def directed_scenarios(u0, hook, rs):
         u = fresh()
         if _face(u, _find(u, lambda c: c is u.obj), rs):
             out.append((u, [A.pickup] + tail))
+        box = _find(u0, lambda c: c.type == "box" and c.contains is not None)
+        if box:                                          # ObstructedMaze: keys hidden in boxes (Box.contains)
+            for acts in ([A.toggle, A.pickup, A.drop], [A.pickup, A.left, A.drop, A.toggle, A.pickup], [A.pickup, A.right, A.right, A.drop]):
+                u = fresh()
+                if _face(u, box, rs):
+                    out.append((u, list(acts) + tail))
     elif hook == 2:
         u = fresh()
         key = _find(u, lambda c: c.type == "key" and c.color == u.door.color)
@@ -595,7 +601,8 @@ def hook_traces():
     for env_id, T in (("MiniGrid-Unlock-v0", 400), ("MiniGrid-UnlockPickup-v0", 300), ("MiniGrid-BlockedUnlockPickup-v0", 300),
                       ("MiniGrid-Fetch-8x8-N3-v0", 500), ("MiniGrid-GoToDoor-6x6-v0", 500), ("MiniGrid-GoToObject-8x8-N2-v0", 400),
                       ("MiniGrid-PutNear-8x8-N3-v0", 400), ("MiniGrid-RedBlueDoors-6x6-v0", 800), ("MiniGrid-MemoryS7-v0", 700),
-                      ("MiniGrid-MemoryS13Random-v0", 300), ("MiniGrid-LockedRoom-v0", 300), ("MiniGrid-Playground-v0", 250)):
+                      ("MiniGrid-MemoryS13Random-v0", 300), ("MiniGrid-LockedRoom-v0", 300), ("MiniGrid-Playground-v0", 250),
+                      ("MiniGrid-ObstructedMaze-1Dlhb-v0", 400), ("MiniGrid-ObstructedMaze-Full-v0", 300)):
         env = R.make(env_id)
         cfg = config_of(env)
         hook = cfg["hook"]

@@ -44,9 +44,10 @@ typedef struct {
     int8_t toggletimes;           /* Goal :158, Box :336 */
     uint8_t overlap;              /* Goal :160 */
     uint8_t is_target;            /* identity of KeyCorridor.obj (keycorridor.py:48) */
+    uint8_t contains_key;         /* Box.contains = Key(colour k): k+1, 0 = None (minigrid.py:335; obstructedmaze.py:68-73) */
 } Obj;
 
-static const Obj NONE = { 0, 0, 0, 0, 0, 0, 0, 0 };
+static const Obj NONE = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 
 static Obj mk(uint8_t type, uint8_t color) {
     Obj o = NONE; o.has = 1; o.type = type; o.color = color; return o;
@@ -549,7 +550,7 @@ static void obj_toggle(Env *e, int x, int y) {
         o.is_open = !o.is_open; grid_set(g, x, y, o);
     } else if (o.type == T_BOX) {
         o.toggletimes -= 1;
-        if (o.toggletimes <= 0) grid_set(g, x, y, NONE);   /* contains == None */
+        if (o.toggletimes <= 0) grid_set(g, x, y, o.contains_key ? mk(T_KEY, (uint8_t)(o.contains_key - 1)) : NONE);   /* cell := contents */
         else grid_set(g, x, y, o);
     } else if (o.type == T_GOAL) {
         if (o.toggletimes > 0) {
@@ -724,6 +725,7 @@ int orc_vec_set_level_pool(orc_vec *v, int32_t n_levels, const uint8_t *grid, co
                 Obj o;
                 if (obj_decode(grid[ci * 3], grid[ci * 3 + 1], grid[ci * 3 + 2], &o)) { snprintf(g_err, sizeof g_err, "orc_vec_set_level_pool: bad cell code"); return -1; }
                 if (o.has && o.type == T_GOAL) { o.color = grid[ci * 3 + 1]; if (aux && (aux[ci] & 1)) { o.toggletimes = 0; o.overlap = 1; } }
+                if (o.has && o.type == T_BOX && aux) o.contains_key = (aux[ci] >> 1) & 7;
                 v->pool_cells[(size_t)l * cells + (size_t)j * W + i] = o;
             }
         for (int k = 0; k < 3; k++) v->pool_agent[l * 3 + k] = agent[l * 3 + k];
@@ -868,12 +870,12 @@ int orc_vec_get_state(orc_vec *v, uint8_t *grid, uint8_t *aux, int32_t *agent,
                     uint8_t *p = grid + ci * 3;
                     if (!o.has) { p[0] = T_EMPTY; p[1] = 0; p[2] = 0; } else obj_encode(&o, p);
                 }
-                if (aux) aux[ci] = (o.has && o.type == T_GOAL && o.overlap) ? 1 : 0;
+                if (aux) aux[ci] = (uint8_t)(((o.has && o.type == T_GOAL && o.overlap) ? 1 : 0) | ((o.has && o.type == T_BOX) ? (o.contains_key << 1) : 0));
             }
         if (agent) { agent[n * 4] = e->ax; agent[n * 4 + 1] = e->ay; agent[n * 4 + 2] = e->adir; agent[n * 4 + 3] = e->step_count; }
         if (carrying) {
             uint8_t *p = carrying + n * 3; p[0] = p[1] = p[2] = 0;
-            if (e->carrying.has) obj_encode(&e->carrying, p);
+            if (e->carrying.has) { obj_encode(&e->carrying, p); if (e->carrying.type == T_BOX) p[2] = (uint8_t)(e->carrying.contains_key << 1); }
         }
         if (obstacles) for (int k = 0; k < ORC_MAX_OBST; k++) {
             obstacles[(n * ORC_MAX_OBST + k) * 2] = (int16_t)(k < v->cfg.n_obstacles ? e->obst[k][0] : 0);
@@ -900,6 +902,7 @@ int orc_vec_set_state(orc_vec *v, const uint8_t *grid, const uint8_t *aux, const
                     snprintf(g_err, sizeof g_err, "orc_vec_set_state: bad cell code"); return -1;
                 }
                 if (o.has && o.type == T_GOAL) { o.color = grid[ci * 3 + 1]; if (aux && (aux[ci] & 1)) { o.toggletimes = 0; o.overlap = 1; } }
+                if (o.has && o.type == T_BOX && aux) o.contains_key = (aux[ci] >> 1) & 7;
                 if (o.has && e->target_type && o.type == e->target_type && o.color == e->target_color) o.is_target = 1;
                 e->grid.c[j * W + i] = o;
             }
@@ -907,7 +910,8 @@ int orc_vec_set_state(orc_vec *v, const uint8_t *grid, const uint8_t *aux, const
         e->has_agent = 1;
         e->carrying = NONE;
         if (carrying && carrying[n * 3]) {
-            if (obj_decode(carrying[n * 3], carrying[n * 3 + 1], carrying[n * 3 + 2], &e->carrying)) return -1;
+            if (obj_decode(carrying[n * 3], carrying[n * 3 + 1], carrying[n * 3] == T_BOX ? 0 : carrying[n * 3 + 2], &e->carrying)) return -1;
+            if (e->carrying.type == T_BOX) e->carrying.contains_key = (carrying[n * 3 + 2] >> 1) & 7;
             if (e->target_type && e->carrying.type == e->target_type && e->carrying.color == e->target_color) e->carrying.is_target = 1;
         }
         if (obstacles) for (int k = 0; k < v->cfg.n_obstacles; k++) {

@@ -299,6 +299,20 @@ class TapeRecorder:
 # --------------------------------------------------------------------------
 # State snapshot of a reference env
 # --------------------------------------------------------------------------
+def _box_aux(c):
+    """aux bits 1-3 of a Box: 0 = contains None, k+1 = contains Key(colour k).  Only what obstructedmaze.py:68-73
+    builds is representable: a grey box holding a default key."""
+    mg = sys.modules["gym_minigrid.minigrid"]
+    if c.triage_color is not None or c.toggletimes != 1:
+        raise NotImplementedError("non-default box")
+    if c.contains is None:
+        return 0
+    k = c.contains
+    if k.type != "key" or k.contains is not None or c.color != "grey":
+        raise NotImplementedError("box contents other than a key in a grey box")
+    return (mg.COLOR_TO_IDX[k.color] + 1) << 1
+
+
 def snapshot(env):
     """-> dict(grid uint8[W,H,3], aux uint8[W,H], agent int32[4]=(x,y,dir,step_count),
     carrying uint8[3] (0,0,0 = none), obstacles int16[n,2], target uint8[2]=(type,color))"""
@@ -320,11 +334,12 @@ def snapshot(env):
                 if c.toggletimes not in (0, 1) or (c.toggletimes <= 0) != bool(c.overlap):
                     raise NotImplementedError("goal toggletimes")
             if c.type == "box":
-                if c.triage_color is not None or c.toggletimes != 1 or c.contains is not None:
-                    raise NotImplementedError("non-default box")
+                aux[x, y] |= _box_aux(c)
     carrying = np.zeros(3, np.uint8)
     if env.carrying is not None:
         carrying[:] = env.carrying.encode()
+        if env.carrying.type == "box":
+            carrying[2] = _box_aux(env.carrying)        # a carried box keeps its contents (state byte is otherwise 0)
     obst = np.zeros((0, 2), np.int16)
     if hasattr(env, "obstacles"):
         obst = np.array([tuple(int(v) for v in o.cur_pos) for o in env.obstacles], np.int16).reshape(-1, 2)

@@ -25,13 +25,13 @@ def header_functions():
 def test_registry_contract():
     for i in HEADLINE:
         assert i in mgb.env_list
-    assert len(mgb.env_list) == len(set(mgb.env_list)) == 69      # 24 with device generators + 45 level-pool ids
+    assert len(mgb.env_list) == len(set(mgb.env_list)) == 78      # 24 with device generators + 54 level-pool ids
     with pytest.raises(AssertionError):            # register.py:12  id must start with "MiniGrid-"
         mgb.register("Foo-v0", "gym_minigrid.envs:EmptyEnv")
     with pytest.raises(AssertionError):            # register.py:13  ids are unique
         mgb.register("MiniGrid-Empty-8x8-v0", "gym_minigrid.envs:EmptyEnv")
     with pytest.raises(KeyError):
-        mgb.spec("MiniGrid-ObstructedMaze-1Dl-v0")  # out of scope (Box.contains hidden state): loud, not silent
+        mgb.spec("MiniGrid-MinimapForSparky-v0")    # out of scope (SAR env): loud, not silent
     assert mgb.spec("MiniGrid-MultiRoom-N6-v0")["config"]["gen"] == 5     # level-pool id
     c = mgb.spec("MiniGrid-Dynamic-Obstacles-16x16-v0")["config"]
     assert (c["n_actions"], c["n_obstacles"], c["reward_range"], c["lava_v1"]) == (3, 8, (-1, 1), 1)
