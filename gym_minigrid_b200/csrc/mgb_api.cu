@@ -427,6 +427,27 @@ int mgb_flat_obs(const uint8_t *img, int32_t img_bytes, const float *mission_tab
     return 0;
 }
 
+int mgb_render_partial(const uint8_t *obs, int32_t view, const uint8_t *atlas, int32_t tile, uint8_t *out, int64_t N, void *stream) {
+    if (!obs || !atlas || !out) return fail("mgb_render_partial: null buffer");
+    if (view < 1 || view > 11 || tile < 8 || tile % 8 != 0 || N < 0) return fail("mgb_render_partial: bad sizes (tile must be a multiple of 8)");
+    if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(atlas)) & 7) return fail("mgb_render_partial: out and atlas must be 8-byte aligned");
+    if (N == 0) return 0;
+    k_render_partial<<<elementwise_grid(N * view * tile * view), 256, 0, (cudaStream_t)stream>>>(obs, view, atlas, tile, out, N);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mgb_render_full(mgb_handle *h, const uint8_t *atlas, int32_t tile, uint8_t *out, void *stream) {
+    if (!h || !atlas || !out) return fail("mgb_render_full: null argument");
+    if (tile < 8 || tile % 8 != 0) return fail("mgb_render_full: tile must be a multiple of 8");
+    if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(atlas)) & 7) return fail("mgb_render_full: out and atlas must be 8-byte aligned");
+    CUDA_OK(cudaSetDevice(h->device));
+    k_render_full<<<elementwise_grid(h->n_envs * h->dc.H * tile * h->dc.W), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, atlas, tile, out, h->n_envs);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
 int mgb_error_flags(mgb_handle *h, void *stream, uint32_t *flags_host) {
     if (!h || !flags_host) return fail("null argument");
     CUDA_OK(cudaSetDevice(h->device));

@@ -7,7 +7,8 @@ Built (with reference lines):      ReseedWrapper (wrappers.py:12-32), ImgObsWrap
     OneHotPartialObsWrapper (:203-243), FullyObsWrapper (:311-338), FullyObsOneHotWrapper (:340-415),
     FlatObsWrapper (:528-577).
     ViewSizeWrapper (:579-608; odd sizes 3..11, the kernel is a template on the view size).
-Not built (out of the hot-path scope): RGBImg*Wrapper (rendering), DACWrapper / ActionBonus / StateBonus /
+    RGBImgPartialObsWrapper (:283-309), RGBImgObsWrapper (:245-281): tile-atlas gathers, pixel-exact (tile_size 8).
+Not built: DACWrapper / ActionBonus / StateBonus /
     AppendActionWrapper / GoalPolicyWrapper / AgentExtraInfoWrapper (bookkeeping on top of step).
 
 Reference quirks, kept or documented:
@@ -244,3 +245,64 @@ class ViewSizeWrapper(Wrapper):
         super().__init__(base)
         self.observation_space = spaces.Dict({
             'image': spaces.Box(0, 255, (agent_view_size, agent_view_size, 3), 'uint8')})
+
+
+_ATLAS = {}
+
+
+def _atlas(tile_size, device):
+    """tile atlas rendered by the reference's own Grid.render_tile (oracle/gen_atlas.py), shipped as data"""
+    import os
+    key = (tile_size, str(device))
+    if key not in _ATLAS:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "tile_atlas_t%d.npz" % tile_size)
+        if not os.path.exists(path):
+            raise _lib.MgbError("no tile atlas for tile_size=%d (shipped: 8); build one with oracle/gen_atlas.py %d "
+                                "on a machine that has the reference" % (tile_size, tile_size))
+        z = np.load(path)
+        _ATLAS[key] = (torch.as_tensor(z["atlas"]).to(device).contiguous(), z["valid"])
+    return _ATLAS[key][0]
+
+
+class RGBImgPartialObsWrapper(ObservationWrapper):
+    """wrappers.py:283-309 -> MiniGridEnv.get_obs_render (minigrid.py:1383-1398): the agent's view as RGB."""
+
+    def __init__(self, env, tile_size=8):
+        super().__init__(env)
+        self.tile_size = tile_size
+        shape = env.observation_space['image'].shape
+        self.observation_space = spaces.Dict(dict(env.observation_space.spaces))
+        self.observation_space.spaces['image'] = spaces.Box(0, 255, (shape[0] * tile_size, shape[1] * tile_size, 3), 'uint8')
+        self._atlas = _atlas(tile_size, env.unwrapped.device)
+
+    def observation(self, obs):
+        L = _lib.load()
+        img = obs['image'].contiguous()
+        N, V = img.shape[0], img.shape[1]
+        ts = self.tile_size
+        out = torch.empty((N, V * ts, V * ts, 3), dtype=torch.uint8, device=img.device)
+        with torch.cuda.device(img.device):
+            _lib.check(L.mgb_render_partial(_ptr(img), V, _ptr(self._atlas), ts, _ptr(out), N,
+                                            C.c_void_p(torch.cuda.current_stream(img.device).cuda_stream)))
+        return {'mission': obs['mission'], 'image': out}
+
+
+class RGBImgObsWrapper(ObservationWrapper):
+    """wrappers.py:245-281 -> env.render('rgb_array', highlight=False): the whole grid as RGB.
+    The declared space keeps the reference's (width*ts, height*ts, 3); the array is [N, height*ts, width*ts, 3]
+    like the reference's render output."""
+
+    def __init__(self, env, tile_size=8):
+        super().__init__(env)
+        self.tile_size = tile_size
+        self.observation_space = spaces.Dict(dict(env.observation_space.spaces))
+        self.observation_space.spaces['image'] = spaces.Box(0, 255, (self.env.width * tile_size, self.env.height * tile_size, 3), 'uint8')
+        self._atlas = _atlas(tile_size, env.unwrapped.device)
+
+    def observation(self, obs):
+        L = _lib.load()
+        u = self.unwrapped
+        ts = self.tile_size
+        out = torch.empty((u.num_envs, u.height * ts, u.width * ts, 3), dtype=torch.uint8, device=u.device)
+        _lib.check(L.mgb_render_full(u._h, _ptr(self._atlas), ts, _ptr(out), u._stream()))
+        return {'mission': obs['mission'], 'image': out}

@@ -668,6 +668,37 @@ def hook_traces():
             sum(int((r[:1] > 0).sum()) for r in sc["sc_reward"]), sum(int(d[0]) for d in sc["sc_done"])))
 
 
+def rgb_traces():
+    """RGBImgPartialObsWrapper / RGBImgObsWrapper (wrappers.py:245-309) outputs of the reference on Philox-injected
+    trajectories: pixel-exact targets for the tile-atlas kernels."""
+    W = sys.modules["gym_minigrid.wrappers"]
+    seed = 2468
+    for env_id in ("MiniGrid-DoorKey-8x8-v0", "MiniGrid-KeyCorridorS3R3-v0", "MiniGrid-Dynamic-Obstacles-8x8-v0", "MiniGrid-FourRooms-v0"):
+        idx, T = [1, 17], 24
+        part, full, acts = [], [], []
+        for k, i in enumerate(idx):
+            env = R.make(env_id)
+            shim = R.PhiloxShim(seed, i, 0)
+            env.np_random = shim
+            obs = env.reset()
+            wp, wf = W.RGBImgPartialObsWrapper(env), W.RGBImgObsWrapper(env)
+            a = np.random.RandomState(300 + k).randint(0, env.action_space.n, size=T).astype(np.uint8)
+            P, F = [wp.observation(obs)["image"].copy()], [wf.observation(obs)["image"].copy()]
+            ep = 1
+            for t in range(T):
+                obs, r, d, _ = env.step(int(a[t]))
+                if d:
+                    shim.new_episode(ep)
+                    ep += 1
+                    obs = env.reset()
+                P.append(wp.observation(obs)["image"].copy()); F.append(wf.observation(obs)["image"].copy())
+            part.append(np.stack(P)); full.append(np.stack(F)); acts.append(a)
+        path = os.path.join(OUT, "rgb_%s.npz" % short(env_id))
+        np.savez_compressed(path, env_id=env_id, seed=np.uint64(seed), env_indices=np.array(idx, np.int64), actions=np.stack(acts),
+                            partial=np.stack(part), full=np.stack(full))
+        print("%-44s %6.1f KB partial %s full %s" % (os.path.basename(path), os.path.getsize(path) / 1024, part[0].shape, full[0].shape))
+
+
 def reward_table():
     """_reward() (minigrid.py:933-937) evaluated BY THE REFERENCE for every step_count of every
     max_steps in the registry (and 50 beyond): r_<max_steps>[k] = reward at step_count == k."""
@@ -695,3 +726,4 @@ if __name__ == "__main__":
     pool_traces()
     viewsize_traces()
     hook_traces()
+    rgb_traces()
