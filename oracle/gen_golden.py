@@ -351,7 +351,8 @@ def pool_traces():
     seed, K = 777, 6
     for env_id, T, n_env in (("MiniGrid-LavaCrossingS9N2-v0", 700, 3), ("MiniGrid-SimpleCrossingS11N5-v0", 600, 2),
                              ("MiniGrid-LavaGapS7-v1", 500, 3), ("MiniGrid-MultiRoom-N4-S5-v0", 400, 3),
-                             ("MiniGrid-DistShift2-v0", 500, 2), ("MiniGrid-SimpleRoom-v0", 300, 2)):
+                             ("MiniGrid-DistShift2-v0", 500, 2), ("MiniGrid-SimpleRoom-v0", 300, 2),
+                             ("MiniGrid-Empty-6x6-v2", 400, 2), ("MiniGrid-Empty-Random-10x10-v0", 450, 2)):
         env = R.make(env_id)
         cfg = config_of(env)
         levels = []
@@ -395,7 +396,7 @@ def pool_traces():
             tr["obs0"].append(O[0]); tr["dir0"].append(D[0]); tr["obs"].append(np.stack(O[1:])); tr["dir"].append(np.array(D[1:], np.uint8))
             tr["reward"].append(np.array(RW)); tr["done"].append(np.array(DN, np.uint8)); tr["actions"].append(a)
             tr["lvl"].append(np.array(lv + [-1] * (T + 1 - len(lv)), np.int32)); tr["grid_end"].append(s["grid"]); tr["agent_end"].append(s["agent"])
-        path = os.path.join(OUT, "pool_%s.npz" % short(env_id).replace("-v1", "_v1"))
+        path = os.path.join(OUT, "pool_%s.npz" % short(env_id).replace("-v1", "_v1").replace("-v2", "_v2"))
         np.savez_compressed(path, env_id=env_id, seed=np.uint64(seed), env_indices=np.array(idx, np.int64),
                             cfg_keys=np.array(list(cfg.keys())), cfg_vals=np.array(list(cfg.values()), np.int32),
                             level_grid=np.stack([l["grid"] for l in levels]), level_aux=np.stack([l["aux"] for l in levels]),

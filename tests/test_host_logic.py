@@ -25,7 +25,7 @@ def header_functions():
 def test_registry_contract():
     for i in HEADLINE:
         assert i in mgb.env_list
-    assert len(mgb.env_list) == len(set(mgb.env_list)) == 78      # 24 with device generators + 54 level-pool ids
+    assert len(mgb.env_list) == len(set(mgb.env_list)) == 81      # 24 with device generators + 57 level-pool ids
     with pytest.raises(AssertionError):            # register.py:12  id must start with "MiniGrid-"
         mgb.register("Foo-v0", "gym_minigrid.envs:EmptyEnv")
     with pytest.raises(AssertionError):            # register.py:13  ids are unique
