@@ -432,7 +432,9 @@ int mgb_render_partial(const uint8_t *obs, int32_t view, const uint8_t *atlas, i
     if (view < 1 || view > 11 || tile < 8 || tile % 8 != 0 || N < 0) return fail("mgb_render_partial: bad sizes (tile must be a multiple of 8)");
     if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(atlas)) & 7) return fail("mgb_render_partial: out and atlas must be 8-byte aligned");
     if (N == 0) return 0;
-    k_render_partial<<<elementwise_grid(N * view * tile * view), 256, 0, (cudaStream_t)stream>>>(obs, view, atlas, tile, out, N);
+    const int64_t segs = N * view * tile * view;
+    if (segs < ((int64_t)1 << 31) - (1 << 24)) k_render_partial<uint32_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(obs, view, atlas, tile, out, N);
+    else k_render_partial<uint64_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(obs, view, atlas, tile, out, N);
     CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -442,7 +444,9 @@ int mgb_render_full(mgb_handle *h, const uint8_t *atlas, int32_t tile, uint8_t *
     if (tile < 8 || tile % 8 != 0) return fail("mgb_render_full: tile must be a multiple of 8");
     if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(atlas)) & 7) return fail("mgb_render_full: out and atlas must be 8-byte aligned");
     CUDA_OK(cudaSetDevice(h->device));
-    k_render_full<<<elementwise_grid(h->n_envs * h->dc.H * tile * h->dc.W), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, atlas, tile, out, h->n_envs);
+    const int64_t segs = h->n_envs * h->dc.H * tile * h->dc.W;
+    if (segs < ((int64_t)1 << 31) - (1 << 24)) k_render_full<uint32_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, atlas, tile, out, h->n_envs);
+    else k_render_full<uint64_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, atlas, tile, out, h->n_envs);
     CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;

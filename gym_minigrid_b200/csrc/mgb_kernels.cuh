@@ -1215,36 +1215,40 @@ __device__ __forceinline__ void copy_tile_row(const uint8_t *__restrict__ atlas,
     for (int k = 0; k < tile * 3 / 8; ++k) d[k] = __ldg(&src[k]);
 }
 
+// IDX = uint32_t whenever the launch has < 2^31 tile rows (the common case): the three div/mods by run-time
+// divisors are several times cheaper in 32 bits, and they are what bounds these kernels, not HBM.
+template <typename IDX>
 __global__ void k_render_partial(const uint8_t *__restrict__ obs, int V, const uint8_t *__restrict__ atlas, int tile,
                                  uint8_t *__restrict__ out, int64_t N) {
-    const int rows = V * tile;
-    const int64_t total = N * rows * V;                         // (env, pixel row, cell column)
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cx = (int)(i % V);
-        const int64_t r = i / V;
-        const int row = (int)(r % rows);
-        const int64_t n = r / rows;
-        const int cy = row / tile, py = row - cy * tile;
-        const uint8_t *q = obs + ((n * V + cx) * V + cy) * 3;   // obs[n][vx][vy][c]
-        const int t = q[0] > 10 ? 0 : q[0], c = q[1] > 6 ? 0 : q[1], st = q[2] > 2 ? 0 : q[2];
-        const int code = (t >= 10 ? 0 : t) * 21 + c * 3 + st;
+    const IDX rows = (IDX)(V * tile), uV = (IDX)V, utile = (IDX)tile;
+    const IDX total = (IDX)N * rows * uV;                       // (env, pixel row, cell column)
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+        const IDX r = i / uV;
+        const int cx = (int)(i - r * uV);
+        const IDX n = r / rows;
+        const int row = (int)(r - n * rows);
+        const int cy = row / (int)utile, py = row - cy * (int)utile;
+        const uint8_t *q = obs + (((size_t)n * V + cx) * V + cy) * 3;   // obs[n][vx][vy][c]
+        const int t = q[0] > 9 ? 0 : q[0], c = q[1] > 6 ? 0 : q[1], st = q[2] > 2 ? 0 : q[2];
+        const int code = t * 21 + c * 3 + st;
         int variant = t != 0 ? 1 : 0;                           // vis_mask = (type != unseen) (minigrid.py:613)
         if (cx == V / 2 && cy == V - 1) variant = 6;            // agent_pos=(V//2, V-1), agent_dir=3 (minigrid.py:1391-1396)
-        copy_tile_row(atlas, tile, code * ATLAS_VARIANTS + variant, py, out + i * tile * 3);
+        copy_tile_row(atlas, tile, code * ATLAS_VARIANTS + variant, py, out + (size_t)i * tile * 3);
     }
 }
 
+template <typename IDX>
 __global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, const uint8_t *__restrict__ atlas, int tile,
                               uint8_t *__restrict__ out, int64_t N) {
-    const int rows = c.H * tile;
-    const int64_t total = N * rows * c.W;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cx = (int)(i % c.W);
-        const int64_t r = i / c.W;
-        const int row = (int)(r % rows);
-        const int64_t n = r / rows;
+    const IDX rows = (IDX)(c.H * tile), uW = (IDX)c.W;
+    const IDX total = (IDX)N * rows * uW;
+    for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
+        const IDX r = i / uW;
+        const int cx = (int)(i - r * uW);
+        const IDX n = r / rows;
+        const int row = (int)(r - n * rows);
         const int cy = row / tile, py = row - cy * tile;
-        const uint32_t *base = state + (n >> 5) * c.S * 32 + (n & 31);
+        const uint32_t *base = state + (size_t)(n >> 5) * c.S * 32 + (n & 31);
         const int cidx = cx * c.HP + cy;
         const uint32_t cc = (base[(cidx >> 2) * 32] >> ((cidx & 3) * 8)) & 0xFF;
         const uint32_t x = lut_entry((int)cc);                  // (type, colour, state) of the real object
@@ -1252,7 +1256,7 @@ __global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, cons
         const uint32_t w0 = base[c.GW * 32];
         const bool agent_here = (int)(w0 & 0xFF) == cx && (int)((w0 >> 8) & 0xFF) == cy;
         const int variant = agent_here ? 2 + (int)((w0 >> 16) & 3) : 0;          // highlight=False (wrappers.py:270)
-        copy_tile_row(atlas, tile, code * ATLAS_VARIANTS + variant, py, out + i * tile * 3);
+        copy_tile_row(atlas, tile, code * ATLAS_VARIANTS + variant, py, out + (size_t)i * tile * 3);
     }
 }
 
