@@ -170,7 +170,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
         return cleanup(fail("mgb_create: cannot opt in to %zu bytes of shared memory", (size_t)prop.sharedMemPerBlockOptin));
     int best_warps = 0;
     for (int wpb = MAX_WARPS_PER_BLOCK; wpb >= 2; --wpb) {
-        const size_t smem = TABLE_BYTES + (size_t)wpb * per_warp;
+        const size_t smem = (size_t)(c.see_through ? table_bytes<true>() : table_bytes<false>()) + (size_t)wpb * per_warp;
         if (smem > prop.sharedMemPerBlockOptin) continue;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, wpb * 32, smem) != cudaSuccess) continue;

@@ -31,6 +31,9 @@ constexpr int STAGE_BYTES = GROUP * OBS_BYTES;   // 4704 = 294 * 16
 __host__ __device__ constexpr int obs_bytes(int V) { return 3 * V * V; }
 __host__ __device__ constexpr int stage_bytes(int V) { return GROUP * 3 * V * V; }      // multiple of 16 for every V
 constexpr int MAX_WARPS_PER_BLOCK = 8;           // the host picks 2..8 warps per CTA to maximise resident warps/SM
+#ifndef MGB_SEE_MIN_BLOCKS
+#define MGB_SEE_MIN_BLOCKS 0     // experiment: >0 adds minBlocksPerSM to the see-through kernels' launch bounds (register cap)
+#endif
 constexpr int MAX_THREADS = MAX_WARPS_PER_BLOCK * 32;
 constexpr int MAX_OBST = 8;
 constexpr int XWORDS = 4;                        // agent, steps/target, episode, ndraws
@@ -60,10 +63,10 @@ constexpr int LUT_PITCH_SEE = 3;   // see-through kernels: [x24, x24|flags<<24, 
                                    // e.g. grey wall 57 / green goal 169 -- the two objects of Empty-8x8)
 template <bool SEE> __host__ __device__ constexpr int lut_pitch() { return SEE ? LUT_PITCH_SEE : LUT_PITCH_OCC; }
 template <bool SEE> __host__ __device__ constexpr int lut_fw() { return SEE ? 1 : 2; }     // word index of the flags word
-constexpr int LUT_BYTES = 256 * LUT_PITCH_OCC * 4;               // 6144 (sized for the larger layout)
+template <bool SEE> __host__ __device__ constexpr int lut_bytes() { return 256 * lut_pitch<SEE>() * 4; }    // 3072 / 6144
 constexpr int AXIS_ENTRIES = 88;                                 // v in [-(V-1), 64+V-2] for V <= 11: index v + AXIS_BIAS
 constexpr int AXIS_BIAS = 10;
-constexpr int TABLE_BYTES = LUT_BYTES + 2 * AXIS_ENTRIES * 4;    // 6848
+template <bool SEE> __host__ __device__ constexpr int table_bytes() { return (lut_bytes<SEE>() + 2 * AXIS_ENTRIES * 4 + 127) / 128 * 128; }   // 3840 / 6912
 
 // minigrid.py:40-52 / 27-35 / 57-61
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
@@ -692,7 +695,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
     //   even dir: x = ax + sgn*(V-1-vy) (rows)    y = ay + sgn*(vx-V/2) (columns)
     //   odd  dir: x = ax - sgn*(vx-V/2) (columns) y = ay + sgn*(V-1-vy) (rows)
     // P[vx] / Q[vy] = shared-memory offsets of those coordinates, read from the CTA's axis tables
-    const uint32_t ax_sa = (uint32_t)__cvta_generic_to_shared(lut) + LUT_BYTES;      // table of x offsets
+    const uint32_t ax_sa = (uint32_t)__cvta_generic_to_shared(lut) + lut_bytes<SEE>();      // table of x offsets
     const uint32_t ay_sa = ax_sa + AXIS_ENTRIES * 4;                                 // table of y offsets
     const int p0 = odd ? e.ax + (V / 2) * sgn : e.ay - (V / 2) * sgn, pstep4 = (odd ? -sgn : sgn) * 4;
     const int q6 = odd ? e.ay : e.ax, qstep4 = sgn * 4;               // row vy = V-1 is the agent's own row
@@ -846,14 +849,20 @@ __device__ __forceinline__ void fence_proxy_async() {
 // ------------------------------------------------------------------------------------------
 // NOTE: no minBlocksPerSM argument on purpose -- with it ptxas spends up to 157 registers/thread and the
 // occupancy loss costs more than it gains (measured: profiles/README.md, A/B table)
+#if MGB_SEE_MIN_BLOCKS
 template <int GEN, bool SEE, int V>
-__global__ void __launch_bounds__(MAX_THREADS) k_rollout(const __grid_constant__ RolloutParams p) {
+__global__ void __launch_bounds__(MAX_THREADS, SEE ? MGB_SEE_MIN_BLOCKS : 1) k_rollout(
+#else
+template <int GEN, bool SEE, int V>
+__global__ void __launch_bounds__(MAX_THREADS) k_rollout(
+#endif
+    const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const DevCfg &c = p.cfg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
-    uint32_t *axis = lut + LUT_BYTES / 4;                                           // [2][AXIS_ENTRIES]
-    uint8_t *stage_base = smem_raw + TABLE_BYTES;
+    uint32_t *axis = lut + lut_bytes<SEE>() / 4;                                           // [2][AXIS_ENTRIES]
+    uint8_t *stage_base = smem_raw + table_bytes<SEE>();
     constexpr int SB = stage_bytes(V), OB = obs_bytes(V);
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * SB);
     uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + wpb * SB) + warp * ((c.S + 1) * 32);
