@@ -452,6 +452,61 @@ int mgb_render_full(mgb_handle *h, const uint8_t *atlas, int32_t tile, uint8_t *
     return 0;
 }
 
+int mgb_visit_bonus(mgb_handle *h, int32_t by_action, const uint8_t *actions, uint32_t *counts, int64_t table,
+                    double *reward, void *stream) {
+    if (!h || !counts || !reward) return fail("mgb_visit_bonus: null argument");
+    if (by_action && !actions) return fail("mgb_visit_bonus: actions is NULL");
+    const int64_t need = (int64_t)h->dc.W * h->dc.H * (by_action ? 4 * h->dc.n_actions : 1);
+    if (table < need) return fail("mgb_visit_bonus: table must hold W*H%s entries per env", by_action ? "*4*n_actions" : "");
+    CUDA_OK(cudaSetDevice(h->device));
+    if (h->n_envs == 0) return 0;
+    k_visit_bonus<<<elementwise_grid(h->n_envs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, by_action, actions, counts, table,
+                                                                              reward, h->n_envs, h->err);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int mgb_dac(mgb_handle *h, int32_t count_ge_max, const uint8_t *done_in, const uint8_t *envdone_in, uint8_t *envdone_out,
+            const uint8_t *reset_dir, uint8_t *obs, double *reward, uint8_t *done_out, uint8_t *dir, void *stream) {
+    if (!h || !done_in || !envdone_in || !envdone_out || !reset_dir || !obs || !reward || !done_out || !dir)
+        return fail("mgb_dac: null argument");
+    if (envdone_in == envdone_out || done_in == done_out) return fail("mgb_dac: in and out buffers must differ");
+    CUDA_OK(cudaSetDevice(h->device));
+    if (h->n_envs == 0) return 0;
+    const int64_t words = (h->n_envs * h->obs_bytes + 3) / 4;
+    k_dac<<<elementwise_grid(words), 256, 0, (cudaStream_t)stream>>>(h->n_envs, h->obs_bytes, count_ge_max != 0, done_in, envdone_in,
+                                                                    envdone_out, reset_dir, obs, reward, done_out, dir);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+int mgb_append_action(int64_t N, int32_t D, int32_t A, int32_t K, const uint8_t *obs, const uint8_t *actions,
+                      const uint8_t *done, uint8_t *hist, uint8_t *out, void *stream) {
+    if (!obs || !hist || !out) return fail("mgb_append_action: null buffer");
+    if (N < 0 || D < 0 || A < 1 || A > 254 || K < 1) return fail("mgb_append_action: bad sizes");
+    if (N == 0) return 0;
+    k_action_history<<<elementwise_grid(N), 256, 0, (cudaStream_t)stream>>>(N, K, actions, done, hist);
+    CUDA_OK(cudaGetLastError());
+    const int64_t words = (N * ((int64_t)D + (int64_t)A * K) + 3) / 4;
+    k_append_action<<<elementwise_grid(words), 256, 0, (cudaStream_t)stream>>>(N, D, A, K, obs, hist, out);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int mgb_goal_policy(int64_t n_cells, int32_t planes, int32_t agent_idx, int32_t empty_idx, int32_t goal_idx,
+                    const uint8_t *obs, uint8_t *achieved, uint8_t *desired, void *stream) {
+    if (!obs || !achieved || !desired) return fail("mgb_goal_policy: null buffer");
+    if (n_cells < 0 || planes < 1 || agent_idx < 0 || agent_idx >= planes || empty_idx < 0 || empty_idx >= planes ||
+        goal_idx < 0 || goal_idx >= planes) return fail("mgb_goal_policy: bad sizes");
+    if (n_cells == 0) return 0;
+    k_goal_policy<<<elementwise_grid(n_cells), 256, 0, (cudaStream_t)stream>>>(n_cells, planes, agent_idx, empty_idx, goal_idx, obs,
+                                                                             achieved, desired);
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int mgb_error_flags(mgb_handle *h, void *stream, uint32_t *flags_host) {
     if (!h || !flags_host) return fail("null argument");
     CUDA_OK(cudaSetDevice(h->device));

@@ -1269,4 +1269,112 @@ __global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// bookkeeping wrappers: DACWrapper, ActionBonus / StateBonus, AppendActionWrapper,
+// GoalPolicyWrapper (reference wrappers.py:35-154,418-526).  Small element-wise kernels on the outputs of a step.
+// ------------------------------------------------------------------------------------------
+
+// ActionBonus (wrappers.py:87-119, key (pos, dir, action)) and StateBonus (:121-154, key pos): the count table of
+// env n is counts[n][table]; bonus = 1 / math.sqrt(new_count) in fp64 (sqrt and division correctly rounded, as CPython).
+__global__ void k_visit_bonus(DevCfg c, const uint32_t *__restrict__ state, int by_action, const uint8_t *__restrict__ actions,
+                              uint32_t *__restrict__ counts, int64_t table, double *__restrict__ reward, int64_t N, uint32_t *err) {
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t w0 = state[(size_t)(n >> 5) * c.S * 32 + (size_t)c.GW * 32 + (n & 31)];
+        const int x = w0 & 0xFF, y = (w0 >> 8) & 0xFF, dir = (w0 >> 16) & 3;
+        int64_t key = (int64_t)x * c.H + y;
+        if (by_action) {
+            const int a = actions[n];
+            if (a >= c.n_actions) { atomicOr(err, ERR_ACTION); continue; }
+            key = (key * 4 + dir) * c.n_actions + a;
+        }
+        if (key >= table) { atomicOr(err, ERR_BOUNDS); continue; }
+        const uint32_t cnt = ++counts[n * table + key];
+        reward[n] = __dadd_rn(reward[n], __ddiv_rn(1.0, __dsqrt_rn((double)cnt)));
+    }
+}
+
+// DACWrapper.step (wrappers.py:56-77).  One thread per 4 bytes of the flat observation array blanks (image*0+1,
+// :51-53) the envs whose episode is over; the first N threads also update the per-env scalars.  `env_done` is
+// double-buffered (in -> out) so that the two roles do not race.
+__global__ void k_dac(int64_t N, int ob, int count_ge_max, const uint8_t *__restrict__ done_in, const uint8_t *__restrict__ envdone_in,
+                      uint8_t *__restrict__ envdone_out, const uint8_t *__restrict__ reset_dir, uint8_t *__restrict__ obs,
+                      double *__restrict__ reward, uint8_t *__restrict__ done_out, uint8_t *__restrict__ dir) {
+    const int64_t bytes = N * ob, words = (bytes + 3) >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < N) {
+            const bool was = envdone_in[i] != 0, now = was || done_in[i] != 0;
+            if (was) reward[i] = 0.0;                                  // `return self.last_obs, 0, ...` (:62-65)
+            envdone_out[i] = now;
+            done_out[i] = now && count_ge_max;                         // done only when the time is up (:62,74)
+            if (now) dir[i] = reset_dir[i];                            // last_obs keeps the reset-time 'direction' (:48-51)
+        }
+        const int64_t b0 = i * 4;
+        const int64_t e0 = b0 / ob, e1 = min((b0 + 3) / ob, N - 1);
+        const bool f0 = envdone_in[e0] | done_in[e0], f1 = envdone_in[e1] | done_in[e1];
+        if (!f0 && !f1) continue;
+        if (b0 + 4 <= bytes && f0 && f1 && (reinterpret_cast<uintptr_t>(obs) & 3) == 0) {
+            reinterpret_cast<uint32_t *>(obs)[i] = 0x01010101u;
+        } else {
+            for (int k = 0; k < 4 && b0 + k < bytes; ++k) {
+                const int64_t e = (b0 + k) / ob;
+                if (envdone_in[e] | done_in[e]) obs[b0 + k] = 1;
+            }
+        }
+    }
+}
+
+// AppendActionWrapper (wrappers.py:418-458): hist[n][K] holds the last K action indices (255 = the all-zero vector
+// a fresh deque holds, :429,438); a finished env starts its next episode with an empty history (reset(), :436-444).
+__global__ void k_action_history(int64_t N, int K, const uint8_t *__restrict__ actions, const uint8_t *__restrict__ done,
+                                 uint8_t *__restrict__ hist) {
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        uint8_t *h = hist + n * K;
+        if (!actions || (done && done[n])) { for (int k = 0; k < K; ++k) h[k] = 255; continue; }
+        for (int k = 0; k + 1 < K; ++k) h[k] = h[k + 1];               // popleft(); append(act) (:452-453)
+        h[K - 1] = actions[n];
+    }
+}
+
+// out[n] = obs[n] ++ one-hot(hist[n][0]) ++ ... ++ one-hot(hist[n][K-1]), uint8 (:454-457).  One thread per 4 output bytes.
+__global__ void k_append_action(int64_t N, int D, int A, int K, const uint8_t *__restrict__ obs, const uint8_t *__restrict__ hist,
+                                uint8_t *__restrict__ out) {
+    const int L = D + A * K;
+    const int64_t bytes = N * L, words = (bytes + 3) >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b0 = i * 4;
+        int64_t n = b0 / L;
+        int j = (int)(b0 - n * L);
+        uint32_t w = 0;
+        const int nb = (int)min((int64_t)4, bytes - b0);
+        for (int k = 0; k < nb; ++k) {
+            uint32_t v;
+            if (j < D) v = obs[n * D + j];
+            else { const int q = (j - D) / A; v = hist[n * K + q] == (j - D) - q * A; }
+            w |= v << (8 * k);
+            if (++j == L) { j = 0; ++n; }
+        }
+        if (nb == 4 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) reinterpret_cast<uint32_t *>(out)[i] = w;
+        else for (int k = 0; k < nb; ++k) out[b0 + k] = (uint8_t)(w >> (8 * k));
+    }
+}
+
+// GoalPolicyWrapper._get_goals (wrappers.py:476-497) on FullyObsOneHotWrapper rows: [cells][planes] per env.
+// achieved: goal plane cleared.  desired: agent cell -> empty, then goal cell -> agent.  One thread per cell.
+__global__ void k_goal_policy(int64_t n_cells, int planes, int agent_idx, int empty_idx, int goal_idx,
+                              const uint8_t *__restrict__ obs, uint8_t *__restrict__ achieved, uint8_t *__restrict__ desired) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_cells; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t *src = obs + i * planes;
+        uint8_t *a = achieved + i * planes, *d = desired + i * planes;
+        const bool is_agent = src[agent_idx] > 0, is_goal = src[goal_idx] > 0;
+        for (int k = 0; k < planes; ++k) {
+            const uint8_t v = src[k];
+            a[k] = k == goal_idx ? 0 : v;
+            uint8_t dv = v;
+            if (is_agent) { if (k == agent_idx) dv = 0; if (k == empty_idx) dv = 1; }
+            if (is_goal) { if (k == goal_idx) dv = 0; if (k == agent_idx) dv = 1; }
+            d[k] = dv;
+        }
+    }
+}
+
 }  // namespace mgb

@@ -113,14 +113,15 @@ class VecMiniGridEnv:
         self._env_id_base = int(env_id_base)
         self._pool_n = 0
         self._pool_missions = None
+        self.autoreset = True
         if not autoreset:
-            _lib.check(self._L.mgb_set_autoreset(self._h, 0))
+            self.set_autoreset(False)
         self._tape = None
         N = self.num_envs
         with torch.cuda.device(self.device):
             self._obs = torch.empty((N, V, V, 3), dtype=torch.uint8, device=self.device)
             self._dir = torch.empty((N,), dtype=torch.uint8, device=self.device)
-            self._reward = torch.empty((N,), dtype=torch.float64, device=self.device)
+            self._rew = torch.empty((N,), dtype=torch.float64, device=self.device)
             self._done = torch.empty((N,), dtype=torch.uint8, device=self.device)
         self._host = None
 
@@ -166,6 +167,19 @@ class VecMiniGridEnv:
     def unwrapped(self):
         return self
 
+    def set_autoreset(self, on):
+        """Auto-reset on done (gym.vector convention) on/off.  Off = the reference's behaviour: a finished env keeps
+        its terminal state until reset(mask) -- what the bookkeeping wrappers (ActionBonus, DACWrapper ...) build on."""
+        _lib.check(self._L.mgb_set_autoreset(self._h, int(bool(on))))
+        self.autoreset = bool(on)
+
+    def _reward(self):
+        """MiniGridEnv._reward (minigrid.py:933-937) for every env at its current step_count: float64 [N]."""
+        steps = self.step_count.to(torch.float64)
+        # three separately rounded fp64 operations, as in Python.  The divisor is a tensor on purpose: torch divides a
+        # CUDA tensor by a Python scalar as a multiplication by its reciprocal, which is 1 ulp off for some step counts.
+        return 1 - 0.9 * (steps / torch.full_like(steps, float(self.max_steps)))
+
     # ------------------------------------------------------------------ gym protocol
     def seed(self, seed=1337):
         """MiniGridEnv.seed (minigrid.py:860-863): re-key the RNG; effective at the next reset."""
@@ -185,7 +199,7 @@ class VecMiniGridEnv:
     def step(self, actions, out=None):
         """MiniGridEnv.step for every env.  `out` = optional (obs, reward, done, dir) tensors to write into."""
         a = self._actions(actions, (self.num_envs,))
-        obs, reward, done, d = out if out is not None else (self._obs, self._reward, self._done, self._dir)
+        obs, reward, done, d = out if out is not None else (self._obs, self._rew, self._done, self._dir)
         _lib.check(self._L.mgb_step(self._h, _ptr(a), _ptr(obs), _ptr(reward), _ptr(done), _ptr(d), self._stream()))
         return self._obs_dict(obs, d), reward, done.view(torch.bool), {}
 

@@ -8,8 +8,10 @@ Built (with reference lines):      ReseedWrapper (wrappers.py:12-32), ImgObsWrap
     FlatObsWrapper (:528-577).
     ViewSizeWrapper (:579-608; odd sizes 3..11, the kernel is a template on the view size).
     RGBImgPartialObsWrapper (:283-309), RGBImgObsWrapper (:245-281): tile-atlas gathers, pixel-exact (tile_size 8).
-Not built: DACWrapper / ActionBonus / StateBonus /
-    AppendActionWrapper / GoalPolicyWrapper / AgentExtraInfoWrapper (bookkeeping on top of step).
+    Bookkeeping wrappers: DACWrapper (:35-84), ActionBonus (:87-119), StateBonus (:121-154),
+    AgentExtraInfoWrapper (:169-200), AppendActionWrapper (:418-458), GoalPolicyWrapper (:461-526).
+    ActionBonus / StateBonus / DACWrapper need the TERMINAL state of a finished env (its last position, or that it
+    stays finished), so they switch the wrapped env's in-kernel auto-reset off and do it themselves afterwards.
 
 Reference quirks, kept or documented:
   * OneHotPartialObsWrapper.observation reads `self.observation_space.shape` of a Dict space
@@ -306,3 +308,190 @@ class RGBImgObsWrapper(ObservationWrapper):
         out = torch.empty((u.num_envs, u.height * ts, u.width * ts, 3), dtype=torch.uint8, device=u.device)
         _lib.check(L.mgb_render_full(u._h, _ptr(self._atlas), ts, _ptr(out), u._stream()))
         return {'mission': obs['mission'], 'image': out}
+
+
+# ------------------------------------------------------------------------------------------------
+# bookkeeping wrappers
+# ------------------------------------------------------------------------------------------------
+def _stream(env):
+    return env.unwrapped._stream()
+
+
+class _TakesOverAutoReset(Wrapper):
+    """The reference wrappers below read the env *after* its step and *before* any reset (terminal agent position).
+    The batched env auto-resets inside the step kernel, so these wrappers turn that off on the wrapped env and, when
+    `autoreset` is True (default: what the wrapped env was doing), reset the finished envs themselves right after the
+    bookkeeping -- the caller still sees the gym.vector convention (obs at a done step = first obs of the next episode)."""
+
+    def __init__(self, env, autoreset=None):
+        super().__init__(env)
+        u = self.unwrapped
+        if env is not u:
+            raise _lib.MgbError("%s must wrap the batched env directly (observation wrappers go on top of it): it resets "
+                                "finished envs after its bookkeeping, which an inner observation wrapper would not see"
+                                % type(self).__name__)
+        self._autoreset = u.autoreset if autoreset is None else bool(autoreset)
+        u.set_autoreset(False)
+
+    def _reset_done(self, obs, done):
+        if not self._autoreset:
+            return obs
+        u = self.unwrapped
+        _lib.check(u._L.mgb_reset(u._h, _ptr(done.view(torch.uint8)), _ptr(u._obs), _ptr(u._dir), u._stream()))
+        return obs
+
+
+class _VisitBonus(_TakesOverAutoReset):
+    _BY_ACTION = 0
+
+    def __init__(self, env, autoreset=None):
+        super().__init__(env, autoreset)
+        u = self.unwrapped
+        self._table = u.width * u.height * (4 * u.action_space.n if self._BY_ACTION else 1)
+        # the reference's `self.counts` dict, one per env instance, never cleared by reset (wrappers.py:94-96,118-119)
+        self.counts = torch.zeros((u.num_envs, self._table), dtype=torch.int32, device=u.device)
+
+    def step(self, action):
+        u = self.unwrapped
+        a = u._actions(action, (u.num_envs,))
+        obs, reward, done, info = self.env.step(a)
+        _lib.check(u._L.mgb_visit_bonus(u._h, self._BY_ACTION, _ptr(a), _ptr(self.counts), self._table, _ptr(reward), u._stream()))
+        return self._reset_done(obs, done), reward, done, info
+
+
+class ActionBonus(_VisitBonus):
+    """wrappers.py:87-119: reward += 1/sqrt(number of times this env saw (agent_pos, agent_dir, action))."""
+    _BY_ACTION = 1
+
+
+class StateBonus(_VisitBonus):
+    """wrappers.py:121-154: reward += 1/sqrt(number of times this env's agent stood on agent_pos)."""
+    _BY_ACTION = 0
+
+
+class DACWrapper(_TakesOverAutoReset):
+    """wrappers.py:35-84: once an env's episode ends it returns a blank observation (image*0+1, the reset-time
+    direction), reward 0, and done only when `count >= max_steps` -- every episode lasts exactly max_steps, so the
+    whole batch finishes on the same step and the caller resets it, as with the reference.  A finished env is still
+    stepped by the kernel (its outputs are discarded; its state is regenerated by the next reset)."""
+
+    def __init__(self, env):
+        super().__init__(env, autoreset=False)
+        u = self.unwrapped
+        N, dev = u.num_envs, u.device
+        self._envdone = [torch.zeros(N, dtype=torch.uint8, device=dev) for _ in range(2)]
+        self._reset_dir = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._done_out = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.count = 0
+
+    @property
+    def env_done(self):
+        return self._envdone[0].view(torch.bool)
+
+    def reset(self, **kw):
+        obs = self.env.reset(**kw)
+        self._envdone[0].zero_()
+        self._reset_dir.copy_(obs['direction'])
+        self.count = 0
+        return obs
+
+    def step(self, action):
+        self.count += 1
+        obs, reward, done, info = self.env.step(action)
+        u = self.unwrapped
+        _lib.check(u._L.mgb_dac(u._h, int(self.count >= u.max_steps), _ptr(done.view(torch.uint8)), _ptr(self._envdone[0]),
+                                _ptr(self._envdone[1]), _ptr(self._reset_dir), _ptr(obs['image']), _ptr(reward),
+                                _ptr(self._done_out), _ptr(obs['direction']), u._stream()))
+        self._envdone.reverse()
+        return obs, reward, self._done_out.view(torch.bool), info
+
+
+class AgentExtraInfoWrapper(ObservationWrapper):
+    """wrappers.py:169-200: adds 'pos' int32 [N,2] and 'dir' int32 [N] to the observation dict."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        self.observation_space = spaces.Dict({
+            'image': env.observation_space.spaces['image'],
+            'pos': spaces.Box(-1, 10000, (2,), 'float32'),
+            'dir': spaces.Box(0, 5, (), 'float32')})
+
+    def observation(self, obs):
+        agent = self.unwrapped.get_state(("agent",))["agent"]
+        out = {'pos': agent[:, :2], 'dir': agent[:, 2]}
+        out.update(obs)
+        return out
+
+    def get_map(self):
+        """type plane of grid.encode() (wrappers.py:188-191): uint8 [N,W,H]."""
+        return self.unwrapped.get_state(("grid",))["grid"][..., 0]
+
+    def get_full_map(self):
+        """grid.encode() with the agent cell := (10, red, dir) (wrappers.py:193-201) -- the FullyObsWrapper image."""
+        return self.unwrapped.full_obs()
+
+
+class AppendActionWrapper(Wrapper):
+    """wrappers.py:418-458: appends the one-hot encodings of the last K actions to a flat uint8 observation
+    (e.g. FullyObsOneHotWrapper(..., flatten=True)).  An env that finished starts over with an empty history."""
+
+    def __init__(self, env, K):
+        super().__init__(env)
+        self.K = int(K)
+        self.actsize = env.action_space.n
+        self._D = int(self.env.observation_space.shape[0])
+        u = self.unwrapped
+        self._hist = torch.full((u.num_envs, self.K), 255, dtype=torch.uint8, device=u.device)
+        self.observation_space = spaces.Box(0, 1, (self._D + self.actsize * self.K,), 'uint8')
+
+    def _append(self, obs, actions, done):
+        u = self.unwrapped
+        obs = obs.contiguous()
+        assert obs.dtype == torch.uint8 and tuple(obs.shape) == (u.num_envs, self._D)
+        out = torch.empty((u.num_envs, self._D + self.actsize * self.K), dtype=torch.uint8, device=u.device)
+        _lib.check(u._L.mgb_append_action(u.num_envs, self._D, self.actsize, self.K, _ptr(obs), _ptr(actions),
+                                          _ptr(None if done is None else done.view(torch.uint8)), _ptr(self._hist), _ptr(out), u._stream()))
+        return out
+
+    def reset(self, **kw):
+        return self._append(self.env.reset(**kw), None, None)
+
+    def step(self, action):
+        u = self.unwrapped
+        a = u._actions(action, (u.num_envs,))
+        obs, reward, done, info = self.env.step(a)
+        return self._append(obs, a, done), reward, done, info
+
+
+class GoalPolicyWrapper(Wrapper):
+    """wrappers.py:461-526 (a gym GoalEnv over FullyObsOneHotWrapper): observation dict with 'achieved_goal' (goal
+    plane erased) and 'desired_goal' (agent moved onto the goal cell)."""
+
+    def __init__(self, env):
+        assert isinstance(env, FullyObsOneHotWrapper)
+        super().__init__(env)
+        self.observation_space = spaces.Dict({
+            'observation': env.observation_space, 'achieved_goal': env.observation_space, 'desired_goal': env.observation_space})
+
+    def _get_goals(self, obs):
+        e, u = self.env, self.unwrapped
+        obs = obs.contiguous()
+        achieved, desired = torch.empty_like(obs), torch.empty_like(obs)
+        _lib.check(u._L.mgb_goal_policy(u.num_envs * e.obsshape, e.N, e.object_to_new_idx[OBJECT_TO_IDX['agent']],
+                                        e.object_to_new_idx[OBJECT_TO_IDX['empty']], e.object_to_new_idx[OBJECT_TO_IDX['goal']],
+                                        _ptr(obs), _ptr(achieved), _ptr(desired), u._stream()))
+        return achieved, desired
+
+    def compute_reward(self, achieved_goal=None, desired_goal=None, info=None):
+        return self.unwrapped._reward()                     # wrappers.py:499-505: the first `_reward` down the chain
+
+    def _pack(self, obs):
+        achieved, desired = self._get_goals(obs)
+        return {'observation': obs, 'achieved_goal': achieved, 'desired_goal': desired}
+
+    def reset(self, **kw):
+        return self._pack(self.env.reset(**kw))
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        return self._pack(obs), reward, done, info

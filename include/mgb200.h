@@ -187,6 +187,34 @@ int mgb_render_partial(const uint8_t *obs, int32_t view, const uint8_t *atlas, i
  * out [N][H*tile][W*tile][3] from the handle's current state. */
 int mgb_render_full(mgb_handle *h, const uint8_t *atlas, int32_t tile, uint8_t *out, void *stream);
 
+/* ---- bookkeeping wrappers: element-wise kernels on the outputs of a step ---- */
+
+/* ActionBonus.step (wrappers.py:87-119; by_action = 1, key (agent_pos, agent_dir, action), table = W*H*4*n_actions)
+ * and StateBonus.step (wrappers.py:121-154; by_action = 0, key agent_pos, table = W*H):
+ * counts uint32 [N][table] (caller-owned, zero-initialised, never cleared by reset -- the reference keeps its dict
+ * across episodes); c = ++counts[n][key(state of env n)]; reward[n] += 1 / sqrt(c) in fp64.  Reads the handle's
+ * CURRENT state, so call it before the env is reset (the facade switches auto-reset off and resets after it). */
+int mgb_visit_bonus(mgb_handle *h, int32_t by_action, const uint8_t *actions, uint32_t *counts, int64_t table,
+                    double *reward, void *stream);
+
+/* DACWrapper.step (wrappers.py:56-77): an env whose episode ended keeps returning the blank observation
+ * (image*0+1, reset-time direction), reward 0, and done only once count >= max_steps.
+ * done_in [N] = done of the wrapped step; envdone_in/envdone_out [N] = the wrapper's env_done flag before/after
+ * (two different buffers); obs [N][obs_bytes], reward [N], dir [N] are modified in place; done_out [N] != done_in. */
+int mgb_dac(mgb_handle *h, int32_t count_ge_max, const uint8_t *done_in, const uint8_t *envdone_in, uint8_t *envdone_out,
+            const uint8_t *reset_dir, uint8_t *obs, double *reward, uint8_t *done_out, uint8_t *dir, void *stream);
+
+/* AppendActionWrapper (wrappers.py:418-458): hist uint8 [N][K] = the last K action indices, 255 = none.
+ * actions == NULL (reset) clears every history; otherwise hist is shifted and actions[n] appended, and envs with
+ * done[n] != 0 (auto-reset) are cleared.  Then out [N][D + A*K] = obs[n] (D bytes) ++ K one-hot vectors of A bytes. */
+int mgb_append_action(int64_t N, int32_t D, int32_t A, int32_t K, const uint8_t *obs, const uint8_t *actions,
+                      const uint8_t *done, uint8_t *hist, uint8_t *out, void *stream);
+
+/* GoalPolicyWrapper._get_goals (wrappers.py:476-497): obs [n_cells][planes] one-hot rows of FullyObsOneHotWrapper ->
+ * achieved (goal plane cleared) and desired (agent cell -> empty, goal cell -> agent). */
+int mgb_goal_policy(int64_t n_cells, int32_t planes, int32_t agent_idx, int32_t empty_idx, int32_t goal_idx,
+                    const uint8_t *obs, uint8_t *achieved, uint8_t *desired, void *stream);
+
 /* Synchronises `stream` and returns the sticky device error flags (then clears them):
  *   1 unknown action (reference: assert False, minigrid.py:1316-1318)   2 RNG tape exhausted
  *   4 tape value outside [low,high)    8 rejection sampling gave up (RecursionError in reset)

@@ -703,6 +703,97 @@ def rgb_traces():
         print("%-44s %6.1f KB partial %s full %s" % (os.path.basename(path), os.path.getsize(path) / 1024, part[0].shape, full[0].shape))
 
 
+def bookkeeping_traces():
+    """bookkeeping wrappers: the reference's own ActionBonus, StateBonus, DACWrapper,
+    AppendActionWrapper, GoalPolicyWrapper and AgentExtraInfoWrapper on Philox-injected trajectories.  A finished
+    episode is followed by reset() of the same wrapper (the batched wrappers auto-reset), except under DACWrapper,
+    which runs one fixed-length episode."""
+    W = sys.modules["gym_minigrid.wrappers"]
+    seed = 5151
+    for env_id, T in (("MiniGrid-Empty-5x5-v0", 230), ("MiniGrid-DoorKey-5x5-v0", 300), ("MiniGrid-Dynamic-Obstacles-5x5-v0", 120),
+                      ("MiniGrid-DoorKey-8x8-v0", 60)):
+        idx = [2, 9]
+        out = {k: [] for k in ("actions", "ab_reward", "ab_done", "ab_image", "sb_reward", "sb_done", "dac_image", "dac_dir",
+                               "dac_reward", "dac_done", "app_obs", "gp_obs", "gp_achieved", "gp_desired", "gp_reward",
+                               "xi_pos", "xi_dir", "xi_map", "xi_full")}
+        for k, i in enumerate(idx):
+            def fresh():
+                env = R.make(env_id)
+                shim = R.PhiloxShim(seed, i, 0)
+                env.np_random = shim
+                return env, shim
+            n_act = R.make(env_id).action_space.n
+            a = np.random.RandomState(500 + k).randint(0, n_act, size=T).astype(np.uint8)
+            out["actions"].append(a)
+            # --- ActionBonus / StateBonus: the counts survive reset() ---
+            for tag, cls in (("ab", W.ActionBonus), ("sb", W.StateBonus)):
+                env, shim = fresh()
+                w = cls(env)
+                w.reset()
+                ep, rr, dd, im = 1, [], [], []
+                for t in range(T):
+                    obs, r, d, _ = w.step(int(a[t]))
+                    if d:
+                        shim.new_episode(ep); ep += 1
+                        obs = w.reset()
+                    rr.append(float(r)); dd.append(bool(d)); im.append(obs["image"].copy())
+                out[tag + "_reward"].append(np.array(rr, np.float64)); out[tag + "_done"].append(np.array(dd))
+                if tag == "ab":
+                    out["ab_image"].append(np.stack(im))
+            # --- DACWrapper: one episode of exactly max_steps steps (plus a few steps beyond) ---
+            env, shim = fresh()
+            w = W.DACWrapper(env)
+            w.reset()
+            Td = min(T, env.max_steps + 4)
+            im, di, rr, dd = [], [], [], []
+            for t in range(Td):
+                obs, r, d, _ = w.step(int(a[t % T]))
+                im.append(np.asarray(obs["image"]).copy()); di.append(int(obs["direction"])); rr.append(float(r)); dd.append(bool(d))
+            pad = T - Td
+            out["dac_image"].append(np.concatenate([np.stack(im), np.zeros((pad,) + im[0].shape, np.uint8)]))
+            out["dac_dir"].append(np.array(di + [0] * pad, np.uint8)); out["dac_reward"].append(np.array(rr + [0.0] * pad, np.float64))
+            out["dac_done"].append(np.array(dd + [False] * pad))
+            dac_len = Td
+            # --- AppendActionWrapper(K=3) over the flat full one-hot observation ---
+            env, shim = fresh()
+            w = W.AppendActionWrapper(W.FullyObsOneHotWrapper(W.ImgObsWrapper(W.FullyObsWrapper(env)), flatten=True), 3)
+            w.reset()
+            ep, oo = 1, []
+            for t in range(T):
+                obs, r, d, _ = w.step(int(a[t]))
+                if d:
+                    shim.new_episode(ep); ep += 1
+                    obs = w.reset()
+                oo.append(np.asarray(obs).copy())
+            out["app_obs"].append(np.stack(oo).astype(np.uint8))
+            # --- GoalPolicyWrapper + AgentExtraInfoWrapper ---
+            env, shim = fresh()
+            w = W.GoalPolicyWrapper(W.FullyObsOneHotWrapper(W.ImgObsWrapper(W.FullyObsWrapper(env)), flatten=True))
+            xi = W.AgentExtraInfoWrapper(env)
+            w.reset()
+            ep, o1, o2, o3, o4, p1, p2, p3, p4 = 1, [], [], [], [], [], [], [], []
+            for t in range(T):
+                obs, r, d, _ = w.step(int(a[t]))
+                if d:
+                    shim.new_episode(ep); ep += 1
+                    obs = w.reset()
+                o1.append(obs["observation"].copy()); o2.append(obs["achieved_goal"].copy()); o3.append(obs["desired_goal"].copy())
+                o4.append(float(w.compute_reward(None, None, None)))
+                x = xi.observation({})
+                p1.append(np.array(x["pos"], np.int32)); p2.append(int(x["dir"])); p3.append(xi.get_map().copy()); p4.append(xi.get_full_map().copy())
+            out["gp_obs"].append(np.stack(o1).astype(np.uint8)); out["gp_achieved"].append(np.stack(o2).astype(np.uint8))
+            out["gp_desired"].append(np.stack(o3).astype(np.uint8)); out["gp_reward"].append(np.array(o4, np.float64))
+            out["xi_pos"].append(np.stack(p1)); out["xi_dir"].append(np.array(p2, np.int32)); out["xi_map"].append(np.stack(p3).astype(np.uint8))
+            out["xi_full"].append(np.stack(p4).astype(np.uint8))
+        path = os.path.join(OUT, "bookkeeping_%s.npz" % short(env_id))
+        np.savez_compressed(path, env_id=env_id, seed=np.uint64(seed), env_indices=np.array(idx, np.int64), dac_len=np.int64(dac_len),
+                            **{k: np.stack(v) for k, v in out.items()})
+        nd = int(np.stack(out["ab_done"]).sum())
+        print("%-50s %7.1f KB  done-steps=%d dac done at %s  max bonus count>1: %s" % (
+            os.path.basename(path), os.path.getsize(path) / 1024, nd, [int(np.argmax(x)) for x in out["dac_done"]],
+            bool((np.stack(out["sb_reward"]) < 0.6).any())))
+
+
 def reward_table():
     """_reward() (minigrid.py:933-937) evaluated BY THE REFERENCE for every step_count of every
     max_steps in the registry (and 50 beyond): r_<max_steps>[k] = reward at step_count == k."""
@@ -723,6 +814,9 @@ def reward_table():
 
 if __name__ == "__main__":
     R.load_reference()
+    if "--bookkeeping-only" in sys.argv:
+        bookkeeping_traces()
+        sys.exit(0)
     if "--extras-only" not in sys.argv:
         main()
     reward_table()
@@ -731,3 +825,4 @@ if __name__ == "__main__":
     viewsize_traces()
     hook_traces()
     rgb_traces()
+    bookkeeping_traces()
