@@ -233,6 +233,20 @@ __device__ __noinline__ void prefetch_draws(uint32_t *draws, uint32_t first_bloc
     }
 }
 
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 constexpr int HARD_TRY_CAP = 1 << 16;   // the reference would spin forever; we flag ERR_SAMPLING
 
 // MiniGridEnv.place_obj (minigrid.py:1003-1061).  max_tries < 0 == math.inf.
@@ -444,6 +458,121 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
 // ------------------------------------------------------------------------------------------
 // transition: MiniGridEnv.step (minigrid.py:1227-1325) + subclass hooks
 // ------------------------------------------------------------------------------------------
+// DynamicObstaclesEnv.step, obstacle update (envs/dynamicobstacles.py:70-78) on the Philox stream.  Balls are taken
+// in list order by all lanes in lock step.  The tries of one ball see an unchanging grid (it only changes when a try
+// succeeds), so the first DYN_SPEC tries are evaluated speculatively in straight-line code -- independent loads,
+// no branches -- and the first valid one wins; a lane whose DYN_SPEC tries all failed (p ~ 0.25^4) or whose draw
+// window is nearly used up continues one try at a time in a (divergent, rare) loop, computing Philox blocks on demand
+// once it runs past the prefetched window.
+constexpr int DYN_SPEC = 4;
+template <int V>
+__device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, uint32_t *draws) {
+    const DevCfg &c = p.cfg;
+    const int W = c.W, H = c.H, HP = c.HP, nob = c.n_obst;
+    constexpr uint32_t WIN = 4 * draw_blocks(V);                  // draws in the window
+    const uint32_t wbase = rg.ndraws & ~3u;                       // draw index of draws[0]
+    prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
+    rg.rblk = 0xFFFFFFFFu;
+    uint32_t nd = rg.ndraws;
+    const uint32_t st_sa = (uint32_t)__cvta_generic_to_shared(st);
+    const uint32_t dr_sa = (uint32_t)__cvta_generic_to_shared(draws);
+    auto cell_at = [&](int x, int y) { const int i = x * HP + y; return lds_u8(st_sa + (uint32_t)((i >> 2) * 128 + (i & 3))); };
+    for (int k = 0; k < nob; ++k) {
+        int ox, oy;
+        obst_get(st, c, k, ox, oy);
+        const int tx = max(ox - 1, 0), ty = max(oy - 1, 0);
+        const uint32_t sx = (uint32_t)(min(tx + 3, W) - tx), sy = (uint32_t)(min(ty + 3, H) - ty);
+        const uint32_t wi = nd - wbase;
+        const bool spec = wi + 2 * DYN_SPEC <= WIN;               // all speculative draws are inside the window
+        const uint32_t wa = dr_sa + (spec ? wi : 0u) * 128u;
+        int sel = -1, nx = 0, ny = 0;
+#pragma unroll
+        for (int j = DYN_SPEC - 1; j >= 0; --j) {                 // descending: the lowest valid try overwrites
+            const int x = tx + (int)__umulhi(lds_u32(wa + (2 * j) * 128), sx);
+            const int y = ty + (int)__umulhi(lds_u32(wa + (2 * j + 1) * 128), sy);
+            // the ball's own cell counts as occupied: it must move (minigrid.py:1040-1041); not onto the agent (:1044)
+            if (cell_at(x, y) == CODE_EMPTY && !(x == e.ax && y == e.ay)) { sel = j; nx = x; ny = y; }
+        }
+        bool placed = spec && sel >= 0;
+        int tries = 0;
+        if (spec) { nd += placed ? 2 * (sel + 1) : 2 * DYN_SPEC; tries = DYN_SPEC; }
+        if (!placed) {
+            while (tries <= 100) {                                // place_obj(max_tries=100) makes 101 tries (:1028-1031)
+                tries++;
+                int x, y;
+                if (nd - wbase + 2 <= WIN) {
+                    x = tx + (int)__umulhi(lds_u32(dr_sa + (nd - wbase) * 128), sx);
+                    y = ty + (int)__umulhi(lds_u32(dr_sa + (nd - wbase + 1) * 128), sy);
+                } else {
+                    rg.ndraws = nd;
+                    x = rand_int_inl(rg, p, tx, tx + (int)sx);
+                    y = rand_int_inl(rg, p, ty, ty + (int)sy);
+                }
+                nd += 2;
+                if (cell_at(x, y) == CODE_EMPTY && !(x == e.ax && y == e.ay)) { placed = true; nx = x; ny = y; break; }
+            }
+        }
+        if (placed) {                                             // a failed placement (RecursionError, swallowed) leaves the ball
+            const uint32_t ball = cell_rd(st, ox * HP + oy);
+            cell_wr(st, nx * HP + ny, ball);
+            obst_set(st, c, k, nx, ny);
+            cell_wr(st, ox * HP + oy, CODE_EMPTY);
+        }
+    }
+    rg.ndraws = nd;
+}
+
+// Warp-cooperative DynamicObstaclesEnv._gen_grid (envs/dynamicobstacles.py:35-58) for the env in column `src` of
+// the warp's state block -- the fixed-start variant: agent at (1,1) facing right, then n_obstacles times
+// place_obj(Ball(), max_tries=100) over the whole grid.  With a uniform random policy an episode lasts ~12 steps, so
+// nearly every warp-step has a lane or two that must reset; doing that inside one lane stalls the other 30.  Here
+// lane j computes Philox block j of the new episode's stream (tries 2j and 2j+1), every lane tests its two
+// candidates against the static layout, and the balls are assigned in draw order with ballots: try t is taken by
+// ball k if it is the first try at or after the cursor that is free and not the position of an earlier ball.
+// Returns false (nothing but the removal of the old balls done) if 64 tries were not enough; the caller then runs the
+// scalar generator, which reproduces the same stream from its start.
+__device__ __forceinline__ bool dynobs_coop_reset(uint32_t *st_warp, int src, int lane, const RolloutParams &p, int64_t gid,
+                                                  uint32_t stream, uint32_t &consumed) {
+    const DevCfg &c = p.cfg;
+    const int W = c.W, H = c.H, HP = c.HP, nob = c.n_obst;
+    uint32_t *col = st_warp + src;
+    const uint32_t col_sa = (uint32_t)__cvta_generic_to_shared(col);
+    auto cell_sa = [&](int x, int y) { const int i = x * HP + y; return col_sa + (uint32_t)((i >> 2) * 128 + (i & 3)); };
+    if (lane < nob) { int ox, oy; obst_get(col, c, lane, ox, oy); sts_u8(cell_sa(ox, oy), CODE_EMPTY); }   // grid := template
+    __syncwarp();
+    uint32_t o0, o1, o2, o3;
+    philox4x32_10((uint32_t)lane, stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32),
+                  o0, o1, o2, o3);
+    const int xa = (int)__umulhi(o0, (uint32_t)W), ya = (int)__umulhi(o1, (uint32_t)H);
+    const int xb = (int)__umulhi(o2, (uint32_t)W), yb = (int)__umulhi(o3, (uint32_t)H);
+    auto is_free = [&](int x, int y) {                            // empty in the static layout and not the agent's cell
+        const int i = x * HP + y;
+        return ((__ldg(&p.tmpl[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) == CODE_EMPTY && !(x == 1 && y == 1);
+    };
+    uint32_t A = __ballot_sync(0xFFFFFFFFu, is_free(xa, ya)), B = __ballot_sync(0xFFFFFFFFu, is_free(xb, yb));
+    const uint32_t ca = (uint32_t)(xa | (ya << 8)), cb = (uint32_t)(xb | (yb << 8));
+    uint32_t mine = 0;
+    int cursor = 0;                                               // next try index (try t = lane t>>1, half t&1)
+    for (int k = 0; k < nob; ++k) {
+        const int la = (cursor + 1) >> 1, lb = cursor >> 1;
+        const uint32_t a = la >= 32 ? 0u : A & (0xFFFFFFFFu << la), b = lb >= 32 ? 0u : B & (0xFFFFFFFFu << lb);
+        const int ta = a ? 2 * (__ffs((int)a) - 1) : 1000, tb = b ? 2 * (__ffs((int)b) - 1) + 1 : 1000;
+        const int t = min(ta, tb);
+        if (t >= 1000) return false;
+        const uint32_t pos = __shfl_sync(0xFFFFFFFFu, (t & 1) ? cb : ca, t >> 1);
+        if (lane == k) mine = pos;
+        A &= ~__ballot_sync(0xFFFFFFFFu, ca == pos);
+        B &= ~__ballot_sync(0xFFFFFFFFu, cb == pos);
+        cursor = t + 1;
+    }
+    consumed = 2u * (uint32_t)cursor;
+    if (lane < nob) sts_u8(cell_sa((int)(mine & 0xFF), (int)(mine >> 8)), (uint32_t)code_of(T_BALL, C_BLUE, 0));
+    const uint32_t lo = __shfl_sync(0xFFFFFFFFu, mine, (2 * lane) & 31), hi = __shfl_sync(0xFFFFFFFFu, mine, (2 * lane + 1) & 31);
+    if (lane < 4) col[(c.GW + XWORDS + lane) * 32] = (2 * lane < nob ? lo : 0u) | (2 * lane + 1 < nob ? hi << 16 : 0u);
+    __syncwarp();
+    return true;
+}
+
 __device__ __forceinline__ double reward_formula(int steps, int max_steps) {
     // _reward (minigrid.py:933-937): 1 - 0.9 * (step_count / max_steps), three separately
     // rounded fp64 operations -- explicit _rn intrinsics so that nvcc cannot contract to an FMA.
@@ -468,45 +597,48 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         // max_tries=100) then clear the old cell; a failed placement (RecursionError, swallowed) leaves
         // the ball where it is.  One loop iteration = one try of whichever ball the lane is on, so a
         // warp runs max-over-lanes(total tries) iterations instead of sum-over-balls(max-over-lanes).
-        int k = 0, tries = 0, ox = 0, oy = 0, tx = 0, ty = 0, hx = 0, hy = 0;
-        uint32_t ball = 0;
-        const int nob = c.n_obst;
-        uint32_t wbase = 0;                                        // draw index of draws[0]
-        if (!p.tape) {
-            wbase = rg.ndraws & ~3u;
-            prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
-            rg.rblk = 0xFFFFFFFFu;
-        }
-        while (k < nob) {
-            if (tries == 0) {
-                obst_get(st, c, k, ox, oy);
-                ball = cell_rd(st, ox * HP + oy);
-                tx = max(ox - 1, 0); ty = max(oy - 1, 0);
-                hx = min(tx + 3, W); hy = min(ty + 3, H);
+        if (!p.tape) dynobs_move<V>(st, e, rg, p, draws);
+        else {
+            int k = 0, tries = 0, ox = 0, oy = 0, tx = 0, ty = 0, hx = 0, hy = 0;
+            uint32_t ball = 0;
+            const int nob = c.n_obst;
+            uint32_t wbase = 0;                                        // draw index of draws[0]
+            if (!p.tape) {
+                wbase = rg.ndraws & ~3u;
+                prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
+                rg.rblk = 0xFFFFFFFFu;
             }
-            if (tries > 100) { k++; tries = 0; continue; }
-            tries++;
-            int x, y;
-            if (p.tape) {
-                x = rand_int_inl(rg, p, tx, hx);
-                y = rand_int_inl(rg, p, ty, hy);
-                if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) break;
-            } else {
-                if (rg.ndraws - wbase + 2 > 4 * draw_blocks(V)) {  // window exhausted (rare): slide it
-                    wbase = rg.ndraws & ~3u;
-                    prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
+            while (k < nob) {
+                if (tries == 0) {
+                    obst_get(st, c, k, ox, oy);
+                    ball = cell_rd(st, ox * HP + oy);
+                    tx = max(ox - 1, 0); ty = max(oy - 1, 0);
+                    hx = min(tx + 3, W); hy = min(ty + 3, H);
                 }
-                const uint32_t i = rg.ndraws - wbase;
-                x = tx + (int)__umulhi(draws[i * 32], (uint32_t)(hx - tx));
-                y = ty + (int)__umulhi(draws[(i + 1) * 32], (uint32_t)(hy - ty));
-                rg.ndraws += 2;
+                if (tries > 100) { k++; tries = 0; continue; }
+                tries++;
+                int x, y;
+                if (p.tape) {
+                    x = rand_int_inl(rg, p, tx, hx);
+                    y = rand_int_inl(rg, p, ty, hy);
+                    if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) break;
+                } else {
+                    if (rg.ndraws - wbase + 2 > 4 * draw_blocks(V)) {  // window exhausted (rare): slide it
+                        wbase = rg.ndraws & ~3u;
+                        prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
+                    }
+                    const uint32_t i = rg.ndraws - wbase;
+                    x = tx + (int)__umulhi(draws[i * 32], (uint32_t)(hx - tx));
+                    y = ty + (int)__umulhi(draws[(i + 1) * 32], (uint32_t)(hy - ty));
+                    rg.ndraws += 2;
+                }
+                if (cell_rd(st, x * HP + y) != CODE_EMPTY) continue;      // the ball's own cell counts: it must move
+                if (x == e.ax && y == e.ay) continue;
+                cell_wr(st, x * HP + y, ball);
+                obst_set(st, c, k, x, y);
+                cell_wr(st, ox * HP + oy, CODE_EMPTY);
+                k++; tries = 0;
             }
-            if (cell_rd(st, x * HP + y) != CODE_EMPTY) continue;      // the ball's own cell counts: it must move
-            if (x == e.ax && y == e.ay) continue;
-            cell_wr(st, x * HP + y, ball);
-            obst_set(st, c, k, x, y);
-            cell_wr(st, ox * HP + oy, CODE_EMPTY);
-            k++; tries = 0;
         }
     } else if (action >= c.n_actions) {
         rg.err |= ERR_ACTION;                             // reference: assert False, "unknown action"
@@ -642,16 +774,6 @@ __device__ __forceinline__ void put3(int sh, uint32_t &a, uint32_t &b, uint32_t 
     else { a = __byte_perm(a, x, 0x4210); b = __byte_perm(b, x, 0x3265); }
 }
 
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
 // code -> LUT word; the address is formed with a multiply-add so that it issues on the (idle) FMA
 // pipe instead of the ALU pipe that bounds this kernel
 __device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
@@ -931,10 +1053,26 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
                     if (lane == 0) bulk_store_wait_read();
                     __syncwarp();
                 }
+                bool need_reset = false;
                 if (valid) {
                     transition<GEN, SEE, V>(st, e, rg, p, lut, action, reward, done, stage_w + lane, pc);
-                    if (done && p.autoreset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
+                    need_reset = done && p.autoreset;
                 }
+                if (GEN == GEN_DYNOBS) {                        // frequent resets: regenerate finished envs with the whole warp
+                    uint32_t rm = __ballot_sync(0xFFFFFFFFu, need_reset && !p.tape && !p.cfg.random_start && (e.flags & 1));
+                    while (rm) {
+                        const int src = __ffs((int)rm) - 1;
+                        rm &= rm - 1;
+                        uint32_t consumed = 0;
+                        const uint32_t stream = __shfl_sync(0xFFFFFFFFu, rg.episode, src);
+                        if (dynobs_coop_reset(st_warp, src, lane, p, p.env_id_base + (int64_t)group * 32 + src, stream, consumed) && lane == src) {
+                            e.ax = 1; e.ay = 1; e.dir = 0; e.carry = 0; e.steps = 0; e.target = 0; e.dirty = true;
+                            rg.episode++; rg.ndraws = consumed; rg.rblk = 0xFFFFFFFFu;
+                            need_reset = false;
+                        }
+                    }
+                }
+                if (need_reset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
             }
             const int64_t o = (int64_t)t * stride + lid;
             if (p.obs) {
