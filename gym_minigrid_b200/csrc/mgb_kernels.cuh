@@ -246,6 +246,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" ::"r"(a), "r"(v) : "memory");
+}
 
 constexpr int HARD_TRY_CAP = 1 << 16;   // the reference would spin forever; we flag ERR_SAMPLING
 
@@ -464,7 +472,13 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
 // no branches -- and the first valid one wins; a lane whose DYN_SPEC tries all failed (p ~ 0.25^4) or whose draw
 // window is nearly used up continues one try at a time in a (divergent, rare) loop, computing Philox blocks on demand
 // once it runs past the prefetched window.
-constexpr int DYN_SPEC = 4;
+#ifndef MGB_DYN_SPEC
+#define MGB_DYN_SPEC 4
+#endif
+constexpr int DYN_SPEC = MGB_DYN_SPEC;
+// byte offset of grid cell (x,y) inside a lane's column: word x*HP/4 + (y>>2) at pitch 128, byte y&3
+__device__ __forceinline__ uint32_t cell_off(int x, int y, int HP) { return (uint32_t)(x * (HP * 32) + y + (y >> 2) * 124); }
+
 template <int V>
 __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, uint32_t *draws) {
     const DevCfg &c = p.cfg;
@@ -476,22 +490,28 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
     uint32_t nd = rg.ndraws;
     const uint32_t st_sa = (uint32_t)__cvta_generic_to_shared(st);
     const uint32_t dr_sa = (uint32_t)__cvta_generic_to_shared(draws);
-    auto cell_at = [&](int x, int y) { const int i = x * HP + y; return lds_u8(st_sa + (uint32_t)((i >> 2) * 128 + (i & 3))); };
+    const uint32_t ob_sa = st_sa + (uint32_t)(c.GW + XWORDS) * 128u;   // obstacle k: 16 bits at ob_sa + (k>>1)*128 + (k&1)*2
+    // "not where the agent is" (minigrid.py:1044): an empty cell under the agent is made non-empty for the duration
+    // of the moves, so that a try is valid iff its cell is empty
+    const uint32_t ag_sa = st_sa + cell_off(e.ax, e.ay, HP);
+    const bool ag_mark = lds_u8(ag_sa) == CODE_EMPTY;
+    if (ag_mark) sts_u8(ag_sa, CODE_WALL);
     for (int k = 0; k < nob; ++k) {
-        int ox, oy;
-        obst_get(st, c, k, ox, oy);
+        const uint32_t opos = lds_u16(ob_sa + (uint32_t)((k >> 1) * 128 + (k & 1) * 2));
+        const int ox = (int)(opos & 0xFF), oy = (int)(opos >> 8);
         const int tx = max(ox - 1, 0), ty = max(oy - 1, 0);
         const uint32_t sx = (uint32_t)(min(tx + 3, W) - tx), sy = (uint32_t)(min(ty + 3, H) - ty);
         const uint32_t wi = nd - wbase;
         const bool spec = wi + 2 * DYN_SPEC <= WIN;               // all speculative draws are inside the window
         const uint32_t wa = dr_sa + (spec ? wi : 0u) * 128u;
-        int sel = -1, nx = 0, ny = 0;
+        int sel = -1;
+        uint32_t npos = 0;
 #pragma unroll
         for (int j = DYN_SPEC - 1; j >= 0; --j) {                 // descending: the lowest valid try overwrites
             const int x = tx + (int)__umulhi(lds_u32(wa + (2 * j) * 128), sx);
             const int y = ty + (int)__umulhi(lds_u32(wa + (2 * j + 1) * 128), sy);
-            // the ball's own cell counts as occupied: it must move (minigrid.py:1040-1041); not onto the agent (:1044)
-            if (cell_at(x, y) == CODE_EMPTY && !(x == e.ax && y == e.ay)) { sel = j; nx = x; ny = y; }
+            // the ball's own cell counts as occupied: it must move (minigrid.py:1040-1041)
+            if (lds_u8(st_sa + cell_off(x, y, HP)) == CODE_EMPTY) { sel = j; npos = (uint32_t)(x | (y << 8)); }
         }
         bool placed = spec && sel >= 0;
         int tries = 0;
@@ -509,16 +529,17 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
                     y = rand_int_inl(rg, p, ty, ty + (int)sy);
                 }
                 nd += 2;
-                if (cell_at(x, y) == CODE_EMPTY && !(x == e.ax && y == e.ay)) { placed = true; nx = x; ny = y; break; }
+                if (lds_u8(st_sa + cell_off(x, y, HP)) == CODE_EMPTY) { placed = true; npos = (uint32_t)(x | (y << 8)); break; }
             }
         }
         if (placed) {                                             // a failed placement (RecursionError, swallowed) leaves the ball
-            const uint32_t ball = cell_rd(st, ox * HP + oy);
-            cell_wr(st, nx * HP + ny, ball);
-            obst_set(st, c, k, nx, ny);
-            cell_wr(st, ox * HP + oy, CODE_EMPTY);
+            const uint32_t old_sa = st_sa + cell_off(ox, oy, HP);
+            sts_u8(st_sa + cell_off((int)(npos & 0xFF), (int)(npos >> 8), HP), lds_u8(old_sa));
+            sts_u8(old_sa, CODE_EMPTY);
+            sts_u16(ob_sa + (uint32_t)((k >> 1) * 128 + (k & 1) * 2), npos);
         }
     }
+    if (ag_mark) sts_u8(ag_sa, CODE_EMPTY);
     rg.ndraws = nd;
 }
 
@@ -526,49 +547,42 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
 // the warp's state block -- the fixed-start variant: agent at (1,1) facing right, then n_obstacles times
 // place_obj(Ball(), max_tries=100) over the whole grid.  With a uniform random policy an episode lasts ~12 steps, so
 // nearly every warp-step has a lane or two that must reset; doing that inside one lane stalls the other 30.  Here
-// lane j computes Philox block j of the new episode's stream (tries 2j and 2j+1), every lane tests its two
-// candidates against the static layout, and the balls are assigned in draw order with ballots: try t is taken by
-// ball k if it is the first try at or after the cursor that is free and not the position of an earlier ball.
-// Returns false (nothing but the removal of the old balls done) if 64 tries were not enough; the caller then runs the
-// scalar generator, which reproduces the same stream from its start.
+// lane t evaluates try t of the new episode's stream (draws 2t, 2t+1: half of Philox block t>>1).  place_obj accepts
+// a try iff its cell is free in the static layout, is not the agent's, and does not hold an earlier ball -- i.e. iff
+// it is free and the first try with that position (an earlier try with the same position was either not free, and
+// then neither is this one, or was itself accepted).  So: ballot(free), match_any(position) for "first with that
+// position", and the n_obstacles lowest accepted lanes each write their own ball.  No loop.
+// Returns false (nothing but the removal of the old balls done) if 32 tries were not enough; the caller then runs the
+// scalar generator, which replays the same stream from its start.
 __device__ __forceinline__ bool dynobs_coop_reset(uint32_t *st_warp, int src, int lane, const RolloutParams &p, int64_t gid,
                                                   uint32_t stream, uint32_t &consumed) {
     const DevCfg &c = p.cfg;
-    const int W = c.W, H = c.H, HP = c.HP, nob = c.n_obst;
-    uint32_t *col = st_warp + src;
-    const uint32_t col_sa = (uint32_t)__cvta_generic_to_shared(col);
-    auto cell_sa = [&](int x, int y) { const int i = x * HP + y; return col_sa + (uint32_t)((i >> 2) * 128 + (i & 3)); };
-    if (lane < nob) { int ox, oy; obst_get(col, c, lane, ox, oy); sts_u8(cell_sa(ox, oy), CODE_EMPTY); }   // grid := template
+    const int HP = c.HP, nob = c.n_obst;
+    const uint32_t col_sa = (uint32_t)__cvta_generic_to_shared(st_warp + src);
+    const uint32_t ob_sa = col_sa + (uint32_t)(c.GW + XWORDS) * 128u;
+    if (lane < nob) {                                             // grid := static layout
+        const uint32_t o = lds_u16(ob_sa + (uint32_t)((lane >> 1) * 128 + (lane & 1) * 2));
+        sts_u8(col_sa + cell_off((int)(o & 0xFF), (int)(o >> 8), HP), CODE_EMPTY);
+    }
     __syncwarp();
     uint32_t o0, o1, o2, o3;
-    philox4x32_10((uint32_t)lane, stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32),
+    philox4x32_10((uint32_t)(lane >> 1), stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32),
                   o0, o1, o2, o3);
-    const int xa = (int)__umulhi(o0, (uint32_t)W), ya = (int)__umulhi(o1, (uint32_t)H);
-    const int xb = (int)__umulhi(o2, (uint32_t)W), yb = (int)__umulhi(o3, (uint32_t)H);
-    auto is_free = [&](int x, int y) {                            // empty in the static layout and not the agent's cell
-        const int i = x * HP + y;
-        return ((__ldg(&p.tmpl[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) == CODE_EMPTY && !(x == 1 && y == 1);
-    };
-    uint32_t A = __ballot_sync(0xFFFFFFFFu, is_free(xa, ya)), B = __ballot_sync(0xFFFFFFFFu, is_free(xb, yb));
-    const uint32_t ca = (uint32_t)(xa | (ya << 8)), cb = (uint32_t)(xb | (yb << 8));
-    uint32_t mine = 0;
-    int cursor = 0;                                               // next try index (try t = lane t>>1, half t&1)
-    for (int k = 0; k < nob; ++k) {
-        const int la = (cursor + 1) >> 1, lb = cursor >> 1;
-        const uint32_t a = la >= 32 ? 0u : A & (0xFFFFFFFFu << la), b = lb >= 32 ? 0u : B & (0xFFFFFFFFu << lb);
-        const int ta = a ? 2 * (__ffs((int)a) - 1) : 1000, tb = b ? 2 * (__ffs((int)b) - 1) + 1 : 1000;
-        const int t = min(ta, tb);
-        if (t >= 1000) return false;
-        const uint32_t pos = __shfl_sync(0xFFFFFFFFu, (t & 1) ? cb : ca, t >> 1);
-        if (lane == k) mine = pos;
-        A &= ~__ballot_sync(0xFFFFFFFFu, ca == pos);
-        B &= ~__ballot_sync(0xFFFFFFFFu, cb == pos);
-        cursor = t + 1;
+    const int x = (int)__umulhi((lane & 1) ? o2 : o0, (uint32_t)c.W), y = (int)__umulhi((lane & 1) ? o3 : o1, (uint32_t)c.H);
+    const int i = x * HP + y;
+    const bool is_free = ((__ldg(&p.tmpl[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) == CODE_EMPTY && !(x == 1 && y == 1);
+    const uint32_t pos = (uint32_t)(x | (y << 8));
+    const uint32_t lt = (1u << lane) - 1u;
+    const bool first = (__match_any_sync(0xFFFFFFFFu, pos) & lt) == 0;
+    const uint32_t acc = __ballot_sync(0xFFFFFFFFu, is_free && first);
+    if (__popc(acc) < nob) return false;
+    const int rank = __popc(acc & lt);
+    const bool mine = ((acc >> lane) & 1u) && rank < nob;
+    consumed = 2u * (uint32_t)__ffs((int)__ballot_sync(0xFFFFFFFFu, mine && rank == nob - 1));   // draws up to the last ball's try
+    if (mine) {
+        sts_u8(col_sa + cell_off(x, y, HP), (uint32_t)code_of(T_BALL, C_BLUE, 0));
+        sts_u16(ob_sa + (uint32_t)((rank >> 1) * 128 + (rank & 1) * 2), pos);
     }
-    consumed = 2u * (uint32_t)cursor;
-    if (lane < nob) sts_u8(cell_sa((int)(mine & 0xFF), (int)(mine >> 8)), (uint32_t)code_of(T_BALL, C_BLUE, 0));
-    const uint32_t lo = __shfl_sync(0xFFFFFFFFu, mine, (2 * lane) & 31), hi = __shfl_sync(0xFFFFFFFFu, mine, (2 * lane + 1) & 31);
-    if (lane < 4) col[(c.GW + XWORDS + lane) * 32] = (2 * lane < nob ? lo : 0u) | (2 * lane + 1 < nob ? hi << 16 : 0u);
     __syncwarp();
     return true;
 }
