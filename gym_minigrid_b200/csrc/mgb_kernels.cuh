@@ -222,7 +222,10 @@ __device__ __noinline__ int rand_int(Rng &e, const RolloutParams &p, int low, in
 // in straight-line code (all lanes active, independent chains -> ILP) into its column of the warp's
 // staging buffer, which is idle between two observations.  word i of the window at draws[i*32].
 // blocks that fit the staging column of a lane (3*V*V/4 words): 9 blocks = 36 draws = 18 tries for V = 7
-__host__ __device__ constexpr int draw_blocks(int V) { return (3 * V * V / 4) / 4 < 9 ? (3 * V * V / 4) / 4 : 9; }
+#ifndef MGB_DYN_BLOCKS
+#define MGB_DYN_BLOCKS 9
+#endif
+__host__ __device__ constexpr int draw_blocks(int V) { return (3 * V * V / 4) / 4 < MGB_DYN_BLOCKS ? (3 * V * V / 4) / 4 : MGB_DYN_BLOCKS; }
 template <int NB>
 __device__ __noinline__ void prefetch_draws(uint32_t *draws, uint32_t first_block, uint32_t stream, int64_t gid, uint64_t seed) {
 #pragma unroll

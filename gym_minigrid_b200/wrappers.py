@@ -341,6 +341,19 @@ class _TakesOverAutoReset(Wrapper):
         return obs
 
 
+class TerminalObservation(_TakesOverAutoReset):
+    """Not a reference class: the gym.vector companion of auto-reset.  The batched env returns, at a done step, the
+    first observation of the next episode; this wrapper also hands out the observation the reference
+    would have returned at that step: info['terminal_observation'] = {'image' uint8 [N,V,V,3], 'direction' [N]},
+    meaningful where `done` is set (elsewhere it equals the returned observation)."""
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        info = dict(info)
+        info['terminal_observation'] = {'image': obs['image'].clone(), 'direction': obs['direction'].clone()}
+        return self._reset_done(obs, done), reward, done, info
+
+
 class _VisitBonus(_TakesOverAutoReset):
     _BY_ACTION = 0
 

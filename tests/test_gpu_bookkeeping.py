@@ -136,3 +136,33 @@ def test_bookkeeping_batch_properties():
         live = ~done
         assert torch.all(tail[live, 3].argmax(1) == acts[t][live].long()) and torch.all(tail[live, 3].sum(1) == 1)
         assert int(tail[done].sum()) == 0
+
+
+def test_terminal_observation_wrapper():
+    """TerminalObservation: same trajectory as the plain auto-resetting env, plus the reference's done-step observation
+    (= what a non-auto-resetting twin returns) in info."""
+    import gym_minigrid_b200 as mgb
+    from gym_minigrid_b200 import wrappers as W
+    N, T = 4099, 60
+    g = torch.Generator().manual_seed(11)
+    plain = mgb.make("MiniGrid-Dynamic-Obstacles-8x8-v0", num_envs=N, seed=5)
+    w = W.TerminalObservation(mgb.make("MiniGrid-Dynamic-Obstacles-8x8-v0", num_envs=N, seed=5))
+    o0, o1 = plain.reset(), w.reset()
+    assert torch.equal(o0["image"], o1["image"])
+    seen = 0
+    for t in range(T):
+        a = torch.randint(0, 3, (N,), dtype=torch.uint8, generator=g)
+        twin_state = plain.get_state()
+        p_obs, p_r, p_d, _ = plain.step(a)
+        w_obs, w_r, w_d, info = w.step(a)
+        assert torch.equal(p_obs["image"], w_obs["image"]) and torch.equal(p_obs["direction"], w_obs["direction"])
+        assert torch.equal(p_r, w_r) and torch.equal(p_d, w_d)
+        # a twin that does not auto-reset, started from the same pre-step state, shows the terminal observation
+        twin = mgb.make("MiniGrid-Dynamic-Obstacles-8x8-v0", num_envs=N, seed=5, autoreset=False)
+        twin.reset(); twin.set_state(twin_state)
+        t_obs, _, t_d, _ = twin.step(a)
+        assert torch.equal(t_d, w_d)
+        term = info["terminal_observation"]
+        assert torch.equal(term["image"], t_obs["image"]) and torch.equal(term["direction"], t_obs["direction"])
+        seen += int(w_d.sum())
+    assert seen > 100
