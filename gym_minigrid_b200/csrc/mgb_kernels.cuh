@@ -783,6 +783,14 @@ template <int V> __device__ __forceinline__ uint32_t revv(uint32_t v) { return _
 // process_vis, minigrid.py:624-635) as a carry chain: ((v&t)+t)^t marks [lowest seed .. run end+1]
 template <int V> __device__ __forceinline__ uint32_t flood_up(uint32_t v, uint32_t t) { return ((((v & t) + t) ^ t) | v) & ((1u << V) - 1u); }
 
+// (v & bit) ? x : 0.  Spelled as and/setp/selp so that ptxas turns the V tests of one row mask into a single R2P
+// (register bits -> predicates) plus one SEL per cell, instead of shift-left / arithmetic-shift-right / and per cell.
+__device__ __forceinline__ uint32_t sel_bit(uint32_t v, uint32_t bit, uint32_t x) {
+    uint32_t r;
+    asm("{ .reg .pred p; .reg .b32 t; and.b32 t, %1, %3; setp.ne.u32 p, t, 0; selp.b32 %0, %2, 0, p; }" : "=r"(r) : "r"(v), "r"(x), "r"(bit));
+    return r;
+}
+
 // insert the 3 low bytes of x at byte offset sh of the word pair (a, b); sh folds after unrolling
 __device__ __forceinline__ void put3(int sh, uint32_t &a, uint32_t &b, uint32_t x) {
     if (sh == 0) a = __byte_perm(a, x, 0x3654);
@@ -946,7 +954,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
                 }
 #else
                 {
-                    const uint32_t x = ((vis >> vx) & 1u) ? xs[vx] : 0u;
+                    const uint32_t x = sel_bit(vis, 1u << vx, xs[vx]);      // invisible cells stay (0,0,0)
                     const int b = 3 * (vx * V + vy);
                     put3(b & 3, acc[b >> 2], acc[(b >> 2) + 1], x);
                 }
