@@ -794,6 +794,67 @@ def bookkeeping_traces():
             bool((np.stack(out["sb_reward"]) < 0.6).any())))
 
 
+def dynobs_boxed_traces():
+    """Directed Dynamic-Obstacles cases: a ball walled in completely (its place_obj makes 101 tries =
+    202 draws every step and it stays), a ball with exactly one free neighbour, a ball whose window is clipped by the
+    grid border, and the agent standing next to a ball (the 'not onto the agent' rejection).  Philox-injected; the draw
+    counter after every step is part of the fixture."""
+    mg = sys.modules["gym_minigrid.minigrid"]
+    seed = 7171
+    for env_id in ("MiniGrid-Dynamic-Obstacles-8x8-v0", "MiniGrid-Dynamic-Obstacles-16x16-v0"):
+        cases = []
+        for k in range(6):
+            env = R.make(env_id)
+            u = env.unwrapped
+            shim = R.PhiloxShim(seed, k, 0)
+            u.np_random = shim
+            env.reset()
+            rs = np.random.RandomState(100 + k)
+            W, H = u.width, u.height
+
+            def free_nb(b):
+                bx, by = (int(v) for v in b.cur_pos)
+                out = []
+                for x in range(bx - 1, bx + 2):
+                    for y in range(by - 1, by + 2):
+                        if (x, y) != (bx, by) and 0 < x < W - 1 and 0 < y < H - 1 and u.grid.get(x, y) is None \
+                                and (x, y) != tuple(int(v) for v in u.agent_pos):
+                            out.append((x, y))
+                return out
+            # ball 0: walled in completely; ball 1: one free neighbour left
+            for bi, leave in ((0, 0), (1, 1)):
+                nb = free_nb(u.obstacles[bi])
+                rs.shuffle(nb)
+                for (x, y) in nb[leave:]:
+                    u.grid.set(x, y, mg.Wall())
+            # agent next to the last ball when possible
+            nb = free_nb(u.obstacles[-1])
+            if nb and k % 2 == 0:
+                u.agent_pos = np.array(nb[rs.randint(0, len(nb))])
+                u.agent_dir = int(rs.randint(0, 4))
+            s0 = R.snapshot(env)
+            nd0 = shim.ndraws
+            T = 10
+            actions = rs.randint(0, 2, size=T).astype(np.uint8)          # turn only: the episode goes on
+            if k == 5:
+                actions[-1] = 2
+            o = dict(obs=np.zeros((T, 7, 7, 3), np.uint8), dir=np.zeros(T, np.uint8), reward=np.zeros(T, np.float64),
+                     done=np.zeros(T, np.uint8), ndraws=np.zeros(T, np.int64), obstacles=np.zeros((T, MAX_OBST, 2), np.int16))
+            for t in range(T):
+                ob, r, d, _ = env.step(int(actions[t]))
+                o["obs"][t] = ob["image"]; o["dir"][t] = ob["direction"]; o["reward"][t] = float(r); o["done"][t] = d
+                o["ndraws"][t] = shim.ndraws
+                o["obstacles"][t] = pad_obst(R.snapshot(env)["obstacles"])
+            s1 = R.snapshot(env)
+            cases.append(dict(cfg=config_of(env), actions=actions, env_index=np.int64(k), seed=np.uint64(seed), ndraws0=np.int64(nd0), **o,
+                              grid0=s0["grid"], aux0=s0["aux"], agent0=s0["agent"], carrying0=s0["carrying"],
+                              obstacles0=pad_obst(s0["obstacles"]), grid1=s1["grid"], agent1=s1["agent"]))
+        path = save_scenes("dynobs_boxed_%s" % short(env_id), env_id, cases)
+        per_step = np.diff(np.stack([c["ndraws"] for c in cases]), axis=1)
+        print("%-50s %6.1f KB seed %d draws/step min %d max %d" % (os.path.basename(path), os.path.getsize(path) / 1024, seed,
+                                                                 per_step.min(), per_step.max()))
+
+
 def reward_table():
     """_reward() (minigrid.py:933-937) evaluated BY THE REFERENCE for every step_count of every
     max_steps in the registry (and 50 beyond): r_<max_steps>[k] = reward at step_count == k."""
@@ -817,6 +878,9 @@ if __name__ == "__main__":
     if "--bookkeeping-only" in sys.argv:
         bookkeeping_traces()
         sys.exit(0)
+    if "--dynobs-boxed-only" in sys.argv:
+        dynobs_boxed_traces()
+        sys.exit(0)
     if "--extras-only" not in sys.argv:
         main()
     reward_table()
@@ -826,3 +890,4 @@ if __name__ == "__main__":
     hook_traces()
     rgb_traces()
     bookkeeping_traces()
+    dynobs_boxed_traces()

@@ -280,3 +280,29 @@ def test_full_size_invariants():
     assert bool(((ag[:, 0] >= 1) & (ag[:, 0] <= 6) & (ag[:, 1] >= 1) & (ag[:, 1] <= 6)).all())
     assert bool((ag[:, 3] == T).all())
     env.check_errors()
+
+
+@pytest.mark.parametrize("path", golden_files("dynobs_boxed_"), ids=os.path.basename)
+def test_cuda_matches_reference_boxed_obstacles(path):
+    """Directed Dynamic-Obstacles cases: walled-in ball (101 tries = 202 draws per step, stays), one free neighbour,
+    agent next to a ball -- exercises the speculative tries, the one-try-at-a-time continuation past the prefetched
+    draw window and the on-demand Philox blocks; the draw counter is compared after every step."""
+    mgb = _mgb()
+    d = load(path)
+    n, T = d["actions"].shape
+    for k in range(n):
+        env = mgb.make(d["env_id"], num_envs=1, seed=int(d["seed"][k]), env_id_base=int(d["env_index"][k]), autoreset=False)
+        env.reset()
+        env.set_state(dict(grid=d["grid0"][k:k + 1], aux=d["aux0"][k:k + 1], agent=d["agent0"][k:k + 1], carrying=d["carrying0"][k:k + 1],
+                           obstacles=d["obstacles0"][k:k + 1], rng=np.array([[1, d["ndraws0"][k]]], np.int32)))
+        tag = "%s[%d]" % (os.path.basename(path), k)
+        for t in range(T):
+            obs, r, dn, _ = env.step(torch.as_tensor(d["actions"][k, t:t + 1]))
+            s = env.get_state(("rng", "obstacles"))
+            assert_same("%s@%d obs" % (tag, t), _np(obs["image"])[0], d["obs"][k, t])
+            assert int(obs["direction"][0]) == int(d["dir"][k, t]) and int(dn[0]) == int(d["done"][k, t])
+            assert bits(_np(r))[0] == bits(d["reward"][k, t:t + 1])[0]
+            assert int(_np(s["rng"])[0, 1]) == int(d["ndraws"][k, t]), "%s@%d draws" % (tag, t)
+            assert_same("%s@%d obstacles" % (tag, t), _np(s["obstacles"])[0], d["obstacles"][k, t])
+        assert_same(tag + " grid1", _np(env.get_state(("grid",))["grid"])[0], d["grid1"][k])
+        env.check_errors()
