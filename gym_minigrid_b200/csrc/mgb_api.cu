@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -47,9 +48,8 @@ struct mgb_handle {
     int view = 7;
     int obs_bytes = OBS_BYTES;
     int sm_count = 0;
-    int blocks_per_sm = 0;
-    int warps_per_block = 4;
-    size_t smem_bytes = 0;
+    // CTA shape per launch kind: [0] persistent rollouts (T > 1), [1] single steps / resets (state round-trips HBM)
+    struct Shape { int blocks_per_sm = 0, warps_per_block = 4, warps = 0; size_t smem_bytes = 0; } shape[2];
     int64_t launches = 0;
     // host pipeline (mgb_step_host)
     cudaStream_t pipe[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
@@ -168,15 +168,29 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     const size_t per_warp = (size_t)stage_bytes(h->view) + (size_t)(d.S + 1) * 32 * 4;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin) != cudaSuccess)
         return cleanup(fail("mgb_create: cannot opt in to %zu bytes of shared memory", (size_t)prop.sharedMemPerBlockOptin));
-    int best_warps = 0;
+    // Measured on B200 (profiles/README.md §4): a single-step launch is bound by the latency of the state round
+    // trip and wants every warp it can get; the persistent rollout is bound by the shared-memory pipe, which 24 warps
+    // saturate -- beyond that more resident warps only cost (28 warps: -4 %), and at equal warps more, smaller CTAs
+    // did slightly better (6 warps x 4 CTAs: +3 % over 8 x 3).
+    constexpr int ROLLOUT_WARP_CAP = 24;
+    const char *force = getenv("MGB_WARPS_PER_BLOCK");           // experiments only: pin the CTA shape
     for (int wpb = MAX_WARPS_PER_BLOCK; wpb >= 2; --wpb) {
+        if (force && atoi(force) != wpb) continue;
         const size_t smem = (size_t)(c.see_through ? table_bytes<true>() : table_bytes<false>()) + (size_t)wpb * per_warp;
         if (smem > prop.sharedMemPerBlockOptin) continue;
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, wpb * 32, smem) != cudaSuccess) continue;
-        if (nb * wpb > best_warps) { best_warps = nb * wpb; h->blocks_per_sm = nb; h->warps_per_block = wpb; h->smem_bytes = smem; }
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, wpb * 32, smem) != cudaSuccess || nb < 1) continue;
+        const int warps = nb * wpb;
+        mgb_handle::Shape cand;
+        cand.blocks_per_sm = nb; cand.warps_per_block = wpb; cand.warps = warps; cand.smem_bytes = smem;
+        if (warps > h->shape[1].warps) h->shape[1] = cand;
+        const mgb_handle::Shape &cur = h->shape[0];
+        const int capped = std::min(warps, ROLLOUT_WARP_CAP), best = std::min(cur.warps, ROLLOUT_WARP_CAP);
+        const int over = warps - capped, cur_over = cur.warps - best;
+        if (capped > best || (capped == best && (over < cur_over || (over == cur_over && wpb >= 6 && nb > cur.blocks_per_sm))))
+            h->shape[0] = cand;
     }
-    if (best_warps < 1) return cleanup(fail("mgb_create: kernel does not fit on an SM (%zu bytes of shared memory per warp)", per_warp));
+    if (h->shape[0].warps < 1) return cleanup(fail("mgb_create: kernel does not fit on an SM (%zu bytes of shared memory per warp)", per_warp));
     const size_t state_bytes = (size_t)h->n_groups * d.S * 32 * 4;
     if (cudaMalloc(&h->state, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: cudaMalloc(%zu) for env state failed", state_bytes));
     if (cudaMemset(h->state, 0, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: memset failed"));
@@ -246,10 +260,11 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
     p.tape = h->tape; p.tape_off = h->tape_off; p.err = h->err; p.pool = h->pool; p.pool_n = h->pool_n;
     p.m0 = 1u; p.m1 = 1u; p.m2 = 2u; p.m8 = 1u << 8; p.m16 = 1u << 16; p.m24 = 1u << 24;
     rollout_fn fn = pick_kernel(h->cfg);
-    const int want = (ng + h->warps_per_block - 1) / h->warps_per_block;
-    const int grid = std::max(1, std::min(want, h->sm_count * h->blocks_per_sm));
+    const mgb_handle::Shape &sh = h->shape[T > 1 ? 0 : 1];
+    const int want = (ng + sh.warps_per_block - 1) / sh.warps_per_block;
+    const int grid = std::max(1, std::min(want, h->sm_count * sh.blocks_per_sm));
     if (timed && h->timing) CUDA_OK(cudaEventRecord(h->ev0, stream));
-    fn<<<grid, h->warps_per_block * 32, h->smem_bytes, stream>>>(p);
+    fn<<<grid, sh.warps_per_block * 32, sh.smem_bytes, stream>>>(p);
     CUDA_OK(cudaGetLastError());
     if (timed && h->timing) { CUDA_OK(cudaEventRecord(h->ev1, stream)); h->ev_valid = true; }
     h->launches++;

@@ -29,7 +29,20 @@ constexpr int GROUP = 32;
 constexpr int STAGE_BYTES = GROUP * OBS_BYTES;   // 4704 = 294 * 16
 // the kernel is a template on the (odd) view size V: record = 3*V*V bytes, staging block = 32 records
 __host__ __device__ constexpr int obs_bytes(int V) { return 3 * V * V; }
-__host__ __device__ constexpr int stage_bytes(int V) { return GROUP * 3 * V * V; }      // multiple of 16 for every V
+// Staging block of a warp: the 32 records of a step, stored to global memory with bulk copies.  Lane l writes the
+// 37 words that cover its own 147-byte record, starting at word floor(36.75 l); for V = 7 four pairs of lanes start in
+// the same bank ({0,27}, {2,29}, {3,30}, {4,31}), which made every one of the 37 stores of a step a 2-way bank conflict
+// (17 % of all shared-memory wavefronts of the kernel).  The block is therefore kept in STAGE_NSEG segments that are
+// contiguous both here and in global memory -- cut where a record's first word is 16-byte aligned, before lanes
+// 6, 11, 16, 22, 27 -- and segment k is placed 12 words further up than the one before: the 32 start banks become a
+// permutation of 0..31, the lane's addressing stays `q + j`, and the block leaves as 6 bulk copies instead of one.
+#ifndef MGB_STAGE_SEG
+#define MGB_STAGE_SEG 0
+#endif
+constexpr int STAGE_SEG_WORDS = 12;                      // extra word offset per segment
+__host__ __device__ constexpr int stage_nseg(int V) { return (MGB_STAGE_SEG && V == 7) ? 6 : 1; }
+__host__ __device__ constexpr int stage_seg_lane(int V, int k) { return stage_nseg(V) == 1 ? (k == 0 ? 0 : GROUP) : (16 * k + 2) / 3; }   // 0,6,11,16,22,27,32
+__host__ __device__ constexpr int stage_bytes(int V) { return GROUP * 3 * V * V + (stage_nseg(V) - 1) * STAGE_SEG_WORDS * 4; }      // multiple of 16 for every V
 constexpr int MAX_WARPS_PER_BLOCK = 8;           // the host picks 2..8 warps per CTA to maximise resident warps/SM
 #ifndef MGB_SEE_MIN_BLOCKS
 #define MGB_SEE_MIN_BLOCKS 0     // experiment: >0 adds minBlocksPerSM to the see-through kernels' launch bounds (register cap)
@@ -860,7 +873,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
     // times 2^s8 (one IMAD.WIDE) gives the bits that stay in block word q+j (low half) and the bits that
     // spill into q+j+1 (high half, carried into the next multiply-add).
     const int boff = lane * R;
-    const int q = boff >> 2;
+    const int q = (boff >> 2) + (stage_nseg(V) > 1 ? STAGE_SEG_WORDS * ((3 * lane) >> 4) : 0);   // (3*lane)>>4 = segment of the lane
     const uint32_t s8 = (boff & 3) * 8;
     const uint32_t M = p.m1 << s8;
     uint32_t first = 0, w36 = 0, w37 = 0, spill = 0;
@@ -981,10 +994,12 @@ __device__ __forceinline__ void bulk_store_wait_read() {
 __device__ __forceinline__ void bulk_store_wait_all() {
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_store(void *gptr, const void *sptr, uint32_t bytes) {
+__device__ __forceinline__ void bulk_copy(void *gptr, const void *sptr, uint32_t bytes) {
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sptr);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gptr), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
@@ -1006,7 +1021,10 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
     const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const DevCfg &c = p.cfg;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    // the warp index goes through a lane-0 broadcast so that ptxas knows it is warp-uniform: everything derived from
+    // it (group, staging block, output addresses) then lives in uniform registers and the bulk copies below need no
+    // per-lane "waterfall" loop around their uniform-register operands
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
     uint32_t *axis = lut + lut_bytes<SEE>() / 4;                                           // [2][AXIS_ENTRIES]
     uint8_t *stage_base = smem_raw + table_bytes<SEE>();
@@ -1108,11 +1126,25 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
                 if (full && ((reinterpret_cast<uintptr_t>(gobs) & 15) == 0)) {
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) bulk_store(gobs, stage_w, SB);
+                    if (lane == 0) {                              // one bulk copy per segment, one commit group
+#pragma unroll
+                        for (int k = 0; k < stage_nseg(V); ++k) {
+                            const int w0 = (stage_seg_lane(V, k) * OB) >> 2, w1 = (stage_seg_lane(V, k + 1) * OB) >> 2;
+                            bulk_copy(gobs + 4 * w0, stage_w + w0 + STAGE_SEG_WORDS * k, 4u * (uint32_t)(w1 - w0));
+                        }
+                        bulk_commit();
+                    }
                 } else {                                         // ragged tail group / unaligned base
                     __syncwarp();
                     const uint8_t *sb = reinterpret_cast<const uint8_t *>(stage_w);
-                    for (int b = lane; b < nvalid * OB; b += 32) gobs[b] = sb[b];
+                    for (int b = lane; b < nvalid * OB; b += 32) {
+                        int sh = 0;
+                        if (stage_nseg(V) > 1) {
+#pragma unroll
+                            for (int k = 1; k < stage_nseg(V); ++k) sh += b >= ((stage_seg_lane(V, k) * OB) & ~3) ? STAGE_SEG_WORDS * 4 : 0;
+                        }
+                        gobs[b] = sb[b + sh];
+                    }
                     __syncwarp();
                 }
             }
