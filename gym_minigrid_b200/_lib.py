@@ -50,7 +50,7 @@ SIGNATURES = {
     "mgb_onehot": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "mgb_flat_obs": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int64, _P]),
     "mgb_render_partial": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.c_int64, _P]),
-    "mgb_render_full": (C.c_int, [_P, _P, C.c_int32, _P, _P]),
+    "mgb_render_full": (C.c_int, [_P, _P, _P, C.c_int32, _P, _P]),
     "mgb_visit_bonus": (C.c_int, [_P, C.c_int32, _P, _P, C.c_int64, _P, _P]),
     "mgb_dac": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mgb_append_action": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),

@@ -454,14 +454,14 @@ int mgb_render_partial(const uint8_t *obs, int32_t view, const uint8_t *atlas, i
     return 0;
 }
 
-int mgb_render_full(mgb_handle *h, const uint8_t *atlas, int32_t tile, uint8_t *out, void *stream) {
+int mgb_render_full(mgb_handle *h, const uint8_t *obs, const uint8_t *atlas, int32_t tile, uint8_t *out, void *stream) {
     if (!h || !atlas || !out) return fail("mgb_render_full: null argument");
     if (tile < 8 || tile % 8 != 0) return fail("mgb_render_full: tile must be a multiple of 8");
     if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(atlas)) & 7) return fail("mgb_render_full: out and atlas must be 8-byte aligned");
     CUDA_OK(cudaSetDevice(h->device));
     const int64_t segs = h->n_envs * h->dc.H * tile * h->dc.W;
-    if (segs < ((int64_t)1 << 31) - (1 << 24)) k_render_full<uint32_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, atlas, tile, out, h->n_envs);
-    else k_render_full<uint64_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, atlas, tile, out, h->n_envs);
+    if (segs < ((int64_t)1 << 31) - (1 << 24)) k_render_full<uint32_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, obs, h->view, atlas, tile, out, h->n_envs);
+    else k_render_full<uint64_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, obs, h->view, atlas, tile, out, h->n_envs);
     CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;

@@ -1412,7 +1412,7 @@ __global__ void k_flat_obs(const uint8_t *__restrict__ img, int img_bytes, const
 // RGB wrappers: one thread copies one tile row (tile*3 bytes, a multiple of 8) from the atlas to the image.
 // Consecutive threads write consecutive segments of an image row, so the output stream is fully coalesced;
 // the atlas (<= 1.3 MB) stays in L2/L1.
-constexpr int ATLAS_VARIANTS = 7;
+constexpr int ATLAS_VARIANTS = 10;   // 0 plain, 1 highlight, 2..5 agent dir 0..3, 6 agent dir 3 + highlight, 7..9 agent dir 0..2 + highlight
 __device__ __forceinline__ void copy_tile_row(const uint8_t *__restrict__ atlas, int tile, int tile_id, int py, uint8_t *dst) {
     const uint2 *src = reinterpret_cast<const uint2 *>(atlas + ((size_t)tile_id * tile + py) * tile * 3);
     uint2 *d = reinterpret_cast<uint2 *>(dst);
@@ -1441,9 +1441,12 @@ __global__ void k_render_partial(const uint8_t *__restrict__ obs, int V, const u
     }
 }
 
+// obs != NULL: MiniGridEnv.render(highlight=True) (minigrid.py:1415-1450): a cell is highlighted iff it lies in the
+// agent's view and is visible there; visibility is read off the partial observation (type != unseen, as Grid.decode
+// does, minigrid.py:613), view cell (vx,vy) of world cell p being  vx = (p-agent).r + V/2,  vy = V-1 - (p-agent).f.
 template <typename IDX>
-__global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, const uint8_t *__restrict__ atlas, int tile,
-                              uint8_t *__restrict__ out, int64_t N) {
+__global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, const uint8_t *__restrict__ obs, int V,
+                              const uint8_t *__restrict__ atlas, int tile, uint8_t *__restrict__ out, int64_t N) {
     const IDX rows = (IDX)(c.H * tile), uW = (IDX)c.W;
     const IDX total = (IDX)N * rows * uW;
     for (IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IDX)gridDim.x * blockDim.x) {
@@ -1458,8 +1461,16 @@ __global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, cons
         const uint32_t x = lut_entry((int)cc);                  // (type, colour, state) of the real object
         const int code = (int)(x & 0xFF) * 21 + (int)((x >> 8) & 0xFF) * 3 + (int)((x >> 16) & 0xFF);
         const uint32_t w0 = base[c.GW * 32];
-        const bool agent_here = (int)(w0 & 0xFF) == cx && (int)((w0 >> 8) & 0xFF) == cy;
-        const int variant = agent_here ? 2 + (int)((w0 >> 16) & 3) : 0;          // highlight=False (wrappers.py:270)
+        const int ax = (int)(w0 & 0xFF), ay = (int)((w0 >> 8) & 0xFF), dir = (int)((w0 >> 16) & 3);
+        const bool agent_here = ax == cx && ay == cy;
+        bool hl = false;
+        if (obs) {
+            const int fx = (dir & 1) ? 0 : 1 - dir, fy = (dir & 1) ? 2 - dir : 0;      // DIR_TO_VEC; right = (-fy, fx)
+            const int rx = cx - ax, ry = cy - ay;
+            const int vx = rx * -fy + ry * fx + V / 2, vy = V - 1 - (rx * fx + ry * fy);
+            if ((unsigned)vx < (unsigned)V && (unsigned)vy < (unsigned)V) hl = obs[(((size_t)n * V + vx) * V + vy) * 3] != 0;
+        }
+        const int variant = agent_here ? (hl ? (dir == 3 ? 6 : 7 + dir) : 2 + dir) : (hl ? 1 : 0);
         copy_tile_row(atlas, tile, code * ATLAS_VARIANTS + variant, py, out + (size_t)i * tile * 3);
     }
 }

@@ -124,6 +124,7 @@ class VecMiniGridEnv:
             self._rew = torch.empty((N,), dtype=torch.float64, device=self.device)
             self._done = torch.empty((N,), dtype=torch.uint8, device=self.device)
         self._host = None
+        self._render_scratch = None
 
     # ------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -332,6 +333,29 @@ class VecMiniGridEnv:
         """FullyObsWrapper.observation (wrappers.py:311-338) for every env: uint8[N,W,H,3]."""
         out = torch.empty((self.num_envs, self.width, self.height, 3), dtype=torch.uint8, device=self.device)
         _lib.check(self._L.mgb_full_obs(self._h, _ptr(out), self._stream()))
+        return out
+
+    def render(self, mode='rgb_array', close=False, highlight=True, tile_size=8):
+        """MiniGridEnv.render (minigrid.py:1400-1466), mode 'rgb_array': uint8 [N, height*ts, width*ts, 3], the cells
+        the agent currently sees highlighted (read off the env's current partial observation).  Only tile sizes with a
+        shipped atlas (8); the reference default is 32.  There is no window ('human' mode)."""
+        if close:
+            return None
+        if mode != 'rgb_array':
+            raise NotImplementedError("batched envs render to arrays only (mode='rgb_array')")
+        from .wrappers import _atlas
+        atlas = _atlas(tile_size, self.device)
+        out = torch.empty((self.num_envs, self.height * tile_size, self.width * tile_size, 3), dtype=torch.uint8, device=self.device)
+        view = None
+        if highlight:                                         # observe the current state (no reset) into a private buffer
+            if self._render_scratch is None:
+                V = self.agent_view_size
+                self._render_scratch = (torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device),
+                                        torch.empty((self.num_envs, V, V, 3), dtype=torch.uint8, device=self.device),
+                                        torch.empty(self.num_envs, dtype=torch.uint8, device=self.device))
+            none, view, vdir = self._render_scratch
+            _lib.check(self._L.mgb_reset(self._h, _ptr(none), _ptr(view), _ptr(vdir), self._stream()))
+        _lib.check(self._L.mgb_render_full(self._h, _ptr(view), _ptr(atlas), tile_size, _ptr(out), self._stream()))
         return out
 
     def check_errors(self):

@@ -302,12 +302,7 @@ class RGBImgObsWrapper(ObservationWrapper):
         self._atlas = _atlas(tile_size, env.unwrapped.device)
 
     def observation(self, obs):
-        L = _lib.load()
-        u = self.unwrapped
-        ts = self.tile_size
-        out = torch.empty((u.num_envs, u.height * ts, u.width * ts, 3), dtype=torch.uint8, device=u.device)
-        _lib.check(L.mgb_render_full(u._h, _ptr(self._atlas), ts, _ptr(out), u._stream()))
-        return {'mission': obs['mission'], 'image': out}
+        return {'mission': obs['mission'], 'image': self.unwrapped.render('rgb_array', highlight=False, tile_size=self.tile_size)}
 
 
 # ------------------------------------------------------------------------------------------------

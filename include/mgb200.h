@@ -174,8 +174,8 @@ int mgb_flat_obs(const uint8_t *img, int32_t img_bytes, const float *mission_tab
                  const uint8_t *mission_idx, float *out, int64_t N, void *stream);
 
 /* ---- RGB observation wrappers: tile-atlas gathers, pixel-exact with the reference rasteriser ----
- * atlas uint8 [231][7][tile][tile][3] (device): tile for cell encoding code = type*21 + colour*3 + state and variant
- * 0 plain, 1 highlighted, 2..5 agent facing dir 0..3, 6 agent facing up + highlight; built from the reference's
+ * atlas uint8 [231][10][tile][tile][3] (device): tile for cell encoding code = type*21 + colour*3 + state and variant
+ * 0 plain, 1 highlighted, 2..5 agent facing dir 0..3, 6 agent facing up + highlight, 7..9 agent facing dir 0..2 + highlight; built from the reference's
  * Grid.render_tile by oracle/gen_atlas.py and shipped as gym_minigrid_b200/data/tile_atlas_t8.npz.  tile % 8 == 0. */
 
 /* RGBImgPartialObsWrapper.observation = MiniGridEnv.get_obs_render (wrappers.py:283-309, minigrid.py:1383-1398):
@@ -183,9 +183,11 @@ int mgb_flat_obs(const uint8_t *img, int32_t img_bytes, const float *mission_tab
  * type != unseen is highlighted. */
 int mgb_render_partial(const uint8_t *obs, int32_t view, const uint8_t *atlas, int32_t tile, uint8_t *out,
                        int64_t N, void *stream);
-/* RGBImgObsWrapper.observation = env.render('rgb_array', highlight=False) (wrappers.py:245-281, minigrid.py:1400-1466):
- * out [N][H*tile][W*tile][3] from the handle's current state. */
-int mgb_render_full(mgb_handle *h, const uint8_t *atlas, int32_t tile, uint8_t *out, void *stream);
+/* MiniGridEnv.render('rgb_array', highlight=...) (minigrid.py:1400-1466) and RGBImgObsWrapper.observation, which is
+ * render(highlight=False) (wrappers.py:245-281): out [N][H*tile][W*tile][3] from the handle's current state.
+ * obs == NULL: no highlight.  obs = the current partial observation [N][V][V][3] (as written by mgb_reset/mgb_step):
+ * the cells the agent sees are highlighted. */
+int mgb_render_full(mgb_handle *h, const uint8_t *obs, const uint8_t *atlas, int32_t tile, uint8_t *out, void *stream);
 
 /* ---- bookkeeping wrappers: element-wise kernels on the outputs of a step ---- */
 

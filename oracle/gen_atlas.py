@@ -6,8 +6,9 @@ the tile_size x tile_size x 3 result.
 
     python oracle/gen_atlas.py            # writes gym_minigrid_b200/data/tile_atlas_t8.npz  (needs /root/reference)
 
-atlas uint8 [231][7][T][T][3]; variants: 0 plain, 1 highlighted, 2..5 agent facing dir 0..3 (no highlight),
-6 agent facing up (dir 3) + highlight (the agent's own cell of the partial view, minigrid.py:1383-1398).
+atlas uint8 [231][10][T][T][3]; variants: 0 plain, 1 highlighted, 2..5 agent facing dir 0..3 (no highlight),
+6 agent facing up (dir 3) + highlight (the agent's own cell of the partial view, minigrid.py:1383-1398),
+7..9 agent facing dir 0..2 + highlight (env.render(highlight=True), minigrid.py:1400-1466).
 Index 231*... rows for type 10 ('agent') stay zero: that type never reaches a renderer.
 """
 import os
@@ -19,7 +20,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_shim as R  # noqa: E402
 
-VARIANTS = [(None, False), (None, True), (0, False), (1, False), (2, False), (3, False), (3, True)]
+VARIANTS = [(None, False), (None, True), (0, False), (1, False), (2, False), (3, False), (3, True), (0, True), (1, True), (2, True)]
 
 
 def main(tile=8):

@@ -679,7 +679,7 @@ def rgb_traces():
     seed = 2468
     for env_id in ("MiniGrid-DoorKey-8x8-v0", "MiniGrid-KeyCorridorS3R3-v0", "MiniGrid-Dynamic-Obstacles-8x8-v0", "MiniGrid-FourRooms-v0"):
         idx, T = [1, 17], 24
-        part, full, acts = [], [], []
+        part, full, fullhl, acts = [], [], [], []
         for k, i in enumerate(idx):
             env = R.make(env_id)
             shim = R.PhiloxShim(seed, i, 0)
@@ -688,6 +688,7 @@ def rgb_traces():
             wp, wf = W.RGBImgPartialObsWrapper(env), W.RGBImgObsWrapper(env)
             a = np.random.RandomState(300 + k).randint(0, env.action_space.n, size=T).astype(np.uint8)
             P, F = [wp.observation(obs)["image"].copy()], [wf.observation(obs)["image"].copy()]
+            H = [env.render('rgb_array', highlight=True, tile_size=8).copy()]        # MiniGridEnv.render, view highlighted
             ep = 1
             for t in range(T):
                 obs, r, d, _ = env.step(int(a[t]))
@@ -696,10 +697,11 @@ def rgb_traces():
                     ep += 1
                     obs = env.reset()
                 P.append(wp.observation(obs)["image"].copy()); F.append(wf.observation(obs)["image"].copy())
-            part.append(np.stack(P)); full.append(np.stack(F)); acts.append(a)
+                H.append(env.render('rgb_array', highlight=True, tile_size=8).copy())
+            part.append(np.stack(P)); full.append(np.stack(F)); fullhl.append(np.stack(H)); acts.append(a)
         path = os.path.join(OUT, "rgb_%s.npz" % short(env_id))
         np.savez_compressed(path, env_id=env_id, seed=np.uint64(seed), env_indices=np.array(idx, np.int64), actions=np.stack(acts),
-                            partial=np.stack(part), full=np.stack(full))
+                            partial=np.stack(part), full=np.stack(full), full_highlight=np.stack(fullhl))
         print("%-44s %6.1f KB partial %s full %s" % (os.path.basename(path), os.path.getsize(path) / 1024, part[0].shape, full[0].shape))
 
 
@@ -877,6 +879,9 @@ if __name__ == "__main__":
     R.load_reference()
     if "--bookkeeping-only" in sys.argv:
         bookkeeping_traces()
+        sys.exit(0)
+    if "--rgb-only" in sys.argv:
+        rgb_traces()
         sys.exit(0)
     if "--dynobs-boxed-only" in sys.argv:
         dynobs_boxed_traces()

@@ -29,6 +29,8 @@ def test_rgb_wrappers_match_reference(path):
             tag = "%s[%d]@%d" % (os.path.basename(path), k, t)
             assert_same(tag + " partial", wp.observation(obs)["image"].cpu().numpy()[0], z["partial"][k, t])
             assert_same(tag + " full", wf.observation(obs)["image"].cpu().numpy()[0], z["full"][k, t])
+            # MiniGridEnv.render('rgb_array', highlight=True): the agent's visible cells highlighted
+            assert_same(tag + " render(highlight)", env.render('rgb_array', highlight=True, tile_size=8).cpu().numpy()[0], z["full_highlight"][k, t])
             if t < T:
                 obs, _, _, _ = env.step(torch.as_tensor(z["actions"][k, t:t + 1]))
 
