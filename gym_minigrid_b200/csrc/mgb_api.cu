@@ -161,6 +161,13 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     d.GW = c.width * d.HP / 4;
     d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0) + (c.gen == MGB_GEN_POOL ? 1 : 0);   // pool: + level word
     h->sm_count = prop.multiProcessorCount;
+#if MGB_LUT_CONST
+    {
+        uint32_t t24[256];
+        for (int i = 0; i < 256; ++i) t24[i] = lut_entry(i) & 0x00FFFFFFu;
+        if (cudaMemcpyToSymbol(c_lut24, t24, sizeof t24) != cudaSuccess) return fail("mgb_create: constant LUT upload failed");
+    }
+#endif
 
     auto cleanup = [&](int rc) { mgb_destroy(h); return rc; };
     // warps per CTA: whatever keeps the most warps resident per SM (shared memory is the limiter for the

@@ -812,6 +812,12 @@ __device__ __forceinline__ void put3(int sh, uint32_t &a, uint32_t &b, uint32_t 
     else { a = __byte_perm(a, x, 0x4210); b = __byte_perm(b, x, 0x3265); }
 }
 
+#ifndef MGB_LUT_CONST
+#define MGB_LUT_CONST 0      // experiment: see-through path reads the 24-bit cell encoding from constant memory instead of shared
+#endif
+#if MGB_LUT_CONST
+__constant__ uint32_t c_lut24[256];
+#endif
 // code -> LUT word; the address is formed with a multiply-add so that it issues on the (idle) FMA
 // pipe instead of the ALU pipe that bounds this kernel
 __device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
@@ -915,7 +921,11 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
             for (int i = 0; i < GB * 4; ++i) {
                 const int ci = g0 * 4 + i;
                 x[i] = 0;
+#if MGB_LUT_CONST
+                if (ci < V * V) x[i] = (ci == AGENT_CI) ? own : c_lut24[code[i]];
+#else
                 if (ci < V * V) x[i] = (ci == AGENT_CI) ? own : lut_ld(lut_sa, code[i]);
+#endif
             }
 #pragma unroll
             for (int gg = 0; gg < GB; ++gg) {
