@@ -383,6 +383,86 @@ class VecMiniGridEnv:
     def carrying(self):
         return self.get_state(("carrying",))["carrying"]
 
+    # ------------------------------------------------------------------ MiniGridEnv geometry helpers, batched
+    # (minigrid.py:1092-1225).  Scalars broadcast over the batch; "None" results become a boolean mask.
+    def _agent(self):
+        return self.get_state(("agent",))["agent"]
+
+    @staticmethod
+    def _vec(d):
+        """DIR_TO_VEC (minigrid.py:63-73): right, down, left, up"""
+        return torch.stack([(1 - d) * (1 - (d & 1)), (2 - d) * (d & 1)], dim=1)
+
+    @property
+    def dir_vec(self):
+        return self._vec(self._agent()[:, 2])
+
+    @property
+    def right_vec(self):
+        v = self.dir_vec
+        return torch.stack([-v[:, 1], v[:, 0]], dim=1)
+
+    @property
+    def front_pos(self):
+        a = self._agent()
+        return a[:, :2] + self._vec(a[:, 2])
+
+    @property
+    def left_pos(self):
+        a = self._agent()
+        return a[:, :2] + self._vec((a[:, 2] - 1) % 4)
+
+    @property
+    def right_pos(self):
+        a = self._agent()
+        return a[:, :2] + self._vec((a[:, 2] + 1) % 4)
+
+    def get_view_coords(self, i, j, agent=None):
+        """absolute (i, j) -> the agent's view coordinates (vx, vy), possibly outside the view (minigrid.py:1135-1160)"""
+        a = self._agent() if agent is None else agent
+        d = self._vec(a[:, 2])
+        rx, ry = -d[:, 1], d[:, 0]
+        sz, hs = self.agent_view_size, self.agent_view_size // 2
+        tx = a[:, 0] + d[:, 0] * (sz - 1) - rx * hs
+        ty = a[:, 1] + d[:, 1] * (sz - 1) - ry * hs
+        lx, ly = torch.as_tensor(i, device=self.device) - tx, torch.as_tensor(j, device=self.device) - ty
+        return rx * lx + ry * ly, -(d[:, 0] * lx + d[:, 1] * ly)
+
+    def get_view_exts(self):
+        """(topX, topY, botX, botY) of the agent's view window, int32 [N,4] (minigrid.py:1162-1189)"""
+        a = self._agent()
+        V, h, d = self.agent_view_size, self.agent_view_size // 2, a[:, 2]
+        top_x = a[:, 0] - torch.where(d == 0, 0, torch.where(d == 2, V - 1, h))
+        top_y = a[:, 1] - torch.where(d == 1, 0, torch.where(d == 3, V - 1, h))
+        return torch.stack([top_x, top_y, top_x + V, top_y + V], dim=1)
+
+    def relative_coords(self, x, y, agent=None):
+        """(vx, vy, valid): valid is False where the reference returns None (minigrid.py:1191-1201)"""
+        vx, vy = self.get_view_coords(x, y, agent)
+        V = self.agent_view_size
+        return vx, vy, (vx >= 0) & (vy >= 0) & (vx < V) & (vy < V)
+
+    def in_view(self, x, y):
+        return self.relative_coords(x, y)[2]
+
+    def gen_obs(self):
+        """MiniGridEnv.gen_obs (minigrid.py:1359-1381): the observation of the current state, without stepping"""
+        return self.reset(mask=torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device))
+
+    def agent_sees(self, x, y):
+        """minigrid.py:1210-1225: (x, y) is in view, shows a non-empty cell there, and its type equals the world cell's.
+        (Where the reference would fail on an empty world cell under a carried object, this returns False.)"""
+        s = self.get_state(("agent", "grid"))
+        vx, vy, ok = self.relative_coords(x, y, s["agent"])
+        img = self.gen_obs()['image']
+        n = torch.arange(self.num_envs, device=self.device)
+        V = self.agent_view_size
+        seen = img[n, vx.clamp(0, V - 1).long(), vy.clamp(0, V - 1).long(), 0]
+        xs = torch.as_tensor(x, device=self.device).expand(self.num_envs).clamp(0, self.width - 1).long()
+        ys = torch.as_tensor(y, device=self.device).expand(self.num_envs).clamp(0, self.height - 1).long()
+        world = s["grid"][n, xs, ys, 0]
+        return ok & (seen > 1) & (seen == world)
+
     @property
     def mission(self):
         return MissionBatch(self)

@@ -857,6 +857,54 @@ def dynobs_boxed_traces():
                                                                  per_step.min(), per_step.max()))
 
 
+def helper_traces():
+    """MiniGridEnv geometry helpers (minigrid.py:1092-1225) evaluated by the reference on Philox-injected trajectories:
+    dir_vec, right_vec, front/left/right_pos, get_view_exts, and get_view_coords / in_view / agent_sees for EVERY cell."""
+    seed = 3131
+    for env_id in ("MiniGrid-DoorKey-8x8-v0", "MiniGrid-KeyCorridorS3R3-v0", "MiniGrid-Dynamic-Obstacles-6x6-v0"):
+        idx, T = [4, 12], 30
+        out = {k: [] for k in ("actions", "dir_vec", "right_vec", "front_pos", "left_pos", "right_pos", "view_exts", "view_coords",
+                               "in_view", "agent_sees")}
+        for k, i in enumerate(idx):
+            env = R.make(env_id)
+            u = env.unwrapped
+            shim = R.PhiloxShim(seed, i, 0)
+            u.np_random = shim
+            env.reset()
+            a = np.random.RandomState(900 + k).randint(0, env.action_space.n, size=T).astype(np.uint8)
+            rec = {k2: [] for k2 in out if k2 != "actions"}
+            ep = 1
+
+            def snap():
+                W_, H_ = u.width, u.height
+                rec["dir_vec"].append(np.array(u.dir_vec, np.int32)); rec["right_vec"].append(np.array(u.right_vec, np.int32))
+                rec["front_pos"].append(np.array(u.front_pos, np.int32)); rec["left_pos"].append(np.array(u.left_pos, np.int32))
+                rec["right_pos"].append(np.array(u.right_pos, np.int32)); rec["view_exts"].append(np.array(u.get_view_exts(), np.int32))
+                vc, iv, sees = np.zeros((W_, H_, 2), np.int32), np.zeros((W_, H_), bool), np.zeros((W_, H_), bool)
+                for x in range(W_):
+                    for y in range(H_):
+                        vc[x, y] = u.get_view_coords(x, y)
+                        iv[x, y] = u.in_view(x, y)
+                        try:
+                            sees[x, y] = bool(u.agent_sees(x, y))
+                        except AttributeError:            # world cell None under a carried object (minigrid.py:1223-1225)
+                            sees[x, y] = False
+                rec["view_coords"].append(vc); rec["in_view"].append(iv); rec["agent_sees"].append(sees)
+            snap()
+            for t in range(T):
+                _, _, d, _ = env.step(int(a[t]))
+                if d:
+                    shim.new_episode(ep); ep += 1
+                    env.reset()
+                snap()
+            out["actions"].append(a)
+            for k2 in rec:
+                out[k2].append(np.stack(rec[k2]))
+        path = os.path.join(OUT, "helpers_%s.npz" % short(env_id))
+        np.savez_compressed(path, env_id=env_id, seed=np.uint64(seed), env_indices=np.array(idx, np.int64), **{k2: np.stack(v) for k2, v in out.items()})
+        print("%-44s %6.1f KB  agent_sees true: %d" % (os.path.basename(path), os.path.getsize(path) / 1024, int(np.stack(out["agent_sees"]).sum())))
+
+
 def reward_table():
     """_reward() (minigrid.py:933-937) evaluated BY THE REFERENCE for every step_count of every
     max_steps in the registry (and 50 beyond): r_<max_steps>[k] = reward at step_count == k."""
@@ -880,6 +928,9 @@ if __name__ == "__main__":
     if "--bookkeeping-only" in sys.argv:
         bookkeeping_traces()
         sys.exit(0)
+    if "--helpers-only" in sys.argv:
+        helper_traces()
+        sys.exit(0)
     if "--rgb-only" in sys.argv:
         rgb_traces()
         sys.exit(0)
@@ -896,3 +947,4 @@ if __name__ == "__main__":
     rgb_traces()
     bookkeeping_traces()
     dynobs_boxed_traces()
+    helper_traces()
