@@ -240,6 +240,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         Ke = max(3, min(K, 10))
+        # host buffers are pinned next to this rank's GPU (one process per GPU: no D2H stream crosses the socket link)
+        from gym_minigrid_b200.sharding import bind_to_gpu_numa_node
+        affinity0 = os.sched_getaffinity(0)
+        numa = bind_to_gpu_numa_node(local)
         hacts = [torch.randint(0, cfg["n_actions"], (N,), dtype=torch.uint8).pin_memory() for _ in range(2)]
         for i in range(2):
             env.step_host(hacts[i % 2])
@@ -252,7 +256,9 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * N * Ke / float(te.item()), "unit": "env-steps/s", "h2d_bytes_per_step": N,
-               "d2h_bytes_per_step": N * (147 + 8 + 1 + 1), "steps": Ke, "api": "VecMiniGridEnv.step_host -> mgb_step_host"}
+               "d2h_bytes_per_step": N * (147 + 8 + 1 + 1), "steps": Ke, "api": "VecMiniGridEnv.step_host -> mgb_step_host",
+               "numa_node": numa}
+        os.sched_setaffinity(0, affinity0)
 
     # ---- secondary: single-step launches (state round-trips HBM every step) ----
     Ks = 16

@@ -1,6 +1,8 @@
 """Multi-GPU plumbing for the path: envs are independent units, so a job of
 `total_envs` shards by contiguous global env id ranges, one process per GPU, and NOTHING is
 exchanged on the step path.  torch.distributed is used only to agree on timing / totals."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -33,3 +35,29 @@ def aggregate_throughput(local_units, local_seconds, device="cpu", group=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     dist.all_reduce(u, op=dist.ReduceOp.SUM, group=group)
     return float(u.item()) / float(t.item()), float(u.item()), float(t.item())
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that host buffers pinned afterwards
+    (step_host) are allocated next to that GPU's PCIe root.  With one process per GPU this keeps the D2H streams of the
+    ranks from crossing the socket interconnect.  Best effort: returns the node number, or None if the topology cannot
+    be read (then nothing is changed)."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
