@@ -53,6 +53,7 @@ struct mgb_handle {
     int64_t launches = 0;
     // host pipeline (mgb_step_host)
     cudaStream_t pipe[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_ev[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
     uint8_t *d_actions = nullptr, *d_obs = nullptr, *d_done = nullptr, *d_dir = nullptr;
     double *d_reward = nullptr;
     // kernel timing
@@ -215,6 +216,7 @@ int mgb_destroy(mgb_handle *h) {
     cudaFree(h->state); cudaFree(h->tmpl); cudaFree(h->err); cudaFree(h->pool);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_dir); cudaFree(h->d_reward);
     for (auto &s : h->pipe) if (s) cudaStreamDestroy(s);
+    for (auto &e : h->pipe_ev) if (e) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -351,29 +353,38 @@ int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host,
     const int64_t N = h->n_envs;
     if (!h->pipe[0]) {
         for (auto &s : h->pipe) CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        for (auto &e : h->pipe_ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_OK(cudaMalloc(&h->d_actions, N));
         CUDA_OK(cudaMalloc(&h->d_obs, (size_t)N * h->obs_bytes));
         CUDA_OK(cudaMalloc(&h->d_reward, (size_t)N * 8));
         CUDA_OK(cudaMalloc(&h->d_done, N));
         CUDA_OK(cudaMalloc(&h->d_dir, N));
     }
-    // chunk the env range so that H2D, kernel and D2H of neighbouring chunks overlap
+    // Chunk the env range so that H2D, kernel and the D2H of the observations of neighbouring chunks overlap.  The
+    // copy engine pays a few microseconds per copy, so the chunks are few and the three small outputs (reward, done,
+    // direction: 10 bytes per env) leave in one copy each after the last kernel instead of one per chunk.
     const int32_t G = h->n_groups;
-    int32_t nchunks = G >= 12288 ? 12 : (G >= 1024 ? 6 : 1);
+    static const int forced = getenv("MGB_HOST_CHUNKS") ? atoi(getenv("MGB_HOST_CHUNKS")) : 0;      // experiments only
+    int32_t nchunks = forced > 0 ? forced : (G >= 4096 ? 4 : (G >= 1024 ? 2 : 1));
     const int32_t per = (G + nchunks - 1) / nchunks;
     CUDA_OK(cudaDeviceSynchronize());   // order against whatever the caller enqueued on other streams
+    int used = 0;
     for (int32_t c = 0, g0 = 0; g0 < G; ++c, g0 += per) {
         cudaStream_t s = h->pipe[c % HOST_PIPE_STREAMS];
+        used = std::max(used, c % HOST_PIPE_STREAMS + 1);
         const int32_t ng = std::min(per, G - g0);
         const int64_t e0 = (int64_t)g0 * 32, ne = std::min((int64_t)ng * 32, N - e0);
         CUDA_OK(cudaMemcpyAsync(h->d_actions + e0, actions_host + e0, ne, cudaMemcpyHostToDevice, s));
         if (launch(h, g0, ng, 1, 0, nullptr, h->d_actions, obs_host ? h->d_obs : nullptr, reward_host ? h->d_reward : nullptr,
                    done_host ? h->d_done : nullptr, dir_host ? h->d_dir : nullptr, N, s, false)) return -1;
+        CUDA_OK(cudaEventRecord(h->pipe_ev[c % HOST_PIPE_STREAMS], s));      // the last record per stream is the one waited on
         if (obs_host) CUDA_OK(cudaMemcpyAsync(obs_host + e0 * h->obs_bytes, h->d_obs + e0 * h->obs_bytes, (size_t)ne * h->obs_bytes, cudaMemcpyDeviceToHost, s));
-        if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host + e0, h->d_reward + e0, (size_t)ne * 8, cudaMemcpyDeviceToHost, s));
-        if (done_host) CUDA_OK(cudaMemcpyAsync(done_host + e0, h->d_done + e0, ne, cudaMemcpyDeviceToHost, s));
-        if (dir_host) CUDA_OK(cudaMemcpyAsync(dir_host + e0, h->d_dir + e0, ne, cudaMemcpyDeviceToHost, s));
     }
+    cudaStream_t tail = h->pipe[0];
+    for (int i = 1; i < used; ++i) CUDA_OK(cudaStreamWaitEvent(tail, h->pipe_ev[i], 0));
+    if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host, h->d_reward, (size_t)N * 8, cudaMemcpyDeviceToHost, tail));
+    if (done_host) CUDA_OK(cudaMemcpyAsync(done_host, h->d_done, N, cudaMemcpyDeviceToHost, tail));
+    if (dir_host) CUDA_OK(cudaMemcpyAsync(dir_host, h->d_dir, N, cudaMemcpyDeviceToHost, tail));
     for (auto &s : h->pipe) CUDA_OK(cudaStreamSynchronize(s));
     return 0;
 }
