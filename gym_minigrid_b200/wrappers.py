@@ -328,6 +328,10 @@ class _TakesOverAutoReset(Wrapper):
         self._autoreset = u.autoreset if autoreset is None else bool(autoreset)
         u.set_autoreset(False)
 
+    def rollout(self, *a, **kw):
+        raise NotImplementedError("%s does its bookkeeping between steps: call step(); rollout() of the wrapped env would "
+                                  "skip it (and no longer auto-resets)" % type(self).__name__)
+
     def _reset_done(self, obs, done):
         if not self._autoreset:
             return obs
