@@ -306,3 +306,29 @@ def test_cuda_matches_reference_boxed_obstacles(path):
             assert_same("%s@%d obstacles" % (tag, t), _np(s["obstacles"])[0], d["obstacles"][k, t])
         assert_same(tag + " grid1", _np(env.get_state(("grid",))["grid"])[0], d["grid1"][k])
         env.check_errors()
+
+
+@pytest.mark.parametrize("n", [1, 31, 32, 33, 65])
+def test_small_and_ragged_batches(n):
+    """edge sizes: a single env, one lane short of / exactly / one over a 32-env group; rollout == oracle, and the
+    unaligned / ragged store path (no bulk copy) is the one exercised.  An empty batch is refused with an error."""
+    from oracle.oracle import OracleVec
+    mgb = _mgb()
+    env_id = "MiniGrid-Dynamic-Obstacles-8x8-v0"
+    cfg = _oracle_cfg(env_id)
+    T = 40
+    actions = np.random.RandomState(n).randint(0, cfg["n_actions"], size=(T, n)).astype(np.uint8)
+    env = mgb.make(env_id, num_envs=n, seed=3, env_id_base=77)
+    orc = OracleVec(cfg, n, seed=3, env0=77, threads=1)
+    o0, d0 = orc.reset()
+    g0 = env.reset()
+    assert_same("obs0", _np(g0["image"]), o0)
+    o, r, dn, dr = env.rollout(torch.as_tensor(actions))
+    oo, orr, odn, odr = orc.rollout(actions)
+    assert_same("obs", _np(o), oo)
+    assert_same("done", _np(dn).astype(np.uint8), odn)
+    assert_same("dir", _np(dr), odr)
+    assert_same("reward bits", bits(_np(r)), bits(orr))
+    env.check_errors()
+    with pytest.raises(Exception):
+        mgb.make(env_id, num_envs=0)
