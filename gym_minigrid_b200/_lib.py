@@ -39,6 +39,7 @@ SIGNATURES = {
     "mgb_reset": (C.c_int, [_P, _P, _P, _P, _P]),
     "mgb_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "mgb_rollout": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
+    "mgb_rollout_random": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "mgb_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "mgb_set_state": (C.c_int, [_P, C.c_int64, C.c_int64] + [_P] * 8),
     "mgb_get_state": (C.c_int, [_P, C.c_int64, C.c_int64] + [_P] * 8),

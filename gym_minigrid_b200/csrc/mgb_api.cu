@@ -29,6 +29,15 @@ static int fail(const char *fmt, ...) {
 
 constexpr int HOST_PIPE_STREAMS = 3;
 
+static int elementwise_grid(int64_t total) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = (total + 255) / 256;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * 16));
+}
+
+
 struct mgb_handle {
     mgb_config cfg;
     DevCfg dc;
@@ -54,6 +63,9 @@ struct mgb_handle {
     // host pipeline (mgb_step_host)
     cudaStream_t pipe[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_ev[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
+    uint32_t policy_epoch = 0;               // number of random-policy rollouts so far (counter word of their action stream)
+    uint8_t *policy_scratch = nullptr;
+    size_t policy_scratch_bytes = 0;
     uint8_t *d_actions = nullptr, *d_obs = nullptr, *d_done = nullptr, *d_dir = nullptr;
     double *d_reward = nullptr;
     // kernel timing
@@ -214,6 +226,7 @@ int mgb_destroy(mgb_handle *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaFree(h->state); cudaFree(h->tmpl); cudaFree(h->err); cudaFree(h->pool);
+    cudaFree(h->policy_scratch);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_dir); cudaFree(h->d_reward);
     for (auto &s : h->pipe) if (s) cudaStreamDestroy(s);
     for (auto &e : h->pipe_ev) if (e) cudaEventDestroy(e);
@@ -346,6 +359,28 @@ int mgb_rollout(mgb_handle *h, int32_t T, const uint8_t *actions, uint8_t *obs, 
     return launch(h, 0, h->n_groups, T, 0, nullptr, actions, obs, reward, done, dir, h->n_envs, (cudaStream_t)stream, true);
 }
 
+int mgb_rollout_random(mgb_handle *h, int32_t T, uint8_t *actions_out, uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir, void *stream) {
+    if (!h) return fail("null handle");
+    if (T < 1) return fail("mgb_rollout_random: T must be >= 1");
+    CUDA_OK(cudaSetDevice(h->device));
+    uint8_t *acts = actions_out;
+    if (!acts) {                                             // nobody wants to see the actions: private scratch
+        const size_t need = (size_t)T * h->n_envs;
+        if (need > h->policy_scratch_bytes) {
+            CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+            cudaFree(h->policy_scratch); h->policy_scratch = nullptr; h->policy_scratch_bytes = 0;
+            CUDA_OK(cudaMalloc(&h->policy_scratch, need));
+            h->policy_scratch_bytes = need;
+        }
+        acts = h->policy_scratch;
+    }
+    k_policy_actions<<<elementwise_grid(h->n_envs * ((T + 3) / 4)), 256, 0, (cudaStream_t)stream>>>(acts, h->n_envs, T, h->seed, h->env_id_base,
+                                                                                           h->policy_epoch++, h->dc.n_actions);
+    CUDA_OK(cudaGetLastError());
+    h->launches++;
+    return launch(h, 0, h->n_groups, T, 0, nullptr, acts, obs, reward, done, dir, h->n_envs, (cudaStream_t)stream, true);
+}
+
 int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host, double *reward_host, uint8_t *done_host, uint8_t *dir_host) {
     if (!h) return fail("null handle");
     if (!actions_host) return fail("mgb_step_host: actions is NULL");
@@ -427,13 +462,6 @@ int mgb_full_obs(mgb_handle *h, uint8_t *out, void *stream) {
     return state_io(h, false, 1, 0, h ? h->n_envs : 0, out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
-static int elementwise_grid(int64_t total) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t want = (total + 255) / 256;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * 16));
-}
 
 int mgb_onehot(const uint8_t *cells, uint8_t *out, int64_t n_cells, const uint8_t *class_map, int32_t n_classes,
                int32_t n_colors, int32_t n_states, void *stream) {

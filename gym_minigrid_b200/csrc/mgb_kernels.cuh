@@ -1485,6 +1485,26 @@ __global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, cons
     }
 }
 
+// Uniform random policy (run_tests.py:43, benchmark.py:27-33: env.action_space.sample()) as a counter-based stream, so
+// that a rollout needs no action input from the host: action of step t of the `epoch`-th random rollout of this handle
+// for global env id g = mulhi32(Philox4x32-10(counter (t>>2, epoch, g lo, g hi), key (seed lo, seed hi ^ "ACT1"))[t&3],
+// n_actions).  Filled by its own small kernel into the [T][N] action array the rollout kernel then reads: the hot kernel
+// does not change.  One thread = one Philox block = 4 consecutive steps of one env.
+constexpr uint32_t ACTION_KEY = 0x41435431u;
+__global__ void k_policy_actions(uint8_t *__restrict__ actions, int64_t N, int T, uint64_t seed, int64_t env_id_base, uint32_t epoch,
+                                 int n_actions) {
+    const int64_t total = N * ((T + 3) / 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t blk = i / N, n = i - blk * N, gid = env_id_base + n;
+        uint32_t o[4];
+        philox4x32_10((uint32_t)blk, epoch, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32) ^ ACTION_KEY,
+                      o[0], o[1], o[2], o[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (blk * 4 + k < T) actions[(blk * 4 + k) * N + n] = (uint8_t)__umulhi(o[k], (uint32_t)n_actions);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // bookkeeping wrappers: DACWrapper, ActionBonus / StateBonus, AppendActionWrapper,
 // GoalPolicyWrapper (reference wrappers.py:35-154,418-526).  Small element-wise kernels on the outputs of a step.

@@ -220,6 +220,18 @@ class VecMiniGridEnv:
         _lib.check(self._L.mgb_rollout(self._h, T, _ptr(a), _ptr(obs), _ptr(reward), _ptr(done), _ptr(d), self._stream()))
         return obs, reward, done.view(torch.bool), d
 
+    def rollout_random(self, T, want_obs=True):
+        """T steps under the uniform random policy (the reference's `env.action_space.sample()` loop), drawn on the device
+        from a counter-based stream: no action input.  Returns (obs, reward, done, dir, actions) with actions uint8 [T,N]."""
+        T, N, V = int(T), self.num_envs, self.agent_view_size
+        obs = torch.empty((T, N, V, V, 3), dtype=torch.uint8, device=self.device) if want_obs else None
+        reward = torch.empty((T, N), dtype=torch.float64, device=self.device)
+        done = torch.empty((T, N), dtype=torch.uint8, device=self.device)
+        d = torch.empty((T, N), dtype=torch.uint8, device=self.device)
+        a = torch.empty((T, N), dtype=torch.uint8, device=self.device)
+        _lib.check(self._L.mgb_rollout_random(self._h, T, _ptr(a), _ptr(obs), _ptr(reward), _ptr(done), _ptr(d), self._stream()))
+        return obs, reward, done.view(torch.bool), d, a
+
     def step_host(self, actions_host):
         """End-to-end step with HOST buffers: actions (pinned uint8[N]) in, pinned numpy-viewable
         obs/reward/done/dir out; H2D + kernel + D2H are pipelined inside libmgb200 (mgb_step_host)."""

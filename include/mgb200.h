@@ -115,6 +115,14 @@ int mgb_step(mgb_handle *h, const uint8_t *actions, uint8_t *obs, double *reward
 int mgb_rollout(mgb_handle *h, int32_t T, const uint8_t *actions, uint8_t *obs, double *reward,
                 uint8_t *done, uint8_t *dir, void *stream);
 
+/* T steps under the uniform random policy of the reference's own drivers (`env.action_space.sample()`, run_tests.py:43,
+ * benchmark.py:27-33), drawn on the device from a counter-based stream -- no action input from the host: the action of
+ * step t of the e-th call of this function on this handle, for global env id g, is
+ *   mulhi32(Philox4x32-10(counter (t>>2, e, g lo, g hi), key (seed lo, seed hi ^ 0x41435431))[t&3], n_actions).
+ * actions_out [T][N] (or NULL) receives the actions taken; everything else as mgb_rollout. */
+int mgb_rollout_random(mgb_handle *h, int32_t T, uint8_t *actions_out, uint8_t *obs, double *reward, uint8_t *done,
+                       uint8_t *dir, void *stream);
+
 /* One step with HOST buffers (pinned memory recommended): H2D of actions, the step kernel and
  * D2H of obs/reward/done/dir are pipelined over internal streams in env chunks.  Synchronous:
  * returns when the outputs are in host memory.  This is the end-to-end path a CPU-side caller

@@ -231,6 +231,7 @@ typedef struct {
 struct orc_vec {
     orc_config cfg;
     int n;
+    uint32_t policy_epoch;   /* number of random-policy rollouts so far */
     Env *envs;
     Obj *cells;
     int pool_n;          /* ORC_GEN_POOL */
@@ -815,6 +816,18 @@ int orc_vec_reset(orc_vec *v, const uint8_t *mask, uint8_t *obs, uint8_t *dir) {
     return 0;
 }
 
+/* The uniform random policy of run_tests.py:43 / benchmark.py (`env.action_space.sample()`), as a counter-based stream
+ * so that the device can draw the same actions without a host round trip: action of step t of the `epoch`-th random
+ * rollout of a vector, for env id g = mulhi32(Philox4x32-10(ctr = (t>>2, epoch, g), key = (seed lo, seed hi ^ ORC_ACTION_KEY))[t&3],
+ * n_actions).  The key differs from the env's own stream, so the policy never correlates with the layout draws. */
+int orc_policy_action(uint64_t seed, int64_t env_id, uint32_t epoch, uint32_t t, int n_actions) {
+    uint32_t ctr[4] = { t >> 2, epoch, (uint32_t)env_id, (uint32_t)((uint64_t)env_id >> 32) };
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) ^ ORC_ACTION_KEY };
+    uint32_t out[4];
+    orc_philox4x32_10(ctr, key, out);
+    return (int)(((uint64_t)out[t & 3] * (uint32_t)n_actions) >> 32);
+}
+
 typedef struct { orc_vec *v; int T; const uint8_t *actions; int autoreset;
                  uint8_t *obs; double *reward; uint8_t *done; uint8_t *dir; } RollCtx;
 static int rollout_range(void *p, int lo, int hi) {
@@ -846,10 +859,21 @@ static int rollout_range(void *p, int lo, int hi) {
 }
 int orc_vec_rollout(orc_vec *v, int32_t T, const uint8_t *actions, int autoreset,
                     uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir) {
+    if (!actions) { snprintf(g_err, sizeof g_err, "orc_vec_rollout: actions is NULL"); return -1; }
     RollCtx c = { v, T, actions, autoreset, obs, reward, done, dir };
     int bad = parallel_for(v->n, rollout_range, &c);
     if (bad) { snprintf(g_err, sizeof g_err, "orc_vec_rollout: error flags 0x%x (1=unknown action, 2=tape exhausted, 4=tape value out of range, 8=rejection sampling failed, 16=grid index out of bounds)", bad); return -1; }
     return 0;
+}
+
+int orc_vec_rollout_random(orc_vec *v, int32_t T, int autoreset, uint8_t *actions_out,
+                           uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir) {
+    if (!actions_out) { snprintf(g_err, sizeof g_err, "orc_vec_rollout_random: actions_out is NULL"); return -1; }
+    for (int t = 0; t < T; t++)
+        for (int i = 0; i < v->n; i++)
+            actions_out[(size_t)t * v->n + i] = (uint8_t)orc_policy_action(v->envs[i].seed, v->envs[i].env_id, v->policy_epoch, (uint32_t)t, v->cfg.n_actions);
+    v->policy_epoch++;
+    return orc_vec_rollout(v, T, actions_out, autoreset, obs, reward, done, dir);
 }
 
 int orc_vec_step(orc_vec *v, const uint8_t *actions, int autoreset,

@@ -79,6 +79,11 @@ int orc_vec_step(orc_vec *v, const uint8_t *actions, int autoreset,
                  uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir);
 
 /* T steps; actions [T][n]; outputs [T][n]...; any output may be NULL */
+#define ORC_ACTION_KEY 0x41435431u   /* "ACT1": key tweak of the random-policy stream */
+int orc_policy_action(uint64_t seed, int64_t env_id, uint32_t epoch, uint32_t t, int n_actions);
+/* T steps under the uniform random policy (run_tests.py:43); the actions taken are written to actions_out [T][n] */
+int orc_vec_rollout_random(orc_vec *v, int32_t T, int autoreset, uint8_t *actions_out,
+                           uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir);
 int orc_vec_rollout(orc_vec *v, int32_t T, const uint8_t *actions, int autoreset,
                     uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir);
 

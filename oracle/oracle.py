@@ -49,6 +49,8 @@ def lib():
         L.orc_vec_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 3
         L.orc_vec_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.orc_vec_rollout.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.orc_vec_rollout_random.argtypes = [C.c_void_p, C.c_int32, C.c_int] + [C.c_void_p] * 5
+        L.orc_policy_action.argtypes = [C.c_uint64, C.c_int64, C.c_uint32, C.c_uint32, C.c_int]
         L.orc_vec_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 7
         L.orc_vec_set_state.argtypes = [C.c_void_p] + [C.c_void_p] * 7
         L.orc_philox4x32_10.argtypes = [C.c_void_p] * 3
@@ -136,6 +138,16 @@ class OracleVec:
         d = np.zeros((T, self.n), np.uint8)
         self._chk(self._L.orc_vec_rollout(self._h, T, _p(a), int(autoreset), _p(obs), _p(r), _p(dn), _p(d)))
         return obs, r, dn, d
+
+    def rollout_random(self, T, autoreset=True, want_obs=True):
+        """T steps under the counter-based uniform random policy; returns (obs, reward, done, dir, actions)"""
+        obs = np.zeros((T, self.n, self.V, self.V, 3), np.uint8) if want_obs else None
+        r = np.zeros((T, self.n), np.float64)
+        dn = np.zeros((T, self.n), np.uint8)
+        d = np.zeros((T, self.n), np.uint8)
+        a = np.zeros((T, self.n), np.uint8)
+        self._chk(self._L.orc_vec_rollout_random(self._h, T, int(autoreset), _p(a), _p(obs), _p(r), _p(dn), _p(d)))
+        return obs, r, dn, d, a
 
     def get_state(self):
         n, W, H = self.n, self.W, self.H

@@ -332,3 +332,29 @@ def test_small_and_ragged_batches(n):
     env.check_errors()
     with pytest.raises(Exception):
         mgb.make(env_id, num_envs=0)
+
+
+@pytest.mark.parametrize("env_id", ["MiniGrid-Empty-8x8-v0", "MiniGrid-Dynamic-Obstacles-16x16-v0", "MiniGrid-DoorKey-16x16-v0"])
+def test_random_policy_rollout_matches_oracle(env_id):
+    """mgb_rollout_random: the uniform random policy drawn on the device (no action input) -- actions and everything
+    downstream equal the oracle's; at 2^20 envs the action histogram is uniform to 0.5 %."""
+    from oracle.oracle import OracleVec
+    mgb = _mgb()
+    cfg = _oracle_cfg(env_id)
+    N, T = 2048 + 17, 48
+    env = mgb.make(env_id, num_envs=N, seed=21, env_id_base=123456789012)
+    orc = OracleVec(cfg, N, seed=21, env0=123456789012)
+    env.reset(); orc.reset()
+    o, r, dn, dr, a = env.rollout_random(T)
+    oo, orr, odn, odr, oa = orc.rollout_random(T)
+    assert_same("actions", _np(a), oa)
+    assert_same("obs", _np(o), oo)
+    assert_same("done", _np(dn).astype(np.uint8), odn)
+    assert_same("dir", _np(dr), odr)
+    assert_same("reward bits", bits(_np(r)), bits(orr))
+    env.check_errors()
+    big = mgb.make(env_id, num_envs=1 << 20, seed=1)
+    big.reset()
+    _, _, _, _, a = big.rollout_random(8, want_obs=False)
+    h = torch.bincount(a.flatten().long(), minlength=cfg["n_actions"]).double()
+    assert h.numel() == cfg["n_actions"] and float((h / h.sum() - 1.0 / cfg["n_actions"]).abs().max()) < 0.005 / cfg["n_actions"] * cfg["n_actions"]
