@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--rollout-T", type=int, default=32, help="env-steps per launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short per-GPU runs of the other BASELINE configs")
     ap.add_argument("--cpu-sample-envs", type=int, default=1 << 14)
     ap.add_argument("--cpu-sample-T", type=int, default=64)
     return ap.parse_args()
@@ -149,6 +150,11 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+OTHER_CONFIGS_OF = "MiniGrid-Empty-8x8-v0"          # the config the metric is quoted on (BASELINE.json north_star)
+OTHER_CONFIGS = ["MiniGrid-DoorKey-16x16-v0", "MiniGrid-FourRooms-v0", "MiniGrid-Dynamic-Obstacles-16x16-v0",
+                 "MiniGrid-KeyCorridorS6R3-v0"]
 
 
 def main():
@@ -275,6 +281,29 @@ def main():
     barrier()
     step_mode = N * Ks / (s0.elapsed_time(s1) * 1e-3)
 
+    # ---- secondary: the other BASELINE.json configs on the same kernel family, per GPU (short: 3 warm-up + 5 launches each) ----
+    others = None
+    if not args.no_other_configs and args.env_id == OTHER_CONFIGS_OF:
+        others = {}
+        del env
+        for oid in OTHER_CONFIGS:
+            ocfg = mgb.spec(oid)["config"]
+            oenv = mgb.make(oid, num_envs=N, device=dev, seed=0, env_id_base=rank * N)
+            oenv.reset()
+            oa = torch.randint(0, ocfg["n_actions"], (T, N), dtype=torch.uint8, device=dev, generator=g)
+            for _ in range(3):
+                oenv.rollout(oa, out=out)
+            barrier()
+            s0.record()
+            for _ in range(5):
+                oenv.rollout(oa, out=out)
+            s1.record()
+            barrier()
+            ov = N * T * 5 / (s0.elapsed_time(s1) * 1e-3)
+            oenv.check_errors()
+            others[oid] = {"env_steps_per_s_per_gpu": ov, "roofline_frac": ov * ALGO_BYTES_PER_STEP / 1e9 / peak}
+            del oenv
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, times, cores = cpu_leg(args.env_id, args.cpu_sample_envs, args.cpu_sample_T, 3)
@@ -292,7 +321,7 @@ def main():
                        "l2": "outputs per launch (%.1f GB) exceed L2; no flush needed" % (N * T * 157 / 1e9),
                        "parallelism": "env shards by global env id, no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "step_mode_env_steps_per_s_per_gpu": step_mode,
+            "step_mode_env_steps_per_s_per_gpu": step_mode, "other_configs_per_gpu": others,
         }))
     if world > 1:
         dist.destroy_process_group()
