@@ -560,7 +560,7 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
 }
 
 // Warp-cooperative DynamicObstaclesEnv._gen_grid (envs/dynamicobstacles.py:35-58) for the env in column `src` of
-// the warp's state block -- the fixed-start variant: agent at (1,1) facing right, then n_obstacles times
+// the warp's state block: agent at (1,1) facing right (or place_agent() for the -Random- ids), then n_obstacles times
 // place_obj(Ball(), max_tries=100) over the whole grid.  With a uniform random policy an episode lasts ~12 steps, so
 // nearly every warp-step has a lane or two that must reset; doing that inside one lane stalls the other 30.  Here
 // lane t evaluates try t of the new episode's stream (draws 2t, 2t+1: half of Philox block t>>1).  place_obj accepts
@@ -571,7 +571,7 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
 // Returns false (nothing but the removal of the old balls done) if 32 tries were not enough; the caller then runs the
 // scalar generator, which replays the same stream from its start.
 __device__ __forceinline__ bool dynobs_coop_reset(uint32_t *st_warp, int src, int lane, const RolloutParams &p, int64_t gid,
-                                                  uint32_t stream, uint32_t &consumed) {
+                                                  uint32_t stream, uint32_t &consumed, uint32_t &agent) {
     const DevCfg &c = p.cfg;
     const int HP = c.HP, nob = c.n_obst;
     const uint32_t col_sa = (uint32_t)__cvta_generic_to_shared(st_warp + src);
@@ -584,17 +584,37 @@ __device__ __forceinline__ bool dynobs_coop_reset(uint32_t *st_warp, int src, in
     uint32_t o0, o1, o2, o3;
     philox4x32_10((uint32_t)(lane >> 1), stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32),
                   o0, o1, o2, o3);
-    const int x = (int)__umulhi((lane & 1) ? o2 : o0, (uint32_t)c.W), y = (int)__umulhi((lane & 1) ? o3 : o1, (uint32_t)c.H);
-    const int i = x * HP + y;
-    const bool is_free = ((__ldg(&p.tmpl[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) == CODE_EMPTY && !(x == 1 && y == 1);
-    const uint32_t pos = (uint32_t)(x | (y << 8));
+    const uint32_t ux = (lane & 1) ? o2 : o0, uy = (lane & 1) ? o3 : o1;          // draws 2*lane, 2*lane+1
+    auto static_free = [&](int x, int y) { const int i = x * HP + y; return ((__ldg(&p.tmpl[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) == CODE_EMPTY; };
     const uint32_t lt = (1u << lane) - 1u;
-    const bool first = (__match_any_sync(0xFFFFFFFFu, pos) & lt) == 0;
+    int x = (int)__umulhi(ux, (uint32_t)c.W), y = (int)__umulhi(uy, (uint32_t)c.H);
+    uint32_t eligible = 0xFFFFFFFFu;                              // lanes whose try is a ball try
+    uint32_t extra = 0;                                           // draws before ball try 0
+    agent = 1u | (1u << 8);                                       // fixed start: (1,1) facing right (dynamicobstacles.py:44-47)
+    if (c.random_start) {
+        // place_agent() (minigrid.py:1072-1090): tries on the pairs (2t, 2t+1) until the cell is empty in the static
+        // layout (agent_pos is None meanwhile), then one draw for the direction; the ball tries that follow are the
+        // odd-aligned pairs (2m+1, 2m+2), m > t_agent: lane m's second draw and lane m+1's first.
+        const uint32_t afree = __ballot_sync(0xFFFFFFFFu, static_free(x, y));
+        if (afree == 0 || (afree & 0x3FFFFFFFu) == 0) return false;           // needs the direction draw and room for balls
+        const int ta = __ffs((int)afree) - 1;
+        const uint32_t apos = __shfl_sync(0xFFFFFFFFu, (uint32_t)(x | (y << 8)), ta);
+        const uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, ux, 1);             // draw 2*lane+2
+        const uint32_t adir = __umulhi(__shfl_sync(0xFFFFFFFFu, nxt, ta), 4u);  // draw 2*ta+2
+        agent = apos | (adir << 16);
+        x = (int)__umulhi(uy, (uint32_t)c.W); y = (int)__umulhi(nxt, (uint32_t)c.H);
+        eligible = (ta >= 30) ? 0u : ((0xFFFFFFFFu << (ta + 1)) & 0x7FFFFFFFu);  // lane 31 has no draw 64
+        extra = 1;
+    }
+    const uint32_t pos = (uint32_t)(x | (y << 8));
+    const bool is_free = static_free(x, y) && pos != (agent & 0xFFFFu) && ((eligible >> lane) & 1u);
+    const bool first = (__match_any_sync(0xFFFFFFFFu, pos) & lt & eligible) == 0;
     const uint32_t acc = __ballot_sync(0xFFFFFFFFu, is_free && first);
     if (__popc(acc) < nob) return false;
     const int rank = __popc(acc & lt);
     const bool mine = ((acc >> lane) & 1u) && rank < nob;
-    consumed = 2u * (uint32_t)__ffs((int)__ballot_sync(0xFFFFFFFFu, mine && rank == nob - 1));   // draws up to the last ball's try
+    // draws up to and including the last ball's try: pairs (2m, 2m+1), or (2m+1, 2m+2) after a random start
+    consumed = 2u * (uint32_t)__ffs((int)__ballot_sync(0xFFFFFFFFu, mine && rank == nob - 1)) + extra;
     if (mine) {
         sts_u8(col_sa + cell_off(x, y, HP), (uint32_t)code_of(T_BALL, C_BLUE, 0));
         sts_u16(ob_sa + (uint32_t)((rank >> 1) * 128 + (rank & 1) * 2), pos);
@@ -1112,14 +1132,15 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
                     need_reset = done && p.autoreset;
                 }
                 if (GEN == GEN_DYNOBS) {                        // frequent resets: regenerate finished envs with the whole warp
-                    uint32_t rm = __ballot_sync(0xFFFFFFFFu, need_reset && !p.tape && !p.cfg.random_start && (e.flags & 1));
+                    uint32_t rm = __ballot_sync(0xFFFFFFFFu, need_reset && !p.tape && (e.flags & 1));
                     while (rm) {
                         const int src = __ffs((int)rm) - 1;
                         rm &= rm - 1;
-                        uint32_t consumed = 0;
+                        uint32_t consumed = 0, agent = 0;
                         const uint32_t stream = __shfl_sync(0xFFFFFFFFu, rg.episode, src);
-                        if (dynobs_coop_reset(st_warp, src, lane, p, p.env_id_base + (int64_t)group * 32 + src, stream, consumed) && lane == src) {
-                            e.ax = 1; e.ay = 1; e.dir = 0; e.carry = 0; e.steps = 0; e.target = 0; e.dirty = true;
+                        if (dynobs_coop_reset(st_warp, src, lane, p, p.env_id_base + (int64_t)group * 32 + src, stream, consumed, agent) && lane == src) {
+                            e.ax = (int)(agent & 0xFF); e.ay = (int)((agent >> 8) & 0xFF); e.dir = (int)(agent >> 16);
+                            e.carry = 0; e.steps = 0; e.target = 0; e.dirty = true;
                             rg.episode++; rg.ndraws = consumed; rg.rblk = 0xFFFFFFFFu;
                             need_reset = false;
                         }
