@@ -138,3 +138,19 @@ def test_two_rank_gloo_aggregation():
     assert (b0, c0, b1, c1) == (0, 501, 501, 500)
     assert u0 == u1 == 10010.0 and s0 == s1 == 2.0      # sum of units, MAX of time
     assert v0 == v1 == 10010.0 / 2.0
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/mgb200.h is the drop-in boundary: it must compile as C (no C++, no torch/CUDA types in the signatures)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "consumer.c"
+    src.write_text('#include "mgb200.h"\n'
+                   'int use(void) { mgb_config c = {0}; mgb_handle *h = 0; c.gen = MGB_GEN_EMPTY;\n'
+                   '  return mgb_create(&c, 1, 0, 0, 0, &h) + mgb_step(h, 0, 0, 0, 0, 0, 0) + (int)mgb_num_envs(h); }\n')
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
