@@ -56,6 +56,7 @@ SIGNATURES = {
     "mgb_dac": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mgb_append_action": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "mgb_goal_policy": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "mgb_episode_stats": (C.c_int, [C.c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mgb_error_flags": (C.c_int, [_P, _P, C.POINTER(C.c_uint32)]),
     "mgb_kernel_launches": (C.c_int64, [_P]),
     "mgb_set_kernel_timing": (C.c_int, [_P, C.c_int]),

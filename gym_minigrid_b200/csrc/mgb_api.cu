@@ -568,6 +568,17 @@ int mgb_goal_policy(int64_t n_cells, int32_t planes, int32_t agent_idx, int32_t 
     return 0;
 }
 
+int mgb_episode_stats(int64_t N, const double *reward, const uint8_t *done, double *run_ret, int32_t *run_len, double *out_ret,
+                      int32_t *out_len, uint64_t *totals, void *stream) {
+    if (!reward || !done || !run_ret || !run_len || !out_ret || !out_len) return fail("mgb_episode_stats: null buffer");
+    if (N < 0) return fail("mgb_episode_stats: bad size");
+    if (N == 0) return 0;
+    k_episode_stats<<<elementwise_grid(N), 256, 0, (cudaStream_t)stream>>>(N, reward, done, run_ret, run_len, out_ret, out_len,
+                                                                        reinterpret_cast<unsigned long long *>(totals));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int mgb_error_flags(mgb_handle *h, void *stream, uint32_t *flags_host) {
     if (!h || !flags_host) return fail("null argument");
     CUDA_OK(cudaSetDevice(h->device));

@@ -1634,4 +1634,27 @@ __global__ void k_goal_policy(int64_t n_cells, int planes, int agent_idx, int em
     }
 }
 
+// Episode bookkeeping (SURVEY §5 "metrics": the reference only prints): running return and length per env; at a done
+// step the finished episode's totals go to out_ret / out_len (elsewhere 0) and the running values restart.
+__global__ void k_episode_stats(int64_t N, const double *__restrict__ reward, const uint8_t *__restrict__ done, double *__restrict__ run_ret,
+                                int32_t *__restrict__ run_len, double *__restrict__ out_ret, int32_t *__restrict__ out_len,
+                                unsigned long long *__restrict__ totals) {
+    unsigned long long episodes = 0, steps = 0;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const double r = run_ret[n] + reward[n];
+        const int32_t l = run_len[n] + 1;
+        const bool d = done[n] != 0;
+        out_ret[n] = d ? r : 0.0;
+        out_len[n] = d ? l : 0;
+        run_ret[n] = d ? 0.0 : r;
+        run_len[n] = d ? 0 : l;
+        if (d) { episodes++; steps += (unsigned long long)l; }
+    }
+    if (totals) {                                               // [0] finished episodes, [1] their summed length
+        episodes = __reduce_add_sync(0xFFFFFFFFu, (unsigned)episodes);
+        steps = __reduce_add_sync(0xFFFFFFFFu, (unsigned)steps);
+        if ((threadIdx.x & 31) == 0 && episodes) { atomicAdd(&totals[0], episodes); atomicAdd(&totals[1], steps); }
+    }
+}
+
 }  // namespace mgb

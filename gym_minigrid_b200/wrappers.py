@@ -507,3 +507,40 @@ class GoalPolicyWrapper(Wrapper):
     def step(self, action):
         obs, reward, done, info = self.env.step(action)
         return self._pack(obs), reward, done, info
+
+
+class EpisodeStatistics(Wrapper):
+    """Not a reference class (the reference only prints; SURVEY §5 "metrics"): running return and length per env on the
+    device.  After every step info['episode'] = {'r': float64 [N], 'l': int32 [N]} holds the totals of the episodes that
+    just ended (0 elsewhere, use `done` as the mask); `episodes` / `mean_length()` give batch totals without a host loop."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        u = self.unwrapped
+        N, dev = u.num_envs, u.device
+        self._ret = torch.zeros(N, dtype=torch.float64, device=dev)
+        self._len = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._out_ret = torch.zeros(N, dtype=torch.float64, device=dev)
+        self._out_len = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._totals = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def reset(self, **kw):
+        self._ret.zero_(); self._len.zero_()
+        return self.env.reset(**kw)
+
+    def step(self, action):
+        obs, reward, done, info = self.env.step(action)
+        u = self.unwrapped
+        _lib.check(u._L.mgb_episode_stats(u.num_envs, _ptr(reward), _ptr(done.view(torch.uint8)), _ptr(self._ret), _ptr(self._len),
+                                          _ptr(self._out_ret), _ptr(self._out_len), _ptr(self._totals), u._stream()))
+        info = dict(info)
+        info['episode'] = {'r': self._out_ret, 'l': self._out_len}
+        return obs, reward, done, info
+
+    @property
+    def episodes(self):
+        return int(self._totals[0])
+
+    def mean_length(self):
+        t = self._totals.tolist()
+        return t[1] / t[0] if t[0] else float('nan')

@@ -220,6 +220,13 @@ int mgb_dac(mgb_handle *h, int32_t count_ge_max, const uint8_t *done_in, const u
 int mgb_append_action(int64_t N, int32_t D, int32_t A, int32_t K, const uint8_t *obs, const uint8_t *actions,
                       const uint8_t *done, uint8_t *hist, uint8_t *out, void *stream);
 
+/* Episode statistics (not in the reference, which only prints): run_ret / run_len [N] are the caller-owned
+ * running return and length (zero-initialised); after a step, out_ret / out_len [N] hold the totals of the episodes that
+ * ended at this step (0 elsewhere) and the running values of those envs restart.  totals (or NULL): uint64 [2] device
+ * counters, += number of finished episodes and += their summed length. */
+int mgb_episode_stats(int64_t N, const double *reward, const uint8_t *done, double *run_ret, int32_t *run_len,
+                      double *out_ret, int32_t *out_len, uint64_t *totals, void *stream);
+
 /* GoalPolicyWrapper._get_goals (wrappers.py:476-497): obs [n_cells][planes] one-hot rows of FullyObsOneHotWrapper ->
  * achieved (goal plane cleared) and desired (agent cell -> empty, goal cell -> agent). */
 int mgb_goal_policy(int64_t n_cells, int32_t planes, int32_t agent_idx, int32_t empty_idx, int32_t goal_idx,

@@ -166,3 +166,24 @@ def test_terminal_observation_wrapper():
         assert torch.equal(term["image"], t_obs["image"]) and torch.equal(term["direction"], t_obs["direction"])
         seen += int(w_d.sum())
     assert seen > 100
+
+
+def test_episode_statistics_wrapper():
+    """EpisodeStatistics: totals at done steps equal a host-side accumulation of the same rewards."""
+    import gym_minigrid_b200 as mgb
+    from gym_minigrid_b200 import wrappers as W
+    N, T = 5000, 80
+    w = W.EpisodeStatistics(mgb.make("MiniGrid-Dynamic-Obstacles-6x6-v0", num_envs=N, seed=4))
+    w.reset()
+    g = torch.Generator().manual_seed(5)
+    ret, ln = np.zeros(N), np.zeros(N, np.int64)
+    eps = steps = 0
+    for t in range(T):
+        _, r, d, info = w.step(torch.randint(0, 3, (N,), dtype=torch.uint8, generator=g))
+        r, d = r.cpu().numpy(), d.cpu().numpy()
+        ret += r; ln += 1
+        assert np.array_equal(info['episode']['r'].cpu().numpy(), np.where(d, ret, 0.0))
+        assert np.array_equal(info['episode']['l'].cpu().numpy(), np.where(d, ln, 0))
+        eps += int(d.sum()); steps += int(ln[d].sum())
+        ret[d] = 0; ln[d] = 0
+    assert w.episodes == eps and eps > 1000 and abs(w.mean_length() - steps / eps) < 1e-12
