@@ -559,6 +559,31 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
     rg.ndraws = nd;
 }
 
+// The same update driven by the RNG tape (parity against the reference's own MT19937 draws): for each ball in list
+// order, place_obj(top=old-(1,1), size=(3,3), max_tries=100), then clear the old cell; a failed placement
+// (RecursionError, swallowed) leaves the ball where it is.  Cold path, out of line.
+__device__ __noinline__ void dynobs_move_tape(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p) {
+    const DevCfg &c = p.cfg;
+    const int W = c.W, H = c.H, HP = c.HP;
+    for (int k = 0; k < c.n_obst; ++k) {
+        int ox, oy;
+        obst_get(st, c, k, ox, oy);
+        const uint32_t ball = cell_rd(st, ox * HP + oy);
+        const int tx = max(ox - 1, 0), ty = max(oy - 1, 0), hx = min(tx + 3, W), hy = min(ty + 3, H);
+        for (int tries = 0; tries <= 100; ++tries) {              // 101 tries (minigrid.py:1028-1031)
+            const int x = rand_int_inl(rg, p, tx, hx);
+            const int y = rand_int_inl(rg, p, ty, hy);
+            if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) return;
+            if (cell_rd(st, x * HP + y) != CODE_EMPTY) continue;  // the ball's own cell counts: it must move
+            if (x == e.ax && y == e.ay) continue;
+            cell_wr(st, x * HP + y, ball);
+            obst_set(st, c, k, x, y);
+            cell_wr(st, ox * HP + oy, CODE_EMPTY);
+            break;
+        }
+    }
+}
+
 // Warp-cooperative DynamicObstaclesEnv._gen_grid (envs/dynamicobstacles.py:35-58) for the env in column `src` of
 // the warp's state block: agent at (1,1) facing right (or place_agent() for the -Random- ids), then n_obstacles times
 // place_obj(Ball(), max_tries=100) over the whole grid.  With a uniform random policy an episode lasts ~12 steps, so
@@ -643,53 +668,9 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         uint32_t front = CODE_WALL;
         if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(st, fx0 * HP + fy0);
         not_clear = front != CODE_EMPTY && (lut[front * lut_pitch<SEE>() + lut_fw<SEE>()] & 0xFF) != T_GOAL;
-        // Update obstacle positions: for each ball in list order, place_obj(top=old-(1,1), size=(3,3),
-        // max_tries=100) then clear the old cell; a failed placement (RecursionError, swallowed) leaves
-        // the ball where it is.  One loop iteration = one try of whichever ball the lane is on, so a
-        // warp runs max-over-lanes(total tries) iterations instead of sum-over-balls(max-over-lanes).
+        // Update obstacle positions (dynamicobstacles.py:70-78)
         if (!p.tape) dynobs_move<V>(st, e, rg, p, draws);
-        else {
-            int k = 0, tries = 0, ox = 0, oy = 0, tx = 0, ty = 0, hx = 0, hy = 0;
-            uint32_t ball = 0;
-            const int nob = c.n_obst;
-            uint32_t wbase = 0;                                        // draw index of draws[0]
-            if (!p.tape) {
-                wbase = rg.ndraws & ~3u;
-                prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
-                rg.rblk = 0xFFFFFFFFu;
-            }
-            while (k < nob) {
-                if (tries == 0) {
-                    obst_get(st, c, k, ox, oy);
-                    ball = cell_rd(st, ox * HP + oy);
-                    tx = max(ox - 1, 0); ty = max(oy - 1, 0);
-                    hx = min(tx + 3, W); hy = min(ty + 3, H);
-                }
-                if (tries > 100) { k++; tries = 0; continue; }
-                tries++;
-                int x, y;
-                if (p.tape) {
-                    x = rand_int_inl(rg, p, tx, hx);
-                    y = rand_int_inl(rg, p, ty, hy);
-                    if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) break;
-                } else {
-                    if (rg.ndraws - wbase + 2 > 4 * draw_blocks(V)) {  // window exhausted (rare): slide it
-                        wbase = rg.ndraws & ~3u;
-                        prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
-                    }
-                    const uint32_t i = rg.ndraws - wbase;
-                    x = tx + (int)__umulhi(draws[i * 32], (uint32_t)(hx - tx));
-                    y = ty + (int)__umulhi(draws[(i + 1) * 32], (uint32_t)(hy - ty));
-                    rg.ndraws += 2;
-                }
-                if (cell_rd(st, x * HP + y) != CODE_EMPTY) continue;      // the ball's own cell counts: it must move
-                if (x == e.ax && y == e.ay) continue;
-                cell_wr(st, x * HP + y, ball);
-                obst_set(st, c, k, x, y);
-                cell_wr(st, ox * HP + oy, CODE_EMPTY);
-                k++; tries = 0;
-            }
-        }
+        else { Env te = e; Rng tr = rg; dynobs_move_tape(st, te, tr, p); e = te; rg = tr; }     // parity-only mode, out of line
     } else if (action >= c.n_actions) {
         rg.err |= ERR_ACTION;                             // reference: assert False, "unknown action"
         action = A_DONE;
