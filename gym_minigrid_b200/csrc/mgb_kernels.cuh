@@ -42,7 +42,8 @@ __host__ __device__ constexpr int obs_bytes(int V) { return 3 * V * V; }
 constexpr int STAGE_SEG_WORDS = 12;                      // extra word offset per segment
 __host__ __device__ constexpr int stage_nseg(int V) { return (MGB_STAGE_SEG && V == 7) ? 6 : 1; }
 __host__ __device__ constexpr int stage_seg_lane(int V, int k) { return stage_nseg(V) == 1 ? (k == 0 ? 0 : GROUP) : (16 * k + 2) / 3; }   // 0,6,11,16,22,27,32
-__host__ __device__ constexpr int stage_bytes(int V) { return GROUP * 3 * V * V + (stage_nseg(V) - 1) * STAGE_SEG_WORDS * 4; }      // multiple of 16 for every V
+// multiple of 16 for every V; at least 1024: the block also parks 32 rows x 32 bytes of actions between two observations
+__host__ __device__ constexpr int stage_bytes(int V) { return GROUP * 3 * V * V + (stage_nseg(V) - 1) * STAGE_SEG_WORDS * 4 < 1024 ? 1024 : GROUP * 3 * V * V + (stage_nseg(V) - 1) * STAGE_SEG_WORDS * 4; }
 constexpr int MAX_WARPS_PER_BLOCK = 8;           // the host picks 2..8 warps per CTA to maximise resident warps/SM
 #ifndef MGB_SEE_MIN_BLOCKS
 #define MGB_SEE_MIN_BLOCKS 0     // experiment: >0 adds minBlocksPerSM to the see-through kernels' launch bounds (register cap)
@@ -67,6 +68,24 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #ifndef MGB_SEE_BATCH
 #define MGB_SEE_BATCH 1       // see-through path: groups of 4 cells whose loads are issued back to back
 #endif
+#ifndef MGB_BULK_STATE
+#define MGB_BULK_STATE 1       // state block HBM -> shared memory with one cp.async.bulk per group instead of an LDG/STS loop
+#endif
+#ifndef MGB_PREFETCH_ACTIONS
+#define MGB_PREFETCH_ACTIONS 0 // rollouts: pull the group's T x 32 action bytes into L2 (evict_last) at group start
+#endif
+#ifndef MGB_PACKED_ACTIONS
+#define MGB_PACKED_ACTIONS 1   // rollouts: 32 steps of actions per lane fetched at once and held as 4-bit fields in 4 registers (1: occluded kernels, 2: all)
+#endif
+#ifndef MGB_PREFETCH_DIST
+#define MGB_PREFETCH_DIST 3
+#endif
+#ifndef MGB_LATE_PREFETCH
+#define MGB_LATE_PREFETCH 0    // request the next action after the transition instead of before it (see k_rollout)
+#endif
+#ifndef MGB_OCC_REGS
+#define MGB_OCC_REGS 1         // occluded path: 1 = cells held in registers, flood, then streaming pack (see observe); 0 = 38-word accumulator; 2,3 = single-word LUT experiments
+#endif
 #ifndef MGB_PACK_IMAD_OCC
 #define MGB_PACK_IMAD_OCC 0    // occluded path: predicated IMAD accumulation instead of LOP3+SEL+PRMT (measured slower: 157 regs)
 #endif
@@ -79,7 +98,8 @@ template <bool SEE> __host__ __device__ constexpr int lut_fw() { return SEE ? 1 
 template <bool SEE> __host__ __device__ constexpr int lut_bytes() { return 256 * lut_pitch<SEE>() * 4; }    // 3072 / 6144
 constexpr int AXIS_ENTRIES = 88;                                 // v in [-(V-1), 64+V-2] for V <= 11: index v + AXIS_BIAS
 constexpr int AXIS_BIAS = 10;
-template <bool SEE> __host__ __device__ constexpr int table_bytes() { return (lut_bytes<SEE>() + 2 * AXIS_ENTRIES * 4 + 127) / 128 * 128; }   // 3840 / 6912
+constexpr int MBAR_BYTES = MAX_WARPS_PER_BLOCK * 8;               // one mbarrier per warp (bulk load of the state block)
+template <bool SEE> __host__ __device__ constexpr int table_bytes() { return (lut_bytes<SEE>() + 2 * AXIS_ENTRIES * 4 + MBAR_BYTES + 127) / 128 * 128; }   // 3840 / 6912
 
 // minigrid.py:40-52 / 27-35 / 57-61
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
@@ -249,6 +269,11 @@ __device__ __noinline__ void prefetch_draws(uint32_t *draws, uint32_t first_bloc
     }
 }
 
+__device__ __forceinline__ int ldg_u8(const uint8_t *g) {        // volatile asm: stays where it is written
+    uint32_t v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(g) : "memory");
+    return (int)v;
+}
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -874,7 +899,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
         P[k] = (int)lds_u32(pa + k * pstep4) + (int)st_sa;            // P carries the column base address
         Q[k] = (int)lds_u32(qa + (V - 1 - k) * qstep4);
     }
-    const uint32_t own = e.carry ? lut[e.carry * lut_pitch<SEE>()] : (uint32_t)T_EMPTY;   // word0: 24-bit (type,colour,state)   // minigrid.py:1349-1356
+    const uint32_t own = e.carry ? lds_u32(lut_sa + (uint32_t)e.carry * (lut_pitch<SEE>() * 4)) : (uint32_t)T_EMPTY;   // word0: 24-bit (type,colour,state)   // minigrid.py:1349-1356
 
     // Realignment of the record to byte offset lane*147 of the warp's 4704-byte block: word j of the record
     // times 2^s8 (one IMAD.WIDE) gives the bits that stay in block word q+j (low half) and the bits that
@@ -944,6 +969,58 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
 #endif
             }
         }
+    } else if (MGB_OCC_REGS) {
+        // Register-held variant: (A) all V*V cell + LUT loads, independent of each other, into registers in output
+        // order; (B) the flood on the V row masks, invisible cells zeroed in place; (C) the streaming pack of the
+        // see-through path.  No 38-word accumulator, half the PRMTs, and the loads do not wait for the flood.
+        uint32_t xs[V * V + 3], opq[V];
+        xs[V * V] = xs[V * V + 1] = xs[V * V + 2] = 0;
+#pragma unroll
+        for (int vy = V - 1; vy >= 0; --vy) {
+            uint32_t code[V];
+#pragma unroll
+            for (int vx = V - 1; vx >= 0; --vx) code[vx] = lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa));
+            uint32_t o = 0;
+#pragma unroll
+            for (int vx = V - 1; vx >= 0; --vx) {                         // descending: Horner
+#if MGB_OCC_REGS == 1
+                uint32_t oq;
+                lut_ld2(lut_sa, code[vx], xs[vx * V + vy], oq);
+                o = o * p.m2 + oq;                                        // FMA pipe
+#else
+                // one 32-bit word per cell: 24-bit encoding + "opaque" in bit 31 (never selected by the PRMTs below)
+                uint32_t a;
+                asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code[vx]), "r"(lut_sa + 4u), "n"(LUT_PITCH_OCC * 4));
+                const uint32_t x = lds_u32(a);
+                xs[vx * V + vy] = x;
+#if MGB_OCC_REGS == 2
+                o = __funnelshift_l(x, o, 1);                             // (o << 1) | (x >> 31)
+#else
+                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(o) : "r"(x), "r"(p.m2 << vx));   // + (x >> (31 - vx)): bits 24..30 of x are 0
+#endif
+#endif
+            }
+            opq[vy] = o;
+        }
+        xs[AGENT_CI] = own;
+        uint32_t rowvis = 1u << (V / 2);                          // mask[(3,6)] = True (minigrid.py:619)
+#pragma unroll
+        for (int vy = V - 1; vy >= 0; --vy) {
+            const uint32_t t = ~opq[vy] & VMASK;
+            const uint32_t f = flood_up<V>(rowvis, t);                       // forward sweep i = 0..5
+            const uint32_t vis = revv<V>(flood_up<V>(revv<V>(f), revv<V>(t)));        // reverse sweep i = 6..1
+            const uint32_t sv = vis & t;
+            rowvis = (sv | (sv << 1) | (sv >> 1)) & VMASK;                // seeds of row vy-1
+#pragma unroll
+            for (int vx = 0; vx < V; ++vx) xs[vx * V + vy] = sel_bit(vis, 1u << vx, xs[vx * V + vy]);
+        }
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const uint32_t *y = &xs[g * 4];
+            emit(g * 3, __byte_perm(y[0], y[1], 0x4210));
+            if (g * 3 + 1 <= FW + 1) emit(g * 3 + 1, __byte_perm(y[1], y[2], 0x5421));
+            if (g * 3 + 2 <= FW + 1) emit(g * 3 + 2, __byte_perm(y[2], y[3], 0x6542));
+        }
     } else {
         uint32_t acc[FW + 2];
 #pragma unroll
@@ -1010,11 +1087,72 @@ __device__ __forceinline__ void bulk_copy(void *gptr, const void *sptr, uint32_t
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gptr), "r"(saddr), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_commit() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+// state block HBM -> shared memory with one bulk copy that signals the warp's mbarrier
+__device__ __forceinline__ void mbar_init(uint32_t mbar_sa, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar_sa), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_sa, const void *gptr, uint32_t bytes, uint32_t mbar_sa) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_sa), "l"(gptr), "r"(bytes), "r"(mbar_sa) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar_sa, uint32_t parity) {
+    asm volatile("{ .reg .pred p; W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1; @!p bra W; }" ::"r"(mbar_sa), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// 32 steps of a group's actions.  Row t of the [T][N] action array holds the 32 bytes of the group at
+// actions + t*stride + group*32: lane t fetches row t0+t (two 16-byte loads when rows are aligned, bytes otherwise),
+// parks it in the warp's staging block (idle between two observations), and every lane then gathers its own column
+// into 32 x 4 bits (values >= 15 stay invalid: n_actions <= 9).  Issue and store/pack are separate so that the
+// state block's load can wait in between.
+struct ActionRow { uint4 lo, hi; };
+__device__ __forceinline__ void actions_issue(ActionRow &r, const uint8_t *row, bool mine, bool fast) {
+    r.lo = r.hi = make_uint4(0, 0, 0, 0);
+    if (mine && fast) {
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.lo.x), "=r"(r.lo.y), "=r"(r.lo.z), "=r"(r.lo.w) : "l"(row) : "memory");
+        asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.hi.x), "=r"(r.hi.y), "=r"(r.hi.z), "=r"(r.hi.w) : "l"(row + 16) : "memory");
+    }
+}
+__device__ __forceinline__ void actions_pack(const ActionRow &r, const uint8_t *row, bool mine, bool fast, int nvalid, uint32_t *stage_w, int lane,
+                                             uint32_t &q0, uint32_t &q1, uint32_t &q2, uint32_t &q3) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the staging block is free
+    __syncwarp();
+    if (mine) {
+        if (fast) {
+            reinterpret_cast<uint4 *>(stage_w)[lane * 2] = r.lo;
+            reinterpret_cast<uint4 *>(stage_w)[lane * 2 + 1] = r.hi;
+        } else {
+            uint8_t *sb = reinterpret_cast<uint8_t *>(stage_w) + lane * 32;
+            for (int k = 0; k < nvalid; ++k) sb[k] = row[k];
+        }
+    }
+    __syncwarp();
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(stage_w) + (uint32_t)lane;
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 32; ++k) w[k >> 3] |= min(lds_u8(sa + k * 32), 15u) << ((k & 7) * 4);
+    q0 = w[0]; q1 = w[1]; q2 = w[2]; q3 = w[3];
+    __syncwarp();
+}
+// One bulk copy (one HBM latency) instead of ceil(S/16) dependent batches of LDG -> STS.  The previous group's
+// generic-proxy accesses to the block are ordered before the async-proxy write by the fence.  Once per
+// group.
+__device__ __forceinline__ void load_state_block(uint32_t dst_sa, const uint32_t *src, uint32_t bytes, uint32_t mbar_sa, uint32_t phase, int lane) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) bulk_load(dst_sa, src, bytes, mbar_sa);
+    mbar_wait(mbar_sa, phase);
+}
+__device__ __forceinline__ void prefetch_l2(const void *g) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+}
+__device__ __forceinline__ void prefetch_l2_keep(const void *g) {
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(g));
+}
+__device__ __forceinline__ void bulk_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1031,6 +1169,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
 #endif
     const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr bool PACKED = MGB_PACKED_ACTIONS == 2 || (MGB_PACKED_ACTIONS == 1 && !SEE);
     const DevCfg &c = p.cfg;
     // the warp index goes through a lane-0 broadcast so that ptxas knows it is warp-uniform: everything derived from
     // it (group, staging block, output addresses) then lives in uniform registers and the bulk copies below need no
@@ -1045,7 +1184,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const uint32_t le = lut_entry(i);
         lut[i * lut_pitch<SEE>()] = le & 0x00FFFFFFu;
-        if (!SEE) lut[i * lut_pitch<SEE>() + 1] = (le >> 24) & F_OPAQUE;
+        if (!SEE) lut[i * lut_pitch<SEE>() + 1] = MGB_OCC_REGS >= 2 ? (le & 0x00FFFFFFu) | (((le >> 24) & F_OPAQUE) << 31) : (le >> 24) & F_OPAQUE;
         lut[i * lut_pitch<SEE>() + lut_fw<SEE>()] = le;
     }
     for (int i = threadIdx.x; i < AXIS_ENTRIES; i += blockDim.x) {
@@ -1053,15 +1192,32 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
         axis[i] = ((unsigned)v < (unsigned)c.W) ? (uint32_t)(v * c.HP * 32) : (uint32_t)wall;                       // x: column pitch
         axis[AXIS_ENTRIES + i] = ((unsigned)v < (unsigned)c.H) ? (uint32_t)(((v >> 2) << 7) + (v & 3)) : (uint32_t)wall;   // y: word + byte
     }
+    const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(axis + 2 * AXIS_ENTRIES) + (uint32_t)warp * 8u;
+    if (MGB_BULK_STATE && lane == 0) mbar_init(mbar_sa, 1);
     __syncthreads();
 
     const int S = c.S, GW = c.GW;
     const int64_t stride = p.stride;
+    uint32_t phase = 0;
     for (int g = blockIdx.x * wpb + warp; g < p.n_groups; g += gridDim.x * wpb) {
         const int group = p.group0 + g;
         uint32_t *gst = p.state + (size_t)group * S * 32 + lane;
+        // The step loop holds no global load: a lane fetches the actions of its env for 32 steps at once (one HBM latency
+        // per 32 steps, overlapped with the state block's) and keeps them as 32 x 4 bits in four registers.  With a load
+        // per step, ptxas gave it a scoreboard that the first instruction after the transition also waited on: 8-15 % of
+        // all stall samples of the occluded kernels (+8-13 % there).  The see-through kernels are bound by the shared-memory
+        // pipe, not by that stall, and measured 6 % slower with this scheme: they keep the per-step load.
+        ActionRow arow;
+        const uint8_t *arow_p = p.actions + (int64_t)lane * p.stride + (int64_t)group * 32;
+        const bool afast = ((p.stride & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.actions) & 15) == 0) && ((int64_t)group * 32 + 32 <= p.n_envs);
+        if (PACKED && p.T > 1) actions_issue(arow, arow_p, lane < p.T, afast);
         // ---- load the group's state block: S coalesced 128-byte rows -> bank == lane ----
-        for (int k = 0; k < S; ++k) st_warp[k * 32 + lane] = gst[k * 32];
+        if (MGB_BULK_STATE == 1 || (MGB_BULK_STATE == 2 && p.T <= 1)) {
+            load_state_block((uint32_t)__cvta_generic_to_shared(st_warp), p.state + (size_t)group * S * 32, (uint32_t)S * 128u, mbar_sa, phase, lane);
+            phase ^= 1u;
+        } else {
+            for (int k = 0; k < S; ++k) st_warp[k * 32 + lane] = gst[k * 32];
+        }
         st_warp[S * 32 + lane] = (uint32_t)CODE_WALL * 0x01010101u;        // out-of-grid pad (minigrid.py:469)
         Env e;
         Rng rg;
@@ -1096,13 +1252,50 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
             if (m) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }   // copy-in/out keeps e, rg in registers
         }
         const int nsteps = p.T > 0 ? p.T : 1;
+#if MGB_PREFETCH_ACTIONS
+        // The group's actions (row t = 32 bytes at actions + t*stride + group*32) are pulled into L2 up front and
+        // marked evict_last, so that the per-step loads below are L2 hits (~0.3 us) instead of HBM reads queued behind
+        // the output stream (~1 us): the first instruction after the transition shares a scoreboard with that load and
+        // waited for it on every step (15 % of the see-through kernel's stall samples).
+        if (MGB_PREFETCH_ACTIONS == 1 && p.T > 1) {
+            const uint8_t *arow = p.actions + (int64_t)group * 32;
+            for (int tt = lane; tt < p.T; tt += 32) {
+                prefetch_l2_keep(arow + (int64_t)tt * stride);
+                prefetch_l2_keep(arow + (int64_t)tt * stride + 31);
+            }
+        }
+#endif
         int a_next = 0;
-        if (p.T > 0 && valid) a_next = p.actions[lid];
+        uint32_t aq0 = 0, aq1 = 0, aq2 = 0, aq3 = 0;
+        if (PACKED) {
+            if (p.T > 1) actions_pack(arow, arow_p, lane < p.T, afast, nvalid, stage_w, lane, aq0, aq1, aq2, aq3);
+            if (p.T == 1 && valid) a_next = min((int)p.actions[lid], 15);
+        } else if (p.T > 0 && valid) a_next = p.actions[lid];
         for (int t = 0; t < nsteps; ++t) {
             double reward = 0.0; bool done = false;
             if (p.T > 0) {
+                if (PACKED && p.T > 1) {
+                    if ((t & 31) == 0 && t > 0) {             // rollouts longer than 32 steps: next chunk
+                        ActionRow r;
+                        const uint8_t *rp = arow_p + (int64_t)t * stride;
+                        actions_issue(r, rp, t + lane < p.T, afast);
+                        actions_pack(r, rp, t + lane < p.T, afast, nvalid, stage_w, lane, aq0, aq1, aq2, aq3);
+                    }
+                    a_next = (int)(aq0 & 15u);
+                    aq0 = __funnelshift_r(aq0, aq1, 4); aq1 = __funnelshift_r(aq1, aq2, 4); aq2 = __funnelshift_r(aq2, aq3, 4); aq3 >>= 4;
+                }
                 const int action = a_next;
-                if (t + 1 < p.T && valid) a_next = p.actions[(int64_t)(t + 1) * stride + lid];
+#if MGB_PREFETCH_ACTIONS >= 2
+                // row t+D of the group's actions -> L2, D steps (~3 us each) ahead of the load that needs it
+                if (t + MGB_PREFETCH_DIST < p.T) {
+                    const uint8_t *arow = p.actions + (int64_t)(t + MGB_PREFETCH_DIST) * stride + (int64_t)group * 32;
+                    if (MGB_PREFETCH_ACTIONS == 2) { prefetch_l2(arow); prefetch_l2(arow + 31); }
+                    else { prefetch_l2_keep(arow); prefetch_l2_keep(arow + 31); }
+                }
+#endif
+#if !MGB_LATE_PREFETCH
+                if (!PACKED && t + 1 < p.T && valid) a_next = p.actions[(int64_t)(t + 1) * stride + lid];
+#endif
                 if (GEN == GEN_DYNOBS) {                        // the staging block doubles as the draw window
                     if (lane == 0) bulk_store_wait_read();
                     __syncwarp();
@@ -1130,6 +1323,13 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
                 if (need_reset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
             }
             const int64_t o = (int64_t)t * stride + lid;
+#if MGB_LATE_PREFETCH
+            // The next action is requested here, after the transition and the (cold) reset path have merged: ptxas
+            // puts this load on the same scoreboard as the local-memory reloads that follow the out-of-line generator
+            // call, so a load issued before the transition made the first instruction after the merge wait for the
+            // full HBM latency on every step (7 % of all stall samples).  The observation below covers the latency.
+            if (p.T > 0 && t + 1 < p.T && valid) a_next = ldg_u8(p.actions + (int64_t)(t + 1) * stride + lid);
+#endif
             if (p.obs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
                 __syncwarp();
