@@ -83,8 +83,11 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #ifndef MGB_LATE_PREFETCH
 #define MGB_LATE_PREFETCH 0    // request the next action after the transition instead of before it (see k_rollout)
 #endif
+#ifndef MGB_FLOOD_SYM
+#define MGB_FLOOD_SYM 1        // occluded path: forward and reverse visibility sweep of a row in one carry chain (see observe)
+#endif
 #ifndef MGB_OCC_REGS
-#define MGB_OCC_REGS 1         // occluded path: 1 = cells held in registers, flood, then streaming pack (see observe); 0 = 38-word accumulator; 2,3 = single-word LUT experiments
+#define MGB_OCC_REGS 2         // occluded path: 1 = cells held in registers, flood, then streaming pack (see observe); 0 = 38-word accumulator; 2,3 = single-word LUT experiments
 #endif
 #ifndef MGB_PACK_IMAD_OCC
 #define MGB_PACK_IMAD_OCC 0    // occluded path: predicated IMAD accumulation instead of LOP3+SEL+PRMT (measured slower: 157 regs)
@@ -1003,6 +1006,25 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
             opq[vy] = o;
         }
         xs[AGENT_CI] = own;
+#if MGB_FLOOD_SYM
+        // Both sweeps of a row with one carry chain: the word holds the row in bits 0..V-1 and, bit-reversed, in bits
+        // 31..32-V, so the "towards higher bits" fill of flood_up runs up the row in the low field and down the row in
+        // the high field at once; or-ing the word with its own reversal merges the two.  The sweeps of process_vis
+        // compute the closure of "a visible see-through cell shows both neighbours", which is the union of the two fills.
+        // Bits 7 and 24 collect carries / shifted-out seeds; no mask has them and no test reads them.
+        uint32_t vw = (1u << (V / 2)) | (0x80000000u >> (V / 2));            // mask[(3,6)] = True (minigrid.py:619)
+#pragma unroll
+        for (int vy = V - 1; vy >= 0; --vy) {
+            const uint32_t t = ~opq[vy] & VMASK;
+            const uint32_t tw = t | __brev(t);
+            const uint32_t fw = (((vw & tw) + tw) ^ tw) | vw;
+            const uint32_t vis = fw | __brev(fw);
+            const uint32_t sw = vis & tw;
+            vw = sw | (sw << 1) | (sw >> 1);                               // seeds of row vy-1
+#pragma unroll
+            for (int vx = 0; vx < V; ++vx) xs[vx * V + vy] = sel_bit(vis, 1u << vx, xs[vx * V + vy]);
+        }
+#else
         uint32_t rowvis = 1u << (V / 2);                          // mask[(3,6)] = True (minigrid.py:619)
 #pragma unroll
         for (int vy = V - 1; vy >= 0; --vy) {
@@ -1014,6 +1036,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
 #pragma unroll
             for (int vx = 0; vx < V; ++vx) xs[vx * V + vy] = sel_bit(vis, 1u << vx, xs[vx * V + vy]);
         }
+#endif
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             const uint32_t *y = &xs[g * 4];
