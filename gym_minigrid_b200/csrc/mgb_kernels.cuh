@@ -83,6 +83,12 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #ifndef MGB_LATE_PREFETCH
 #define MGB_LATE_PREFETCH 0    // request the next action after the transition instead of before it (see k_rollout)
 #endif
+#ifndef MGB_HOIST
+#define MGB_HOIST 1            // step-loop invariants kept in registers (1: occluded kernels only, 2: all, 0: none)
+#endif
+#ifndef MGB_BULK_WB
+#define MGB_BULK_WB 1          // state write-back with one bulk copy
+#endif
 #ifndef MGB_FLOOD_SYM
 #define MGB_FLOOD_SYM 1        // occluded path: forward and reverse visibility sweep of a row in one carry chain (see observe)
 #endif
@@ -1165,7 +1171,10 @@ __device__ __forceinline__ void actions_pack(const ActionRow &r, const uint8_t *
 __device__ __forceinline__ void load_state_block(uint32_t dst_sa, const uint32_t *src, uint32_t bytes, uint32_t mbar_sa, uint32_t phase, int lane) {
     fence_proxy_async();
     __syncwarp();
-    if (lane == 0) bulk_load(dst_sa, src, bytes, mbar_sa);
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous group's write-back has been read
+        bulk_load(dst_sa, src, bytes, mbar_sa);
+    }
     mbar_wait(mbar_sa, phase);
 }
 __device__ __forceinline__ void prefetch_l2(const void *g) {
@@ -1294,10 +1303,24 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
             if (p.T > 1) actions_pack(arow, arow_p, lane < p.T, afast, nvalid, stage_w, lane, aq0, aq1, aq2, aq3);
             if (p.T == 1 && valid) a_next = min((int)p.actions[lid], 15);
         } else if (p.T > 0 && valid) a_next = p.actions[lid];
+        // loop invariants spelled out: ptxas otherwise re-derives them from the parameter bank on every step
+        // (69 of the occluded kernel's 880 instructions per step were this bookkeeping).  HOIST is off for the
+        // see-through kernels: at their 64 registers the extra live values cost more than the bookkeeping (measured -4 %).
+        constexpr bool HOIST = MGB_HOIST == 2 || (MGB_HOIST == 1 && !SEE);
+        const bool stepping = p.T > 0, multi = PACKED && p.T > 1;
+        const bool w_rew = valid && stepping && p.reward != nullptr, w_done = valid && stepping && p.done != nullptr;
+        const bool w_dir = valid && p.dir != nullptr;
+        int64_t o = lid;                                                  // this env's slot in the [t][N] outputs
+        uint8_t *gobs = p.obs ? p.obs + (int64_t)group * 32 * OB : nullptr;   // the group's block of step t (warp-uniform)
+        const int64_t obs_pitch = stride * OB;
         for (int t = 0; t < nsteps; ++t) {
             double reward = 0.0; bool done = false;
-            if (p.T > 0) {
-                if (PACKED && p.T > 1) {
+            if (!HOIST) {
+                o = (int64_t)t * stride + lid;
+                gobs = p.obs ? p.obs + ((int64_t)t * stride + (int64_t)group * 32) * OB : nullptr;
+            }
+            if (HOIST ? stepping : p.T > 0) {
+                if (HOIST ? multi : (PACKED && p.T > 1)) {
                     if ((t & 31) == 0 && t > 0) {             // rollouts longer than 32 steps: next chunk
                         ActionRow r;
                         const uint8_t *rp = arow_p + (int64_t)t * stride;
@@ -1345,7 +1368,6 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
                 }
                 if (need_reset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
             }
-            const int64_t o = (int64_t)t * stride + lid;
 #if MGB_LATE_PREFETCH
             // The next action is requested here, after the transition and the (cold) reset path have merged: ptxas
             // puts this load on the same scoreboard as the local-memory reloads that follow the out-of-line generator
@@ -1353,11 +1375,10 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
             // full HBM latency on every step (7 % of all stall samples).  The observation below covers the latency.
             if (p.T > 0 && t + 1 < p.T && valid) a_next = ldg_u8(p.actions + (int64_t)(t + 1) * stride + lid);
 #endif
-            if (p.obs) {
+            if (gobs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
                 __syncwarp();
                 observe<SEE, V>(st, e, p, lut, stage_w, lane);
-                uint8_t *gobs = p.obs + ((int64_t)t * stride + (int64_t)group * 32) * OB;
                 if (full && ((reinterpret_cast<uintptr_t>(gobs) & 15) == 0)) {
                     fence_proxy_async();
                     __syncwarp();
@@ -1382,8 +1403,14 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
                     }
                     __syncwarp();
                 }
+                if (HOIST) gobs += obs_pitch;
             }
-            if (valid) {
+            if (HOIST) {
+                if (w_rew) p.reward[o] = reward;
+                if (w_done) p.done[o] = done ? 1 : 0;
+                if (w_dir) p.dir[o] = (uint8_t)e.dir;
+                o += stride;
+            } else if (valid) {
                 if (p.T > 0) {
                     if (p.reward) p.reward[o] = reward;
                     if (p.done) p.done[o] = done ? 1 : 0;
@@ -1398,8 +1425,20 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
         st[(GW + 3) * 32] = rg.ndraws;
         if (GEN == GEN_POOL) st[(GW + XWORDS) * 32] = (uint32_t)pc.level;
         const bool any_dirty = __any_sync(0xFFFFFFFFu, e.dirty);
-        __syncwarp();
-        for (int k = any_dirty ? 0 : GW; k < S; ++k) gst[k * 32] = st_warp[k * 32 + lane];
+        const int k0 = any_dirty ? 0 : GW;                            // an untouched grid stays where it is
+        if (MGB_BULK_STATE == 1 && MGB_BULK_WB && (any_dirty || p.T > 1)) {      // a clean single step writes 4-5 rows: the loop is cheaper
+            // one bulk copy (rows k0..S-1 are contiguous here and in HBM) instead of a 7-instruction loop per word;
+            // load_state_block waits for it to have left shared memory before the block is reused
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_copy(p.state + (size_t)group * S * 32 + (size_t)k0 * 32, st_warp + k0 * 32, (uint32_t)(S - k0) * 128u);
+                bulk_commit();
+            }
+        } else {
+            __syncwarp();
+            for (int k = k0; k < S; ++k) gst[k * 32] = st_warp[k * 32 + lane];
+        }
         if (rg.err) atomicOr(p.err, rg.err);
         __syncwarp();
     }
