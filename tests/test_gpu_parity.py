@@ -358,3 +358,50 @@ def test_random_policy_rollout_matches_oracle(env_id):
     _, _, _, _, a = big.rollout_random(8, want_obs=False)
     h = torch.bincount(a.flatten().long(), minlength=cfg["n_actions"]).double()
     assert h.numel() == cfg["n_actions"] and float((h / h.sum() - 1.0 / cfg["n_actions"]).abs().max()) < 0.005 / cfg["n_actions"] * cfg["n_actions"]
+
+
+@pytest.mark.parametrize("env_id,misalign", [("MiniGrid-DoorKey-16x16-v0", 0), ("MiniGrid-FourRooms-v0", 0),
+                                             ("MiniGrid-KeyCorridorS6R3-v0", 1), ("MiniGrid-Empty-8x8-v0", 0)])
+def test_aligned_long_rollout_matches_oracle(env_id, misalign):
+    """N a multiple of 32 and T > 64: the occluded kernels fetch 32 steps of actions at a time with 16-byte row loads
+    (chunks 32 + 32 + 6 here), or byte-wise when the action array does not start on a 16-byte boundary (misalign=1);
+    the state block comes and goes with bulk copies.  Everything against the oracle, then the full state."""
+    from oracle.oracle import OracleVec
+    mgb = _mgb()
+    cfg = _oracle_cfg(env_id)
+    N, T, seed, base = 1024, 70, 11, 4242
+    actions = np.random.RandomState(17).randint(0, cfg["n_actions"], size=(T, N)).astype(np.uint8)
+    env = mgb.make(env_id, num_envs=N, seed=seed, env_id_base=base)
+    orc = OracleVec(cfg, N, seed=seed, env0=base)
+    env.reset(); orc.reset()
+    buf = torch.zeros(T * N + 16, dtype=torch.uint8, device="cuda")
+    a_dev = buf[misalign:misalign + T * N].view(T, N)
+    a_dev.copy_(torch.as_tensor(actions))
+    assert (a_dev.data_ptr() % 16 == 0) == (misalign == 0)
+    o, r, dn, dr = env.rollout(a_dev)
+    wo, wr, wdn, wdr = orc.rollout(actions, autoreset=True)
+    assert_same(env_id + " obs", _np(o), wo)
+    assert_same(env_id + " done", _np(dn).astype(np.uint8), wdn)
+    assert_same(env_id + " dir", _np(dr), wdr)
+    assert_same(env_id + " reward bits", bits(_np(r)), bits(wr))
+    s, so = env.get_state(), orc.get_state()
+    for key in ("grid", "agent", "carrying", "target"):
+        assert_same(env_id + " state." + key, _np(s[key]), so[key])
+    assert_same(env_id + " state.rng", _np(s["rng"]).view(np.uint32), so["rng"])
+    env.check_errors()
+
+
+def test_invalid_action_inside_a_rollout_is_flagged():
+    """an out-of-range action deep inside a rollout (step 40 of 48, second 32-step chunk of the packed action path)
+    raises the same error flag as in a single step; 15 and 200 are both invalid."""
+    mgb = _mgb()
+    for bad in (7, 15, 200):
+        env = mgb.make("MiniGrid-DoorKey-16x16-v0", num_envs=64)
+        env.reset()
+        a = torch.zeros((48, 64), dtype=torch.uint8, device="cuda")
+        env.rollout(a)
+        env.check_errors()
+        a[40, 33] = bad
+        env.rollout(a)
+        with pytest.raises(Exception, match="unknown action"):
+            env.check_errors()
