@@ -192,7 +192,8 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     // trip and wants every warp it can get; the persistent rollout is bound by the shared-memory pipe, which 24 warps
     // saturate -- beyond that more resident warps only cost (28 warps: -4 %), and at equal warps more, smaller CTAs
     // did slightly better (6 warps x 4 CTAs: +3 % over 8 x 3).
-    constexpr int ROLLOUT_WARP_CAP = 24;
+    int ROLLOUT_WARP_CAP = 24;
+    if (const char *cap = getenv("MGB_ROLLOUT_WARP_CAP")) ROLLOUT_WARP_CAP = std::max(2, atoi(cap));   // experiments only
     const char *force = getenv("MGB_WARPS_PER_BLOCK");           // experiments only: pin the CTA shape
     for (int wpb = MAX_WARPS_PER_BLOCK; wpb >= 2; --wpb) {
         if (force && atoi(force) != wpb) continue;

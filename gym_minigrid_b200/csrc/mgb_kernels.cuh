@@ -83,6 +83,15 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #ifndef MGB_LATE_PREFETCH
 #define MGB_LATE_PREFETCH 0    // request the next action after the transition instead of before it (see k_rollout)
 #endif
+#ifndef MGB_OBS_L2_HINT
+#define MGB_OBS_L2_HINT 0
+#endif
+#ifndef MGB_EXP_OBS_WRAP
+#define MGB_EXP_OBS_WRAP 0     // DIAGNOSTIC ONLY (wrong results): all observation blocks land in a 4.8 MB window that stays in L2
+#endif
+#ifndef MGB_STAGE_DELAY
+#define MGB_STAGE_DELAY 0      // see-through kernels: conflict-free staging stores through a 4-word delay on 14 lanes (see observe); measured: no gain
+#endif
 #ifndef MGB_HOIST
 #define MGB_HOIST 1            // step-loop invariants kept in registers (1: occluded kernels only, 2: all, 0: none)
 #endif
@@ -878,7 +887,13 @@ struct Stitch {
     uint32_t prev, first, w36, w37;
 };
 
-template <bool SEE, int V>
+// DELAY (V = 7 only): lanes {0,27}, {2,29}, {3,30}, {4,31} start their 147-byte records in the same bank, so every
+// staging store of the streaming pack is a 2-way conflict (37 of the see-through kernel's 222 shared-memory wavefronts
+// per warp-step, and that pipe is what bounds it).  The lanes of STAGE_DELAY_MASK store word j-4 instead of word j at
+// instruction j (one SEL per word, four words of history in registers, four flush stores at the end): start banks
+// (q - 4*delayed) mod 32 are then a permutation of 0..31.
+constexpr uint32_t STAGE_DELAY_MASK = 0x100477ddu;
+template <bool SEE, int V, bool DELAY>
 __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const RolloutParams &p, const uint32_t *lut,
                                         uint32_t *stage_w, int lane) {
     const DevCfg &c = p.cfg;
@@ -918,6 +933,10 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
     const uint32_t s8 = (boff & 3) * 8;
     const uint32_t M = p.m1 << s8;
     uint32_t first = 0, w36 = 0, w37 = 0, spill = 0;
+    static_assert(!DELAY || (V == 7 && stage_nseg(V) == 1), "the delay table is the one of 147-byte records");
+    const bool dl = DELAY && ((STAGE_DELAY_MASK >> lane) & 1u);
+    uint32_t *const sw = stage_w + q - (dl ? 4 : 0);
+    uint32_t h1 = 0, h2 = 0, h3 = 0, h4 = 0;                     // words j-1 .. j-4
     auto emit = [&](int j, uint32_t a) {
 #if MGB_STITCH_IMAD
         const uint64_t wide = (uint64_t)a * M + spill;
@@ -928,7 +947,13 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
         spill = a;
 #endif
         if (j == 0) first = o;
-        else if (j < FW) stage_w[q + j] = o;
+        else if (j < FW) {
+            if (DELAY) {
+                const uint32_t v = dl ? h4 : o;
+                if (j >= 5 || !dl) sw[j] = v;                    // a delayed lane has nothing to store before word 1
+                h4 = h3; h3 = h2; h2 = h1; h1 = o;
+            } else stage_w[q + j] = o;
+        }
         else if (j == FW) w36 = o;
         else w37 = o;
     };
@@ -1094,6 +1119,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
 #pragma unroll
         for (int j = 0; j < FW + 2; ++j) emit(j, acc[j]);
     }
+    if (DELAY && dl) { sw[FW] = h4; sw[FW + 1] = h3; sw[FW + 2] = h2; sw[FW + 3] = h1; }   // words FW-4 .. FW-1
     // the partial last word of lane t-1 shares a 32-bit word with the head of lane t
     const uint32_t tail = (s8 >= 16) ? w37 : w36;
     const uint32_t ptail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
@@ -1113,8 +1139,20 @@ __device__ __forceinline__ void bulk_store_wait_all() {
 }
 __device__ __forceinline__ void bulk_copy(void *gptr, const void *sptr, uint32_t bytes) {
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sptr);
+#if MGB_OBS_L2_HINT
+    // experiment: L2 eviction priority for the observation stream (1 = evict_first, 2 = evict_last, 3 = no_allocate-like normal)
+    uint64_t pol;
+#if MGB_OBS_L2_HINT == 1
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#else
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gptr), "r"(saddr), "r"(bytes), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gptr), "r"(saddr), "r"(bytes) : "memory");
+#endif
 }
 // state block HBM -> shared memory with one bulk copy that signals the warp's mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t mbar_sa, uint32_t count) {
@@ -1317,7 +1355,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
             double reward = 0.0; bool done = false;
             if (!HOIST) {
                 o = (int64_t)t * stride + lid;
-                gobs = p.obs ? p.obs + ((int64_t)t * stride + (int64_t)group * 32) * OB : nullptr;
+                gobs = p.obs ? p.obs + (MGB_EXP_OBS_WRAP ? (int64_t)(group & 1023) * 32 * OB : ((int64_t)t * stride + (int64_t)group * 32) * OB) : nullptr;
             }
             if (HOIST ? stepping : p.T > 0) {
                 if (HOIST ? multi : (PACKED && p.T > 1)) {
@@ -1378,7 +1416,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
             if (gobs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
                 __syncwarp();
-                observe<SEE, V>(st, e, p, lut, stage_w, lane);
+                observe<SEE, V, MGB_STAGE_DELAY && SEE && V == 7 && GEN != GEN_DYNOBS && !MGB_STAGE_SEG>(st, e, p, lut, stage_w, lane);
                 if (full && ((reinterpret_cast<uintptr_t>(gobs) & 15) == 0)) {
                     fence_proxy_async();
                     __syncwarp();
