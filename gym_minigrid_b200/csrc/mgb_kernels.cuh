@@ -531,10 +531,14 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
 // no branches -- and the first valid one wins; a lane whose DYN_SPEC tries all failed (p ~ 0.25^4) or whose draw
 // window is nearly used up continues one try at a time in a (divergent, rare) loop, computing Philox blocks on demand
 // once it runs past the prefetched window.
+#ifndef MGB_DYN_UNROLL
+#define MGB_DYN_UNROLL 1       // unroll factor of the per-ball loop of dynobs_move
+#endif
 #ifndef MGB_DYN_SPEC
 #define MGB_DYN_SPEC 4
 #endif
 constexpr int DYN_SPEC = MGB_DYN_SPEC;
+constexpr int DYN_UNROLL = MGB_DYN_UNROLL;
 // byte offset of grid cell (x,y) inside a lane's column: word x*HP/4 + (y>>2) at pitch 128, byte y&3
 __device__ __forceinline__ uint32_t cell_off(int x, int y, int HP) { return (uint32_t)(x * (HP * 32) + y + (y >> 2) * 124); }
 
@@ -555,6 +559,7 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
     const uint32_t ag_sa = st_sa + cell_off(e.ax, e.ay, HP);
     const bool ag_mark = lds_u8(ag_sa) == CODE_EMPTY;
     if (ag_mark) sts_u8(ag_sa, CODE_WALL);
+#pragma unroll DYN_UNROLL
     for (int k = 0; k < nob; ++k) {
         const uint32_t opos = lds_u16(ob_sa + (uint32_t)((k >> 1) * 128 + (k & 1) * 2));
         const int ox = (int)(opos & 0xFF), oy = (int)(opos >> 8);
