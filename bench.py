@@ -280,6 +280,15 @@ def main():
     s1.record()
     barrier()
     step_mode = N * Ks / (s0.elapsed_time(s1) * 1e-3)
+    # bytes a single-step launch must move per env-step: the 158 output/action bytes plus the env's state block read
+    # (S words) and, for an untouched grid, its non-grid words written back
+    hp = (cfg["height"] + 3) // 4 * 4
+    gw = cfg["width"] * hp // 4
+    s_words = gw + 4 + (4 if cfg.get("n_obstacles", 0) > 0 else 0)
+    step_bytes = 158 + 4 * s_words + 4 * (s_words - gw)
+    step_mode_info = {"env_steps_per_s_per_gpu": step_mode, "state_inclusive_bytes_per_env_step": step_bytes,
+                      "state_inclusive_gbs": step_mode * step_bytes / 1e9,
+                      "frac_of_hbm_peak": (step_mode * step_bytes / 1e9) / roofline["peak"] if roofline and roofline.get("peak") else None}
 
     # ---- secondary: the other BASELINE.json configs on the same kernel family, per GPU (short: 3 warm-up + 5 launches each) ----
     others = None
@@ -321,7 +330,7 @@ def main():
                        "l2": "outputs per launch (%.1f GB) exceed L2; no flush needed" % (N * T * 157 / 1e9),
                        "parallelism": "env shards by global env id, no collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "step_mode_env_steps_per_s_per_gpu": step_mode, "other_configs_per_gpu": others,
+            "step_mode_env_steps_per_s_per_gpu": step_mode, "step_mode": step_mode_info, "other_configs_per_gpu": others,
         }))
     if world > 1:
         dist.destroy_process_group()
