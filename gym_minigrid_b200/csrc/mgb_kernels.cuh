@@ -83,6 +83,9 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #ifndef MGB_LATE_PREFETCH
 #define MGB_LATE_PREFETCH 0    // request the next action after the transition instead of before it (see k_rollout)
 #endif
+#ifndef MGB_STAGGER
+#define MGB_STAGGER 0          // ns of start delay per resident-warp slot (experiment)
+#endif
 #ifndef MGB_OBS_L2_HINT
 #define MGB_OBS_L2_HINT 0
 #endif
@@ -1271,6 +1274,11 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
     if (MGB_BULK_STATE && lane == 0) mbar_init(mbar_sa, 1);
     __syncthreads();
 
+#if MGB_STAGGER
+    // experiment: start the resident warps of an SM at different phases of the step so that they do not all sit in the
+    // load-heavy gather (or the ALU-heavy pack) at the same time
+    if (p.T > 1) __nanosleep((uint32_t)(((blockIdx.x & 3) * wpb + warp) * MGB_STAGGER));
+#endif
     const int S = c.S, GW = c.GW;
     const int64_t stride = p.stride;
     uint32_t phase = 0;
