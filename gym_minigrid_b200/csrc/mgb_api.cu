@@ -211,6 +211,11 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
         if (capped > best || (capped == best && (over < cur_over || (over == cur_over && wpb >= 6 && nb > cur.blocks_per_sm))))
             h->shape[0] = cand;
     }
+    if (const char *nbs = getenv("MGB_BLOCKS_PER_SM"))            // experiments only: fewer resident CTAs for rollouts
+        h->shape[0].blocks_per_sm = std::max(1, std::min(h->shape[0].blocks_per_sm, atoi(nbs)));
+    if (getenv("MGB_PRINT_SHAPE"))
+        fprintf(stderr, "mgb_create: rollout shape %d CTAs x %d warps (%zu B smem), single-step shape %d x %d\n", h->shape[0].blocks_per_sm,
+                h->shape[0].warps_per_block, h->shape[0].smem_bytes, h->shape[1].blocks_per_sm, h->shape[1].warps_per_block);
     if (h->shape[0].warps < 1) return cleanup(fail("mgb_create: kernel does not fit on an SM (%zu bytes of shared memory per warp)", per_warp));
     const size_t state_bytes = (size_t)h->n_groups * d.S * 32 * 4;
     if (cudaMalloc(&h->state, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: cudaMalloc(%zu) for env state failed", state_bytes));
