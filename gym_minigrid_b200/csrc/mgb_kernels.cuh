@@ -78,7 +78,7 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #define MGB_PACKED_ACTIONS 1   // rollouts: 32 steps of actions per lane fetched at once and held as 4-bit fields in 4 registers (1: occluded kernels, 2: all)
 #endif
 #ifndef MGB_PREFETCH_DIST
-#define MGB_PREFETCH_DIST 3
+#define MGB_PREFETCH_DIST 3     // steps ahead for MGB_PREFETCH_ACTIONS >= 2 (per-step L2 prefetch of the action row)
 #endif
 #ifndef MGB_LATE_PREFETCH
 #define MGB_LATE_PREFETCH 0    // request the next action after the transition instead of before it (see k_rollout)
@@ -87,7 +87,7 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #define MGB_STAGGER 0          // ns of start delay per resident-warp slot (experiment)
 #endif
 #ifndef MGB_OBS_L2_HINT
-#define MGB_OBS_L2_HINT 0
+#define MGB_OBS_L2_HINT 0      // experiment: L2 eviction hint on the observation stores (1 evict_first, 2 evict_last); measured -1..-2 %
 #endif
 #ifndef MGB_EXP_OBS_WRAP
 #define MGB_EXP_OBS_WRAP 0     // DIAGNOSTIC ONLY (wrong results): all observation blocks land in a 4.8 MB window that stays in L2
@@ -105,7 +105,7 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #define MGB_FLOOD_SYM 1        // occluded path: forward and reverse visibility sweep of a row in one carry chain (see observe)
 #endif
 #ifndef MGB_OCC_REGS
-#define MGB_OCC_REGS 2         // occluded path: 1 = cells held in registers, flood, then streaming pack (see observe); 0 = 38-word accumulator; 2,3 = single-word LUT experiments
+#define MGB_OCC_REGS 2         // occluded path: 2 = cells held in registers (one LUT word per cell, "opaque" in bit 31, row mask by funnel shift), flood, streaming pack; 1 = same with LDS.64 (word + opacity); 3 = row mask by mad.hi (-4 %); 0 = 38-word accumulator (-10 %)
 #endif
 #ifndef MGB_PACK_IMAD_OCC
 #define MGB_PACK_IMAD_OCC 0    // occluded path: predicated IMAD accumulation instead of LOP3+SEL+PRMT (measured slower: 157 regs)
