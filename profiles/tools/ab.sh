@@ -1,5 +1,9 @@
 #!/bin/bash
-# usage: scratch/ab.sh "<env ids>" <lib1> <lib2> ...
+# A/B of library variants on the GPU box.  Build a variant next to the product library with
+#   python -m gym_minigrid_b200.build -DMGB_<SWITCH>=<v> --out=build/ab/<name>.so
+# (build/ is git-ignored but travels with gpurun; gpurun_out/ does not), then
+#   gpurun -- 'bash profiles/tools/ab.sh "<env ids>" $PWD/gym_minigrid_b200/libmgb200.so $PWD/build/ab/<name>.so ...'
+# MGB_LIB selects the library for one process; run the parity tests on a variant the same way.
 ids="$1"; shift
 for lib in "$@"; do
   for id in $ids; do
