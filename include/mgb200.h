@@ -111,7 +111,9 @@ int mgb_step(mgb_handle *h, const uint8_t *actions, uint8_t *obs, double *reward
              uint8_t *done, uint8_t *dir, void *stream);
 
 /* T consecutive steps in ONE persistent kernel; env state stays in shared memory between steps.
- * actions [T][N]; obs [T][N][147]; reward/done/dir [T][N].  Any output may be NULL (not written). */
+ * actions [T][N]; obs [T][N][147]; reward/done/dir [T][N].  Any output may be NULL (not written).
+ * Alignment is a matter of speed only, never of results: obs blocks leave with bulk copies when obs is 16-byte aligned
+ * (else byte stores), and action rows are fetched 16 bytes at a time when actions and N are multiples of 16 (else bytes). */
 int mgb_rollout(mgb_handle *h, int32_t T, const uint8_t *actions, uint8_t *obs, double *reward,
                 uint8_t *done, uint8_t *dir, void *stream);
 
