@@ -89,6 +89,9 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #ifndef MGB_OBS_L2_HINT
 #define MGB_OBS_L2_HINT 0      // experiment: L2 eviction hint on the observation stores (1 evict_first, 2 evict_last); measured -1..-2 %
 #endif
+#ifndef MGB_EXP_NO_OBS_STORE
+#define MGB_EXP_NO_OBS_STORE 0 // DIAGNOSTIC ONLY (wrong results): observations are staged but never leave the SM
+#endif
 #ifndef MGB_EXP_OBS_WRAP
 #define MGB_EXP_OBS_WRAP 0     // DIAGNOSTIC ONLY (wrong results): all observation blocks land in a 4.8 MB window that stays in L2
 #endif
@@ -1437,7 +1440,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
 #pragma unroll
                         for (int k = 0; k < stage_nseg(V); ++k) {
                             const int w0 = (stage_seg_lane(V, k) * OB) >> 2, w1 = (stage_seg_lane(V, k + 1) * OB) >> 2;
-                            bulk_copy(gobs + 4 * w0, stage_w + w0 + STAGE_SEG_WORDS * k, 4u * (uint32_t)(w1 - w0));
+                            if (!MGB_EXP_NO_OBS_STORE) bulk_copy(gobs + 4 * w0, stage_w + w0 + STAGE_SEG_WORDS * k, 4u * (uint32_t)(w1 - w0));
                         }
                         bulk_commit();
                     }
