@@ -208,8 +208,18 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
         const mgb_handle::Shape &cur = h->shape[0];
         const int capped = std::min(warps, ROLLOUT_WARP_CAP), best = std::min(cur.warps, ROLLOUT_WARP_CAP);
         const int over = warps - capped, cur_over = cur.warps - best;
-        if (capped > best || (capped == best && (over < cur_over || (over == cur_over && wpb >= 6 && nb > cur.blocks_per_sm))))
-            h->shape[0] = cand;
+        if (c.see_through) {
+            // see-through kernels (64 registers): at equal warps more, smaller CTAs, but not below 6 warps
+            // (Empty-8x8: 6 x 4 beats 8 x 3 by 3 % and 4 x 6 by 1 %; profiles/r1_cta_shape_sweep.txt)
+            if (capped > best || (capped == best && (over < cur_over || (over == cur_over && wpb >= 6 && nb > cur.blocks_per_sm))))
+                h->shape[0] = cand;
+        } else {
+            // occluded kernels (128 registers = 4 warps per scheduler partition): CTAs of 4 or 8 warps fill the four
+            // partitions evenly; a 6-warp CTA does not (FourRooms: 4 x 3 beats 6 x 2 and 3 x 4 by 4 %; DoorKey-8x8: 8 x 2
+            // beats 4 x 4 by 3 % and 6 x 2 by 11 %).  Ties go to the larger CTA (fewer copies of the tables).
+            const int score = capped - ((wpb & 3) ? 4 : 0), cur_score = cur.warps < 1 ? -1 : best - ((cur.warps_per_block & 3) ? 4 : 0);
+            if (score > cur_score) h->shape[0] = cand;
+        }
     }
     if (const char *nbs = getenv("MGB_BLOCKS_PER_SM"))            // experiments only: fewer resident CTAs for rollouts
         h->shape[0].blocks_per_sm = std::max(1, std::min(h->shape[0].blocks_per_sm, atoi(nbs)));

@@ -113,17 +113,22 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 #ifndef MGB_PACK_IMAD_OCC
 #define MGB_PACK_IMAD_OCC 0    // occluded path: predicated IMAD accumulation instead of LOP3+SEL+PRMT (measured slower: 157 regs)
 #endif
-constexpr int LUT_PITCH_OCC = 6;   // occluded kernels: [x24, opaque, x24|flags<<24, -, -, -]  (LDS.64 of the first two)
+#ifndef MGB_LUT_PITCH_OCC
+#define MGB_LUT_PITCH_OCC (MGB_OCC_REGS >= 2 ? 3 : 6)
+#endif
+// occluded kernels: [x24, x24|opaque<<31, x24|flags<<24] at pitch 3 (MGB_OCC_REGS >= 2: one word per cell), or
+// [x24, opaque, x24|flags<<24, -, -, -] at pitch 6 for the LDS.64 of the first two (MGB_OCC_REGS 0/1)
+constexpr int LUT_PITCH_OCC = MGB_LUT_PITCH_OCC;
 constexpr int LUT_PITCH_SEE = 3;   // see-through kernels: [x24, x24|flags<<24, -]; odd pitch -> any 32 consecutive
                                    // codes map to 32 different banks (pitch 6 makes codes 16 apart collide,
                                    // e.g. grey wall 57 / green goal 169 -- the two objects of Empty-8x8)
 template <bool SEE> __host__ __device__ constexpr int lut_pitch() { return SEE ? LUT_PITCH_SEE : LUT_PITCH_OCC; }
 template <bool SEE> __host__ __device__ constexpr int lut_fw() { return SEE ? 1 : 2; }     // word index of the flags word
-template <bool SEE> __host__ __device__ constexpr int lut_bytes() { return 256 * lut_pitch<SEE>() * 4; }    // 3072 / 6144
+template <bool SEE> __host__ __device__ constexpr int lut_bytes() { return 256 * lut_pitch<SEE>() * 4; }    // 3072 (6144 at pitch 6)
 constexpr int AXIS_ENTRIES = 88;                                 // v in [-(V-1), 64+V-2] for V <= 11: index v + AXIS_BIAS
 constexpr int AXIS_BIAS = 10;
 constexpr int MBAR_BYTES = MAX_WARPS_PER_BLOCK * 8;               // one mbarrier per warp (bulk load of the state block)
-template <bool SEE> __host__ __device__ constexpr int table_bytes() { return (lut_bytes<SEE>() + 2 * AXIS_ENTRIES * 4 + MBAR_BYTES + 127) / 128 * 128; }   // 3840 / 6912
+template <bool SEE> __host__ __device__ constexpr int table_bytes() { return (lut_bytes<SEE>() + 2 * AXIS_ENTRIES * 4 + MBAR_BYTES + 127) / 128 * 128; }   // 3840 (6912 at pitch 6)
 
 // minigrid.py:40-52 / 27-35 / 57-61
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
