@@ -174,14 +174,6 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     d.GW = c.width * d.HP / 4;
     d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0) + (c.gen == MGB_GEN_POOL ? 1 : 0);   // pool: + level word
     h->sm_count = prop.multiProcessorCount;
-#if MGB_LUT_CONST
-    {
-        uint32_t t24[256];
-        for (int i = 0; i < 256; ++i) t24[i] = lut_entry(i) & 0x00FFFFFFu;
-        if (cudaMemcpyToSymbol(c_lut24, t24, sizeof t24) != cudaSuccess) return fail("mgb_create: constant LUT upload failed");
-    }
-#endif
-
     auto cleanup = [&](int rc) { mgb_destroy(h); return rc; };
     // warps per CTA: whatever keeps the most warps resident per SM (shared memory is the limiter for the
     // larger grids: each warp needs its 32-env state block + a 4704-byte staging block)
@@ -193,8 +185,11 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     // saturate -- beyond that more resident warps only cost (28 warps: -4 %), and at equal warps more, smaller CTAs
     // did slightly better (6 warps x 4 CTAs: +3 % over 8 x 3).
     int ROLLOUT_WARP_CAP = 24;
-    if (const char *cap = getenv("MGB_ROLLOUT_WARP_CAP")) ROLLOUT_WARP_CAP = std::max(2, atoi(cap));   // experiments only
-    const char *force = getenv("MGB_WARPS_PER_BLOCK");           // experiments only: pin the CTA shape
+    const char *force = nullptr;
+#ifdef MGB_EXPERIMENT       // experiment builds only (profiles/tools/*.sh): override the shape heuristics from the environment
+    if (const char *cap = getenv("MGB_ROLLOUT_WARP_CAP")) ROLLOUT_WARP_CAP = std::max(2, atoi(cap));
+    force = getenv("MGB_WARPS_PER_BLOCK");
+#endif
     for (int wpb = MAX_WARPS_PER_BLOCK; wpb >= 2; --wpb) {
         if (force && atoi(force) != wpb) continue;
         const size_t smem = (size_t)(c.see_through ? table_bytes<true>() : table_bytes<false>()) + (size_t)wpb * per_warp;
@@ -221,11 +216,13 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
             if (score > cur_score) h->shape[0] = cand;
         }
     }
-    if (const char *nbs = getenv("MGB_BLOCKS_PER_SM"))            // experiments only: fewer resident CTAs for rollouts
+#ifdef MGB_EXPERIMENT
+    if (const char *nbs = getenv("MGB_BLOCKS_PER_SM"))
         h->shape[0].blocks_per_sm = std::max(1, std::min(h->shape[0].blocks_per_sm, atoi(nbs)));
     if (getenv("MGB_PRINT_SHAPE"))
         fprintf(stderr, "mgb_create: rollout shape %d CTAs x %d warps (%zu B smem), single-step shape %d x %d\n", h->shape[0].blocks_per_sm,
                 h->shape[0].warps_per_block, h->shape[0].smem_bytes, h->shape[1].blocks_per_sm, h->shape[1].warps_per_block);
+#endif
     if (h->shape[0].warps < 1) return cleanup(fail("mgb_create: kernel does not fit on an SM (%zu bytes of shared memory per warp)", per_warp));
     const size_t state_bytes = (size_t)h->n_groups * d.S * 32 * 4;
     if (cudaMalloc(&h->state, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: cudaMalloc(%zu) for env state failed", state_bytes));
@@ -296,7 +293,6 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
     p.reset_mask = mask; p.actions = actions; p.obs = obs; p.reward = reward; p.done = done; p.dir = dir;
     p.stride = stride; p.seed = h->seed; p.env_id_base = h->env_id_base;
     p.tape = h->tape; p.tape_off = h->tape_off; p.err = h->err; p.pool = h->pool; p.pool_n = h->pool_n;
-    p.m0 = 1u; p.m1 = 1u; p.m2 = 2u; p.m8 = 1u << 8; p.m16 = 1u << 16; p.m24 = 1u << 24;
     rollout_fn fn = pick_kernel(h->cfg);
     const mgb_handle::Shape &sh = h->shape[T > 1 ? 0 : 1];
     const int want = (ng + sh.warps_per_block - 1) / sh.warps_per_block;
@@ -415,7 +411,11 @@ int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host,
     // copy engine pays a few microseconds per copy, so the chunks are few and the three small outputs (reward, done,
     // direction: 10 bytes per env) leave in one copy each after the last kernel instead of one per chunk.
     const int32_t G = h->n_groups;
-    static const int forced = getenv("MGB_HOST_CHUNKS") ? atoi(getenv("MGB_HOST_CHUNKS")) : 0;      // experiments only
+#ifdef MGB_EXPERIMENT
+    static const int forced = getenv("MGB_HOST_CHUNKS") ? atoi(getenv("MGB_HOST_CHUNKS")) : 0;
+#else
+    constexpr int forced = 0;
+#endif
     int32_t nchunks = forced > 0 ? forced : (G >= 4096 ? 4 : (G >= 1024 ? 2 : 1));
     const int32_t per = (G + nchunks - 1) / nchunks;
     CUDA_OK(cudaDeviceSynchronize());   // order against whatever the caller enqueued on other streams

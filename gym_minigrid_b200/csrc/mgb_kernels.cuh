@@ -29,25 +29,10 @@ constexpr int GROUP = 32;
 constexpr int STAGE_BYTES = GROUP * OBS_BYTES;   // 4704 = 294 * 16
 // the kernel is a template on the (odd) view size V: record = 3*V*V bytes, staging block = 32 records
 __host__ __device__ constexpr int obs_bytes(int V) { return 3 * V * V; }
-// Staging block of a warp: the 32 records of a step, stored to global memory with bulk copies.  Lane l writes the
-// 37 words that cover its own 147-byte record, starting at word floor(36.75 l); for V = 7 four pairs of lanes start in
-// the same bank ({0,27}, {2,29}, {3,30}, {4,31}), which made every one of the 37 stores of a step a 2-way bank conflict
-// (17 % of all shared-memory wavefronts of the kernel).  The block is therefore kept in STAGE_NSEG segments that are
-// contiguous both here and in global memory -- cut where a record's first word is 16-byte aligned, before lanes
-// 6, 11, 16, 22, 27 -- and segment k is placed 12 words further up than the one before: the 32 start banks become a
-// permutation of 0..31, the lane's addressing stays `q + j`, and the block leaves as 6 bulk copies instead of one.
-#ifndef MGB_STAGE_SEG
-#define MGB_STAGE_SEG 0
-#endif
-constexpr int STAGE_SEG_WORDS = 12;                      // extra word offset per segment
-__host__ __device__ constexpr int stage_nseg(int V) { return (MGB_STAGE_SEG && V == 7) ? 6 : 1; }
-__host__ __device__ constexpr int stage_seg_lane(int V, int k) { return stage_nseg(V) == 1 ? (k == 0 ? 0 : GROUP) : (16 * k + 2) / 3; }   // 0,6,11,16,22,27,32
-// multiple of 16 for every V; at least 1024: the block also parks 32 rows x 32 bytes of actions between two observations
-__host__ __device__ constexpr int stage_bytes(int V) { return GROUP * 3 * V * V + (stage_nseg(V) - 1) * STAGE_SEG_WORDS * 4 < 1024 ? 1024 : GROUP * 3 * V * V + (stage_nseg(V) - 1) * STAGE_SEG_WORDS * 4; }
+// Staging block of a warp: the 32 records of a step, contiguous here and in global memory, stored with one bulk copy.
+// Multiple of 16 bytes for every V; at least 1024: the block also parks 32 rows x 32 bytes of actions between two observations.
+__host__ __device__ constexpr int stage_bytes(int V) { return GROUP * 3 * V * V < 1024 ? 1024 : GROUP * 3 * V * V; }
 constexpr int MAX_WARPS_PER_BLOCK = 8;           // the host picks 2..8 warps per CTA to maximise resident warps/SM
-#ifndef MGB_SEE_MIN_BLOCKS
-#define MGB_SEE_MIN_BLOCKS 0     // experiment: >0 adds minBlocksPerSM to the see-through kernels' launch bounds (register cap)
-#endif
 constexpr int MAX_THREADS = MAX_WARPS_PER_BLOCK * 32;
 constexpr int MAX_OBST = 8;
 constexpr int XWORDS = 4;                        // agent, steps/target, episode, ndraws
@@ -59,66 +44,8 @@ constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 //   8-byte alignment lets the occluded path fetch word0+word1 with one LDS.64.
 //   AXIS tables: shared-memory offset of grid coordinate v (index v+6) along x and along y, out-of-grid
 //   entries = offset of the wall pad word (see observe()).
-#ifndef MGB_STITCH_IMAD
-#define MGB_STITCH_IMAD 0      // realign words with IMAD.WIDE (FMA pipe) instead of SHF funnel shifts (ALU pipe)
-#endif
-#ifndef MGB_PACK_IMAD_SEE
-#define MGB_PACK_IMAD_SEE 0    // see-through path: pack 4 cells -> 3 words with IMAD/IMAD.HI instead of PRMT
-#endif
-#ifndef MGB_SEE_BATCH
-#define MGB_SEE_BATCH 1       // see-through path: groups of 4 cells whose loads are issued back to back
-#endif
-#ifndef MGB_BULK_STATE
-#define MGB_BULK_STATE 1       // state block HBM -> shared memory with one cp.async.bulk per group instead of an LDG/STS loop
-#endif
-#ifndef MGB_PREFETCH_ACTIONS
-#define MGB_PREFETCH_ACTIONS 0 // rollouts: pull the group's T x 32 action bytes into L2 (evict_last) at group start
-#endif
-#ifndef MGB_PACKED_ACTIONS
-#define MGB_PACKED_ACTIONS 1   // rollouts: 32 steps of actions per lane fetched at once and held as 4-bit fields in 4 registers (1: occluded kernels, 2: all)
-#endif
-#ifndef MGB_PREFETCH_DIST
-#define MGB_PREFETCH_DIST 3     // steps ahead for MGB_PREFETCH_ACTIONS >= 2 (per-step L2 prefetch of the action row)
-#endif
-#ifndef MGB_LATE_PREFETCH
-#define MGB_LATE_PREFETCH 0    // request the next action after the transition instead of before it (see k_rollout)
-#endif
-#ifndef MGB_STAGGER
-#define MGB_STAGGER 0          // ns of start delay per resident-warp slot (experiment)
-#endif
-#ifndef MGB_OBS_L2_HINT
-#define MGB_OBS_L2_HINT 0      // experiment: L2 eviction hint on the observation stores (1 evict_first, 2 evict_last); measured -1..-2 %
-#endif
-#ifndef MGB_EXP_NO_OBS_STORE
-#define MGB_EXP_NO_OBS_STORE 0 // DIAGNOSTIC ONLY (wrong results): observations are staged but never leave the SM
-#endif
-#ifndef MGB_EXP_OBS_WRAP
-#define MGB_EXP_OBS_WRAP 0     // DIAGNOSTIC ONLY (wrong results): all observation blocks land in a 4.8 MB window that stays in L2
-#endif
-#ifndef MGB_STAGE_DELAY
-#define MGB_STAGE_DELAY 0      // see-through kernels: conflict-free staging stores through a 4-word delay on 14 lanes (see observe); measured: no gain
-#endif
-#ifndef MGB_HOIST
-#define MGB_HOIST 1            // step-loop invariants kept in registers (1: occluded kernels only, 2: all, 0: none)
-#endif
-#ifndef MGB_BULK_WB
-#define MGB_BULK_WB 1          // state write-back with one bulk copy
-#endif
-#ifndef MGB_FLOOD_SYM
-#define MGB_FLOOD_SYM 1        // occluded path: forward and reverse visibility sweep of a row in one carry chain (see observe)
-#endif
-#ifndef MGB_OCC_REGS
-#define MGB_OCC_REGS 2         // occluded path: 2 = cells held in registers (one LUT word per cell, "opaque" in bit 31, row mask by funnel shift), flood, streaming pack; 1 = same with LDS.64 (word + opacity); 3 = row mask by mad.hi (-4 %); 0 = 38-word accumulator (-10 %)
-#endif
-#ifndef MGB_PACK_IMAD_OCC
-#define MGB_PACK_IMAD_OCC 0    // occluded path: predicated IMAD accumulation instead of LOP3+SEL+PRMT (measured slower: 157 regs)
-#endif
-#ifndef MGB_LUT_PITCH_OCC
-#define MGB_LUT_PITCH_OCC (MGB_OCC_REGS >= 2 ? 3 : 6)
-#endif
-// occluded kernels: [x24, x24|opaque<<31, x24|flags<<24] at pitch 3 (MGB_OCC_REGS >= 2: one word per cell), or
-// [x24, opaque, x24|flags<<24, -, -, -] at pitch 6 for the LDS.64 of the first two (MGB_OCC_REGS 0/1)
-constexpr int LUT_PITCH_OCC = MGB_LUT_PITCH_OCC;
+// occluded kernels: [x24, x24|opaque<<31, x24|flags<<24] at pitch 3 (one word per cell for the view gather)
+constexpr int LUT_PITCH_OCC = 3;
 constexpr int LUT_PITCH_SEE = 3;   // see-through kernels: [x24, x24|flags<<24, -]; odd pitch -> any 32 consecutive
                                    // codes map to 32 different banks (pitch 6 makes codes 16 apart collide,
                                    // e.g. grey wall 57 / green goal 169 -- the two objects of Empty-8x8)
@@ -204,10 +131,6 @@ struct RolloutParams {
                                 //   tcode | mcode<<8 ; tx|ty<<8|A.x<<16|A.y<<24 ; B.x|B.y<<8|C.x<<16|C.y<<24 ; D.x|D.y<<8
     int32_t pool_n;
     uint32_t *err;
-    // run-time copies of 1, 1, 2, 2^8, 2^16, 2^24.  Multiplying by these (instead of literal shifts) keeps the
-    // byte packing / realignment on IMAD/IMAD.HI/IMAD.WIDE, i.e. on the FMA pipe: ptxas would turn a literal
-    // power of two back into SHF/LEA/PRMT on the ALU pipe, which is the pipe that bounds this kernel.
-    uint32_t m0, m1, m2, m8, m16, m24;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -851,11 +774,6 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
 // ------------------------------------------------------------------------------------------
 // observation: gen_obs_grid + Grid.encode (minigrid.py:1327-1381, 571-594)
 // ------------------------------------------------------------------------------------------
-template <int V> __device__ __forceinline__ uint32_t revv(uint32_t v) { return __brev(v) >> (32 - V); }
-// cells reachable towards higher bits through runs of transparent cells (one sweep of
-// process_vis, minigrid.py:624-635) as a carry chain: ((v&t)+t)^t marks [lowest seed .. run end+1]
-template <int V> __device__ __forceinline__ uint32_t flood_up(uint32_t v, uint32_t t) { return ((((v & t) + t) ^ t) | v) & ((1u << V) - 1u); }
-
 // (v & bit) ? x : 0.  Spelled as and/setp/selp so that ptxas turns the V tests of one row mask into a single R2P
 // (register bits -> predicates) plus one SEL per cell, instead of shift-left / arithmetic-shift-right / and per cell.
 __device__ __forceinline__ uint32_t sel_bit(uint32_t v, uint32_t bit, uint32_t x) {
@@ -864,20 +782,6 @@ __device__ __forceinline__ uint32_t sel_bit(uint32_t v, uint32_t bit, uint32_t x
     return r;
 }
 
-// insert the 3 low bytes of x at byte offset sh of the word pair (a, b); sh folds after unrolling
-__device__ __forceinline__ void put3(int sh, uint32_t &a, uint32_t &b, uint32_t x) {
-    if (sh == 0) a = __byte_perm(a, x, 0x3654);
-    else if (sh == 1) a = __byte_perm(a, x, 0x6540);
-    else if (sh == 2) { a = __byte_perm(a, x, 0x5410); b = __byte_perm(b, x, 0x3216); }
-    else { a = __byte_perm(a, x, 0x4210); b = __byte_perm(b, x, 0x3265); }
-}
-
-#ifndef MGB_LUT_CONST
-#define MGB_LUT_CONST 0      // experiment: see-through path reads the 24-bit cell encoding from constant memory instead of shared
-#endif
-#if MGB_LUT_CONST
-__constant__ uint32_t c_lut24[256];
-#endif
 // code -> LUT word; the address is formed with a multiply-add so that it issues on the (idle) FMA
 // pipe instead of the ALU pipe that bounds this kernel
 __device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
@@ -885,31 +789,13 @@ __device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
     asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_SEE * 4));
     return lds_u32(a);
 }
-// word0 (output bytes) and word1 (opaque) of a LUT entry with one LDS.64
-__device__ __forceinline__ void lut_ld2(uint32_t lut_sa, uint32_t code, uint32_t &x, uint32_t &opq) {
-    uint32_t a;
-    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_OCC * 4));
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(opq) : "r"(a) : "memory");
-}
-
 // Addressing of the view gather: the shared-memory offset of grid cell (x,y) inside a lane's column is
 // offx(x) + offy(y) with offx(x) = x*HP*32 and offy(y) = (y>>2)*128 + (y&3).  Out-of-grid coordinates map to
 // the offset of a pad word that holds CODE_WALL; any sum with an out-of-grid term is >= that offset, so one
 // min() clamps it onto the pad -- no per-cell bounds test (minigrid.py:465-469).  offx/offy are tabulated
 // once per CTA (axis tables).
 
-// realign + store one 32-bit word of the 147-byte record (see observe)
-struct Stitch {
-    uint32_t prev, first, w36, w37;
-};
-
-// DELAY (V = 7 only): lanes {0,27}, {2,29}, {3,30}, {4,31} start their 147-byte records in the same bank, so every
-// staging store of the streaming pack is a 2-way conflict (37 of the see-through kernel's 222 shared-memory wavefronts
-// per warp-step, and that pipe is what bounds it).  The lanes of STAGE_DELAY_MASK store word j-4 instead of word j at
-// instruction j (one SEL per word, four words of history in registers, four flush stores at the end): start banks
-// (q - 4*delayed) mod 32 are then a permutation of 0..31.
-constexpr uint32_t STAGE_DELAY_MASK = 0x100477ddu;
-template <bool SEE, int V, bool DELAY>
+template <bool SEE, int V>
 __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const RolloutParams &p, const uint32_t *lut,
                                         uint32_t *stage_w, int lane) {
     const DevCfg &c = p.cfg;
@@ -941,52 +827,30 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
     }
     const uint32_t own = e.carry ? lds_u32(lut_sa + (uint32_t)e.carry * (lut_pitch<SEE>() * 4)) : (uint32_t)T_EMPTY;   // word0: 24-bit (type,colour,state)   // minigrid.py:1349-1356
 
-    // Realignment of the record to byte offset lane*147 of the warp's 4704-byte block: word j of the record
-    // times 2^s8 (one IMAD.WIDE) gives the bits that stay in block word q+j (low half) and the bits that
-    // spill into q+j+1 (high half, carried into the next multiply-add).
+    // Realignment of the record to byte offset lane*147 of the warp's 4704-byte block: block word q+j takes the
+    // high bytes of record word j-1 and the low bytes of record word j -- one funnel shift per word.
     const int boff = lane * R;
-    const int q = (boff >> 2) + (stage_nseg(V) > 1 ? STAGE_SEG_WORDS * ((3 * lane) >> 4) : 0);   // (3*lane)>>4 = segment of the lane
+    const int q = boff >> 2;
     const uint32_t s8 = (boff & 3) * 8;
-    const uint32_t M = p.m1 << s8;
     uint32_t first = 0, w36 = 0, w37 = 0, spill = 0;
-    static_assert(!DELAY || (V == 7 && stage_nseg(V) == 1), "the delay table is the one of 147-byte records");
-    const bool dl = DELAY && ((STAGE_DELAY_MASK >> lane) & 1u);
-    uint32_t *const sw = stage_w + q - (dl ? 4 : 0);
-    uint32_t h1 = 0, h2 = 0, h3 = 0, h4 = 0;                     // words j-1 .. j-4
     auto emit = [&](int j, uint32_t a) {
-#if MGB_STITCH_IMAD
-        const uint64_t wide = (uint64_t)a * M + spill;
-        const uint32_t o = (uint32_t)wide;
-        spill = (uint32_t)(wide >> 32);
-#else
         const uint32_t o = __funnelshift_l(spill, a, s8);      // spill holds the previous un-shifted word
         spill = a;
-#endif
         if (j == 0) first = o;
-        else if (j < FW) {
-            if (DELAY) {
-                const uint32_t v = dl ? h4 : o;
-                if (j >= 5 || !dl) sw[j] = v;                    // a delayed lane has nothing to store before word 1
-                h4 = h3; h3 = h2; h2 = h1; h1 = o;
-            } else stage_w[q + j] = o;
-        }
+        else if (j < FW) stage_w[q + j] = o;
         else if (j == FW) w36 = o;
         else w37 = o;
     };
-    const uint32_t m0 = p.m0, m8 = p.m8, m16 = p.m16, m24 = p.m24;
 
     if (SEE) {
-        // no occlusion: stream cells in output order (vx-major); 4 cells (3 bytes each) -> 3 words.
-        // Software-pipelined by hand: a warp issues in order, so the cell loads of a whole batch
-        // (MGB_SEE_BATCH groups of 4 cells) are issued before the first dependent LUT load, and all LUT loads
-        // before the first pack -- fewer exposed LDS latencies per step.
-        constexpr int GB = MGB_SEE_BATCH;
+        // no occlusion: stream cells in output order (vx-major); 4 cells (3 bytes each) -> 3 words.  The four cell
+        // loads of a group are issued before the first dependent LUT load, and all LUT loads before the pack.
 #pragma unroll
-        for (int g0 = 0; g0 < NG; g0 += GB) {
-            uint32_t code[GB * 4], x[GB * 4];
+        for (int g = 0; g < NG; ++g) {
+            uint32_t code[4], x[4];
 #pragma unroll
-            for (int i = 0; i < GB * 4; ++i) {
-                const int ci = g0 * 4 + i;
+            for (int i = 0; i < 4; ++i) {
+                const int ci = g * 4 + i;
                 code[i] = 0;
                 if (ci < V * V && ci != AGENT_CI) {
                     const int vx = ci / V, vy = ci % V;
@@ -994,35 +858,18 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
                 }
             }
 #pragma unroll
-            for (int i = 0; i < GB * 4; ++i) {
-                const int ci = g0 * 4 + i;
+            for (int i = 0; i < 4; ++i) {
+                const int ci = g * 4 + i;
                 x[i] = 0;
-#if MGB_LUT_CONST
-                if (ci < V * V) x[i] = (ci == AGENT_CI) ? own : c_lut24[code[i]];
-#else
                 if (ci < V * V) x[i] = (ci == AGENT_CI) ? own : lut_ld(lut_sa, code[i]);
-#endif
             }
-#pragma unroll
-            for (int gg = 0; gg < GB; ++gg) {
-                const int g = g0 + gg;
-                if (g >= NG) continue;
-                const uint32_t *y = &x[gg * 4];
-#if MGB_PACK_IMAD_SEE
-                emit(g * 3, y[1] * m24 + y[0]);                                   // x0.b0 x0.b1 x0.b2 x1.b0
-                if (g * 3 + 1 <= FW + 1) emit(g * 3 + 1, y[2] * m16 + __umulhi(y[1], m24));   // x1.b1 x1.b2 x2.b0 x2.b1
-                if (g * 3 + 2 <= FW + 1) emit(g * 3 + 2, y[3] * m8 + __umulhi(y[2], m16));    // x2.b2 x3.b0 x3.b1 x3.b2
-#else
-                emit(g * 3, __byte_perm(y[0], y[1], 0x4210));                              // x0.b0 x0.b1 x0.b2 x1.b0
-                if (g * 3 + 1 <= FW + 1) emit(g * 3 + 1, __byte_perm(y[1], y[2], 0x5421));     // x1.b1 x1.b2 x2.b0 x2.b1
-                if (g * 3 + 2 <= FW + 1) emit(g * 3 + 2, __byte_perm(y[2], y[3], 0x6542));     // x2.b2 x3.b0 x3.b1 x3.b2
-#endif
-            }
+            emit(g * 3, __byte_perm(x[0], x[1], 0x4210));                              // x0.b0 x0.b1 x0.b2 x1.b0
+            if (g * 3 + 1 <= FW + 1) emit(g * 3 + 1, __byte_perm(x[1], x[2], 0x5421));     // x1.b1 x1.b2 x2.b0 x2.b1
+            if (g * 3 + 2 <= FW + 1) emit(g * 3 + 2, __byte_perm(x[2], x[3], 0x6542));     // x2.b2 x3.b0 x3.b1 x3.b2
         }
-    } else if (MGB_OCC_REGS) {
-        // Register-held variant: (A) all V*V cell + LUT loads, independent of each other, into registers in output
-        // order; (B) the flood on the V row masks, invisible cells zeroed in place; (C) the streaming pack of the
-        // see-through path.  No 38-word accumulator, half the PRMTs, and the loads do not wait for the flood.
+    } else {
+        // (A) all V*V cell + LUT loads, independent of each other, into registers in output order; (B) the flood on
+        // the V row masks, invisible cells zeroed in place; (C) the streaming pack of the see-through path.
         uint32_t xs[V * V + 3], opq[V];
         xs[V * V] = xs[V * V + 1] = xs[V * V + 2] = 0;
 #pragma unroll
@@ -1032,33 +879,23 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
             for (int vx = V - 1; vx >= 0; --vx) code[vx] = lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa));
             uint32_t o = 0;
 #pragma unroll
-            for (int vx = V - 1; vx >= 0; --vx) {                         // descending: Horner
-#if MGB_OCC_REGS == 1
-                uint32_t oq;
-                lut_ld2(lut_sa, code[vx], xs[vx * V + vy], oq);
-                o = o * p.m2 + oq;                                        // FMA pipe
-#else
+            for (int vx = V - 1; vx >= 0; --vx) {
                 // one 32-bit word per cell: 24-bit encoding + "opaque" in bit 31 (never selected by the PRMTs below)
                 uint32_t a;
                 asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code[vx]), "r"(lut_sa + 4u), "n"(LUT_PITCH_OCC * 4));
                 const uint32_t x = lds_u32(a);
                 xs[vx * V + vy] = x;
-#if MGB_OCC_REGS == 2
                 o = __funnelshift_l(x, o, 1);                             // (o << 1) | (x >> 31)
-#else
-                asm("mad.hi.u32 %0, %1, %2, %0;" : "+r"(o) : "r"(x), "r"(p.m2 << vx));   // + (x >> (31 - vx)): bits 24..30 of x are 0
-#endif
-#endif
             }
             opq[vy] = o;
         }
         xs[AGENT_CI] = own;
-#if MGB_FLOOD_SYM
-        // Both sweeps of a row with one carry chain: the word holds the row in bits 0..V-1 and, bit-reversed, in bits
-        // 31..32-V, so the "towards higher bits" fill of flood_up runs up the row in the low field and down the row in
-        // the high field at once; or-ing the word with its own reversal merges the two.  The sweeps of process_vis
-        // compute the closure of "a visible see-through cell shows both neighbours", which is the union of the two fills.
-        // Bits 7 and 24 collect carries / shifted-out seeds; no mask has them and no test reads them.
+        // Both sweeps of a row (process_vis, minigrid.py:617-648) with one carry chain: the word holds the row in bits
+        // 0..V-1 and, bit-reversed, in bits 31..32-V, so the "towards higher bits" fill ((v&t)+t)^t runs up the row in
+        // the low field and down the row in the high field at once; or-ing the word with its own reversal merges the two.
+        // The sweeps compute the closure of "a visible see-through cell shows both neighbours", which is the union of the
+        // two fills (tests/test_kernel_algebra.py).  Bits V and 31-V collect carries / shifted-out seeds; no mask has
+        // them and no test reads them.
         uint32_t vw = (1u << (V / 2)) | (0x80000000u >> (V / 2));            // mask[(3,6)] = True (minigrid.py:619)
 #pragma unroll
         for (int vy = V - 1; vy >= 0; --vy) {
@@ -1071,19 +908,6 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
 #pragma unroll
             for (int vx = 0; vx < V; ++vx) xs[vx * V + vy] = sel_bit(vis, 1u << vx, xs[vx * V + vy]);
         }
-#else
-        uint32_t rowvis = 1u << (V / 2);                          // mask[(3,6)] = True (minigrid.py:619)
-#pragma unroll
-        for (int vy = V - 1; vy >= 0; --vy) {
-            const uint32_t t = ~opq[vy] & VMASK;
-            const uint32_t f = flood_up<V>(rowvis, t);                       // forward sweep i = 0..5
-            const uint32_t vis = revv<V>(flood_up<V>(revv<V>(f), revv<V>(t)));        // reverse sweep i = 6..1
-            const uint32_t sv = vis & t;
-            rowvis = (sv | (sv << 1) | (sv >> 1)) & VMASK;                // seeds of row vy-1
-#pragma unroll
-            for (int vx = 0; vx < V; ++vx) xs[vx * V + vy] = sel_bit(vis, 1u << vx, xs[vx * V + vy]);
-        }
-#endif
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             const uint32_t *y = &xs[g * 4];
@@ -1091,51 +915,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
             if (g * 3 + 1 <= FW + 1) emit(g * 3 + 1, __byte_perm(y[1], y[2], 0x5421));
             if (g * 3 + 2 <= FW + 1) emit(g * 3 + 2, __byte_perm(y[2], y[3], 0x6542));
         }
-    } else {
-        uint32_t acc[FW + 2];
-#pragma unroll
-        for (int i = 0; i < FW + 2; ++i) acc[i] = 0;
-        uint32_t rowvis = 1u << (V / 2);                          // mask[(3,6)] = True (minigrid.py:619)
-#pragma unroll
-        for (int vy = V - 1; vy >= 0; --vy) {
-            uint32_t xs[V];
-            uint32_t opaque = 0;
-#pragma unroll
-            for (int vx = V - 1; vx >= 0; --vx) {                         // descending: Horner on the FMA pipe
-                uint32_t oq;
-                lut_ld2(lut_sa, lds_u8((uint32_t)min(P[vx] + Q[vy], wall_sa)), xs[vx], oq);
-                opaque = opaque * p.m2 + oq;
-            }
-            const uint32_t t = ~opaque & VMASK;
-            const uint32_t f = flood_up<V>(rowvis, t);                       // forward sweep i = 0..5
-            const uint32_t vis = revv<V>(flood_up<V>(revv<V>(f), revv<V>(t)));        // reverse sweep i = 6..1
-            const uint32_t sv = vis & t;
-            rowvis = (sv | (sv << 1) | (sv >> 1)) & VMASK;                // seeds of row vy-1
-            if (vy == V - 1) xs[V / 2] = own;
-#pragma unroll
-            for (int vx = 0; vx < V; ++vx) {
-#if MGB_PACK_IMAD_OCC
-                if ((vis >> vx) & 1u) {                                   // invisible cells stay (0,0,0)
-                    const uint32_t x = xs[vx];
-                    const int b = 3 * (vx * V + vy), w = b >> 2, sh = b & 3;
-                    if (sh == 0) acc[w] = x * m0 + acc[w];
-                    else if (sh == 1) acc[w] = x * m8 + acc[w];
-                    else if (sh == 2) { acc[w] = x * m16 + acc[w]; acc[w + 1] = __umulhi(x, m16) + acc[w + 1]; }
-                    else { acc[w] = x * m24 + acc[w]; acc[w + 1] = __umulhi(x, m24) + acc[w + 1]; }
-                }
-#else
-                {
-                    const uint32_t x = sel_bit(vis, 1u << vx, xs[vx]);      // invisible cells stay (0,0,0)
-                    const int b = 3 * (vx * V + vy);
-                    put3(b & 3, acc[b >> 2], acc[(b >> 2) + 1], x);
-                }
-#endif
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < FW + 2; ++j) emit(j, acc[j]);
     }
-    if (DELAY && dl) { sw[FW] = h4; sw[FW + 1] = h3; sw[FW + 2] = h2; sw[FW + 3] = h1; }   // words FW-4 .. FW-1
     // the partial last word of lane t-1 shares a 32-bit word with the head of lane t
     const uint32_t tail = (s8 >= 16) ? w37 : w36;
     const uint32_t ptail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
@@ -1155,20 +935,8 @@ __device__ __forceinline__ void bulk_store_wait_all() {
 }
 __device__ __forceinline__ void bulk_copy(void *gptr, const void *sptr, uint32_t bytes) {
     const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sptr);
-#if MGB_OBS_L2_HINT
-    // experiment: L2 eviction priority for the observation stream (1 = evict_first, 2 = evict_last, 3 = no_allocate-like normal)
-    uint64_t pol;
-#if MGB_OBS_L2_HINT == 1
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-#else
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-#endif
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
-                 :: "l"(gptr), "r"(saddr), "r"(bytes), "l"(pol) : "memory");
-#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gptr), "r"(saddr), "r"(bytes) : "memory");
-#endif
 }
 // state block HBM -> shared memory with one bulk copy that signals the warp's mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t mbar_sa, uint32_t count) {
@@ -1231,12 +999,6 @@ __device__ __forceinline__ void load_state_block(uint32_t dst_sa, const uint32_t
     }
     mbar_wait(mbar_sa, phase);
 }
-__device__ __forceinline__ void prefetch_l2(const void *g) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
-}
-__device__ __forceinline__ void prefetch_l2_keep(const void *g) {
-    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(g));
-}
 __device__ __forceinline__ void bulk_commit() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -1246,16 +1008,11 @@ __device__ __forceinline__ void bulk_commit() {
 // ------------------------------------------------------------------------------------------
 // NOTE: no minBlocksPerSM argument on purpose -- with it ptxas spends up to 157 registers/thread and the
 // occupancy loss costs more than it gains (measured: profiles/README.md, A/B table)
-#if MGB_SEE_MIN_BLOCKS
-template <int GEN, bool SEE, int V>
-__global__ void __launch_bounds__(MAX_THREADS, SEE ? MGB_SEE_MIN_BLOCKS : 1) k_rollout(
-#else
 template <int GEN, bool SEE, int V>
 __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
-#endif
     const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    constexpr bool PACKED = MGB_PACKED_ACTIONS == 2 || (MGB_PACKED_ACTIONS == 1 && !SEE);
+    constexpr bool PACKED = !SEE;     // rollouts of the occluded kernels hold 32 steps of actions in 4 registers (see below)
     const DevCfg &c = p.cfg;
     // the warp index goes through a lane-0 broadcast so that ptxas knows it is warp-uniform: everything derived from
     // it (group, staging block, output addresses) then lives in uniform registers and the bulk copies below need no
@@ -1264,13 +1021,13 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
     uint32_t *axis = lut + lut_bytes<SEE>() / 4;                                           // [2][AXIS_ENTRIES]
     uint8_t *stage_base = smem_raw + table_bytes<SEE>();
-    constexpr int SB = stage_bytes(V), OB = obs_bytes(V);
+    constexpr int SB = stage_bytes(V), OB = obs_bytes(V), SB_OBS = GROUP * OB;
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * SB);
     uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + wpb * SB) + warp * ((c.S + 1) * 32);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const uint32_t le = lut_entry(i);
         lut[i * lut_pitch<SEE>()] = le & 0x00FFFFFFu;
-        if (!SEE) lut[i * lut_pitch<SEE>() + 1] = MGB_OCC_REGS >= 2 ? (le & 0x00FFFFFFu) | (((le >> 24) & F_OPAQUE) << 31) : (le >> 24) & F_OPAQUE;
+        if (!SEE) lut[i * lut_pitch<SEE>() + 1] = (le & 0x00FFFFFFu) | (((le >> 24) & F_OPAQUE) << 31);
         lut[i * lut_pitch<SEE>() + lut_fw<SEE>()] = le;
     }
     for (int i = threadIdx.x; i < AXIS_ENTRIES; i += blockDim.x) {
@@ -1279,14 +1036,9 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
         axis[AXIS_ENTRIES + i] = ((unsigned)v < (unsigned)c.H) ? (uint32_t)(((v >> 2) << 7) + (v & 3)) : (uint32_t)wall;   // y: word + byte
     }
     const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(axis + 2 * AXIS_ENTRIES) + (uint32_t)warp * 8u;
-    if (MGB_BULK_STATE && lane == 0) mbar_init(mbar_sa, 1);
+    if (lane == 0) mbar_init(mbar_sa, 1);
     __syncthreads();
 
-#if MGB_STAGGER
-    // experiment: start the resident warps of an SM at different phases of the step so that they do not all sit in the
-    // load-heavy gather (or the ALU-heavy pack) at the same time
-    if (p.T > 1) __nanosleep((uint32_t)(((blockIdx.x & 3) * wpb + warp) * MGB_STAGGER));
-#endif
     const int S = c.S, GW = c.GW;
     const int64_t stride = p.stride;
     uint32_t phase = 0;
@@ -1303,12 +1055,8 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
         const bool afast = ((p.stride & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.actions) & 15) == 0) && ((int64_t)group * 32 + 32 <= p.n_envs);
         if (PACKED && p.T > 1) actions_issue(arow, arow_p, lane < p.T, afast);
         // ---- load the group's state block: S coalesced 128-byte rows -> bank == lane ----
-        if (MGB_BULK_STATE == 1 || (MGB_BULK_STATE == 2 && p.T <= 1)) {
-            load_state_block((uint32_t)__cvta_generic_to_shared(st_warp), p.state + (size_t)group * S * 32, (uint32_t)S * 128u, mbar_sa, phase, lane);
-            phase ^= 1u;
-        } else {
-            for (int k = 0; k < S; ++k) st_warp[k * 32 + lane] = gst[k * 32];
-        }
+        load_state_block((uint32_t)__cvta_generic_to_shared(st_warp), p.state + (size_t)group * S * 32, (uint32_t)S * 128u, mbar_sa, phase, lane);
+        phase ^= 1u;
         st_warp[S * 32 + lane] = (uint32_t)CODE_WALL * 0x01010101u;        // out-of-grid pad (minigrid.py:469)
         Env e;
         Rng rg;
@@ -1343,19 +1091,6 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
             if (m) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }   // copy-in/out keeps e, rg in registers
         }
         const int nsteps = p.T > 0 ? p.T : 1;
-#if MGB_PREFETCH_ACTIONS
-        // The group's actions (row t = 32 bytes at actions + t*stride + group*32) are pulled into L2 up front and
-        // marked evict_last, so that the per-step loads below are L2 hits (~0.3 us) instead of HBM reads queued behind
-        // the output stream (~1 us): the first instruction after the transition shares a scoreboard with that load and
-        // waited for it on every step (15 % of the see-through kernel's stall samples).
-        if (MGB_PREFETCH_ACTIONS == 1 && p.T > 1) {
-            const uint8_t *arow = p.actions + (int64_t)group * 32;
-            for (int tt = lane; tt < p.T; tt += 32) {
-                prefetch_l2_keep(arow + (int64_t)tt * stride);
-                prefetch_l2_keep(arow + (int64_t)tt * stride + 31);
-            }
-        }
-#endif
         int a_next = 0;
         uint32_t aq0 = 0, aq1 = 0, aq2 = 0, aq3 = 0;
         if (PACKED) {
@@ -1365,7 +1100,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
         // loop invariants spelled out: ptxas otherwise re-derives them from the parameter bank on every step
         // (69 of the occluded kernel's 880 instructions per step were this bookkeeping).  HOIST is off for the
         // see-through kernels: at their 64 registers the extra live values cost more than the bookkeeping (measured -4 %).
-        constexpr bool HOIST = MGB_HOIST == 2 || (MGB_HOIST == 1 && !SEE);
+        constexpr bool HOIST = !SEE;
         const bool stepping = p.T > 0, multi = PACKED && p.T > 1;
         const bool w_rew = valid && stepping && p.reward != nullptr, w_done = valid && stepping && p.done != nullptr;
         const bool w_dir = valid && p.dir != nullptr;
@@ -1376,7 +1111,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
             double reward = 0.0; bool done = false;
             if (!HOIST) {
                 o = (int64_t)t * stride + lid;
-                gobs = p.obs ? p.obs + (MGB_EXP_OBS_WRAP ? (int64_t)(group & 1023) * 32 * OB : ((int64_t)t * stride + (int64_t)group * 32) * OB) : nullptr;
+                gobs = p.obs ? p.obs + ((int64_t)t * stride + (int64_t)group * 32) * OB : nullptr;
             }
             if (HOIST ? stepping : p.T > 0) {
                 if (HOIST ? multi : (PACKED && p.T > 1)) {
@@ -1390,17 +1125,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
                     aq0 = __funnelshift_r(aq0, aq1, 4); aq1 = __funnelshift_r(aq1, aq2, 4); aq2 = __funnelshift_r(aq2, aq3, 4); aq3 >>= 4;
                 }
                 const int action = a_next;
-#if MGB_PREFETCH_ACTIONS >= 2
-                // row t+D of the group's actions -> L2, D steps (~3 us each) ahead of the load that needs it
-                if (t + MGB_PREFETCH_DIST < p.T) {
-                    const uint8_t *arow = p.actions + (int64_t)(t + MGB_PREFETCH_DIST) * stride + (int64_t)group * 32;
-                    if (MGB_PREFETCH_ACTIONS == 2) { prefetch_l2(arow); prefetch_l2(arow + 31); }
-                    else { prefetch_l2_keep(arow); prefetch_l2_keep(arow + 31); }
-                }
-#endif
-#if !MGB_LATE_PREFETCH
                 if (!PACKED && t + 1 < p.T && valid) a_next = p.actions[(int64_t)(t + 1) * stride + lid];
-#endif
                 if (GEN == GEN_DYNOBS) {                        // the staging block doubles as the draw window
                     if (lane == 0) bulk_store_wait_read();
                     __syncwarp();
@@ -1427,39 +1152,18 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
                 }
                 if (need_reset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
             }
-#if MGB_LATE_PREFETCH
-            // The next action is requested here, after the transition and the (cold) reset path have merged: ptxas
-            // puts this load on the same scoreboard as the local-memory reloads that follow the out-of-line generator
-            // call, so a load issued before the transition made the first instruction after the merge wait for the
-            // full HBM latency on every step (7 % of all stall samples).  The observation below covers the latency.
-            if (p.T > 0 && t + 1 < p.T && valid) a_next = ldg_u8(p.actions + (int64_t)(t + 1) * stride + lid);
-#endif
             if (gobs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
                 __syncwarp();
-                observe<SEE, V, MGB_STAGE_DELAY && SEE && V == 7 && GEN != GEN_DYNOBS && !MGB_STAGE_SEG>(st, e, p, lut, stage_w, lane);
+                observe<SEE, V>(st, e, p, lut, stage_w, lane);
                 if (full && ((reinterpret_cast<uintptr_t>(gobs) & 15) == 0)) {
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) {                              // one bulk copy per segment, one commit group
-#pragma unroll
-                        for (int k = 0; k < stage_nseg(V); ++k) {
-                            const int w0 = (stage_seg_lane(V, k) * OB) >> 2, w1 = (stage_seg_lane(V, k + 1) * OB) >> 2;
-                            if (!MGB_EXP_NO_OBS_STORE) bulk_copy(gobs + 4 * w0, stage_w + w0 + STAGE_SEG_WORDS * k, 4u * (uint32_t)(w1 - w0));
-                        }
-                        bulk_commit();
-                    }
+                    if (lane == 0) { bulk_copy(gobs, stage_w, (uint32_t)SB_OBS); bulk_commit(); }
                 } else {                                         // ragged tail group / unaligned base
                     __syncwarp();
                     const uint8_t *sb = reinterpret_cast<const uint8_t *>(stage_w);
-                    for (int b = lane; b < nvalid * OB; b += 32) {
-                        int sh = 0;
-                        if (stage_nseg(V) > 1) {
-#pragma unroll
-                            for (int k = 1; k < stage_nseg(V); ++k) sh += b >= ((stage_seg_lane(V, k) * OB) & ~3) ? STAGE_SEG_WORDS * 4 : 0;
-                        }
-                        gobs[b] = sb[b + sh];
-                    }
+                    for (int b = lane; b < nvalid * OB; b += 32) gobs[b] = sb[b];
                     __syncwarp();
                 }
                 if (HOIST) gobs += obs_pitch;
@@ -1485,7 +1189,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
         if (GEN == GEN_POOL) st[(GW + XWORDS) * 32] = (uint32_t)pc.level;
         const bool any_dirty = __any_sync(0xFFFFFFFFu, e.dirty);
         const int k0 = any_dirty ? 0 : GW;                            // an untouched grid stays where it is
-        if (MGB_BULK_STATE == 1 && MGB_BULK_WB && (any_dirty || p.T > 1)) {      // a clean single step writes 4-5 rows: the loop is cheaper
+        if (any_dirty || p.T > 1) {      // a clean single step writes 4-5 rows: the loop is cheaper
             // one bulk copy (rows k0..S-1 are contiguous here and in HBM) instead of a 7-instruction loop per word;
             // load_state_block waits for it to have left shared memory before the block is reused
             fence_proxy_async();

@@ -82,20 +82,6 @@ def test_rows_chain_like_process_vis():
             v_ref = want_up                       # vis_mask[., j-1] starts as what row j set (minigrid.py:631-633)
 
 
-def test_stage_delay_mask_makes_start_banks_a_permutation():
-    """MGB_STAGE_DELAY: lanes of STAGE_DELAY_MASK store word j-4 at instruction j; with it the 32 start banks of the
-    147-byte records are pairwise different (without it lanes {0,27}, {2,29}, {3,30}, {4,31} collide)."""
-    import os
-    import re
-    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gym_minigrid_b200", "csrc", "mgb_kernels.cuh")).read()
-    mask = int(re.search(r"STAGE_DELAY_MASK\s*=\s*(0x[0-9a-fA-F]+)u", src).group(1), 16)
-    q = [(lane * 147) >> 2 for lane in range(32)]
-    plain = [w % 32 for w in q]
-    assert len(set(plain)) == 28
-    delayed = [(q[lane] - (4 if (mask >> lane) & 1 else 0)) % 32 for lane in range(32)]
-    assert sorted(delayed) == list(range(32))
-
-
 def test_packed_action_nibbles_round_trip():
     """the occluded kernels hold 32 steps of actions as 4-bit fields, clamped to 15 (still invalid: n_actions <= 9),
     and shift them out one per step with three funnel shifts"""
