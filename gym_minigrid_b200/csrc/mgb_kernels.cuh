@@ -176,6 +176,16 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
+// The env's random stream ("RNG"): Philox4x32-10, key = seed, counter = (block, episode, global env id).
+// Every 32-bit output word serves TWO consecutive draws: draw n takes word (n>>1)&3 of block n>>3, as it is for even n
+// and multiplied by DRAW_ODD_MULT (2^32 / golden ratio, odd: a bijection of the 32-bit words) for odd n.  The pair
+// (w, w*M) is the 2-D lattice of a multiplicative congruential generator with a good multiplier, so two consecutive
+// bounded draws (the x and the y of a placement try) are jointly uniform far below the resolution any span here needs
+// (span_x * span_y <= 2^12 against 2^32 lattice points; tests/test_host_logic.py checks the joint histogram).  This
+// halves the Philox work of Dynamic-Obstacles, whose rejection sampling draws ~21 numbers per env-step.
+constexpr uint32_t DRAW_ODD_MULT = 0x9E3779B1u;
+__device__ __forceinline__ uint32_t draw_word(uint32_t w, uint32_t n) { return (n & 1u) ? w * DRAW_ODD_MULT : w; }
+
 // MiniGridEnv._rand_int (minigrid.py:939-944): low + mulhi32(u32, high-low) on the stream
 // (seed, global env id, episode); or the next tape entry in RNG-tape mode.
 __device__ __forceinline__ int rand_int_inl(Rng &e, const RolloutParams &p, int low, int high) {
@@ -186,14 +196,14 @@ __device__ __forceinline__ int rand_int_inl(Rng &e, const RolloutParams &p, int 
         if (v < low || v >= high) e.err |= ERR_TAPE_RANGE;
         return v;
     }
-    const uint32_t blk = e.ndraws >> 2;
+    const uint32_t blk = e.ndraws >> 3;
     if (blk != e.rblk) {
         philox4x32_10(blk, e.episode - 1u, (uint32_t)e.gid, (uint32_t)((uint64_t)e.gid >> 32),
                       (uint32_t)p.seed, (uint32_t)(p.seed >> 32), e.rb0, e.rb1, e.rb2, e.rb3);
         e.rblk = blk;
     }
-    const uint32_t sel = e.ndraws & 3;
-    const uint32_t u = sel == 0 ? e.rb0 : sel == 1 ? e.rb1 : sel == 2 ? e.rb2 : e.rb3;
+    const uint32_t sel = (e.ndraws >> 1) & 3;
+    const uint32_t u = draw_word(sel == 0 ? e.rb0 : sel == 1 ? e.rb1 : sel == 2 ? e.rb2 : e.rb3, e.ndraws);
     e.ndraws++;
     return low + (int)__umulhi(u, (uint32_t)(high - low));
 }
@@ -202,18 +212,29 @@ __device__ __noinline__ int rand_int(Rng &e, const RolloutParams &p, int low, in
     return rand_int_inl(e, p, low, high);
 }
 
-// Dynamic-Obstacles consumes ~2 draws per ball try, ~20-60 draws per step.  Instead of computing a Philox
-// block inside the (divergent) try loop, a lane pre-computes DRAW_BLOCKS consecutive blocks of its stream
-// in straight-line code (all lanes active, independent chains -> ILP) into its column of the warp's
-// staging buffer, which is idle between two observations.  word i of the window at draws[i*32].
-// blocks that fit the staging column of a lane (3*V*V/4 words): 9 blocks = 36 draws = 18 tries for V = 7
+// Dynamic-Obstacles consumes 2 draws (one stream word) per ball try, ~11 tries per step.  Instead of computing a Philox
+// block inside the (divergent) try loop, a lane pre-computes DYN_BLOCKS consecutive blocks of its stream in
+// straight-line code (all lanes active, independent chains -> ILP) into its column of the warp's staging buffer,
+// which is idle between two observations.  Word i of the window at draws[i*32]; 5 blocks = 20 words = 20 tries
+// (P(a step needs more) ~ 1e-3 per env; those continue on demand).  Small views have a shorter staging column.
 #ifndef MGB_DYN_BLOCKS
-#define MGB_DYN_BLOCKS 9
+#define MGB_DYN_BLOCKS 5
 #endif
-__host__ __device__ constexpr int draw_blocks(int V) { return (3 * V * V / 4) / 4 < MGB_DYN_BLOCKS ? (3 * V * V / 4) / 4 : MGB_DYN_BLOCKS; }
+#ifndef MGB_DYN_ROLLED
+#define MGB_DYN_ROLLED 0       // experiment: Philox blocks of the window in a rolled loop (code size)
+#endif
+#ifndef MGB_DYN_HOIST
+#define MGB_DYN_HOIST 0        // experiment: step-loop invariants in registers for the Dynamic-Obstacles kernel too
+#endif
+constexpr int DYN_BLOCKS = MGB_DYN_BLOCKS;
+__host__ __device__ constexpr int draw_blocks(int V) { return (3 * V * V / 4) / 4 < DYN_BLOCKS ? (3 * V * V / 4) / 4 : DYN_BLOCKS; }
 template <int NB>
 __device__ __noinline__ void prefetch_draws(uint32_t *draws, uint32_t first_block, uint32_t stream, int64_t gid, uint64_t seed) {
+#if MGB_DYN_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int j = 0; j < NB; ++j) {
         uint32_t o0, o1, o2, o3;
         philox4x32_10(first_block + j, stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1, o2, o3);
@@ -464,15 +485,10 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
 // succeeds), so the first DYN_SPEC tries are evaluated speculatively in straight-line code -- independent loads,
 // no branches -- and the first valid one wins; a lane whose DYN_SPEC tries all failed (p ~ 0.25^4) or whose draw
 // window is nearly used up continues one try at a time in a (divergent, rare) loop, computing Philox blocks on demand
-// once it runs past the prefetched window.
-#ifndef MGB_DYN_UNROLL
-#define MGB_DYN_UNROLL 1       // unroll factor of the per-ball loop of dynobs_move
-#endif
-#ifndef MGB_DYN_SPEC
-#define MGB_DYN_SPEC 4
-#endif
-constexpr int DYN_SPEC = MGB_DYN_SPEC;
-constexpr int DYN_UNROLL = MGB_DYN_UNROLL;
+// once it runs past the prefetched window.  A try is one stream word when the draw counter is even (x from the word,
+// y from the word times DRAW_ODD_MULT); after an odd number of draws (the -Random- ids: place_agent's direction draw)
+// it straddles two words.
+constexpr int DYN_SPEC = 4;
 // byte offset of grid cell (x,y) inside a lane's column: word x*HP/4 + (y>>2) at pitch 128, byte y&3
 __device__ __forceinline__ uint32_t cell_off(int x, int y, int HP) { return (uint32_t)(x * (HP * 32) + y + (y >> 2) * 124); }
 
@@ -480,36 +496,44 @@ template <int V>
 __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, uint32_t *draws) {
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP, nob = c.n_obst;
-    constexpr uint32_t WIN = 4 * draw_blocks(V);                  // draws in the window
-    const uint32_t wbase = rg.ndraws & ~3u;                       // draw index of draws[0]
-    prefetch_draws<draw_blocks(V)>(draws, wbase >> 2, rg.episode - 1u, rg.gid, p.seed);
+    constexpr uint32_t WINW = 4 * draw_blocks(V);                 // words (= aligned tries) in the window
+    const uint32_t wbase = rg.ndraws & ~7u;                       // draw index of draws[0]
+    prefetch_draws<draw_blocks(V)>(draws, wbase >> 3, rg.episode - 1u, rg.gid, p.seed);
     rg.rblk = 0xFFFFFFFFu;
     uint32_t nd = rg.ndraws;
+    const uint32_t par = nd & 1u;                                 // every try takes two draws: the parity holds for the step
     const uint32_t st_sa = (uint32_t)__cvta_generic_to_shared(st);
     const uint32_t dr_sa = (uint32_t)__cvta_generic_to_shared(draws);
-    const uint32_t ob_sa = st_sa + (uint32_t)(c.GW + XWORDS) * 128u;   // obstacle k: 16 bits at ob_sa + (k>>1)*128 + (k&1)*2
+    uint32_t ob_p = st_sa + (uint32_t)(c.GW + XWORDS) * 128u;    // obstacle k: 16 bits at +(k>>1)*128 + (k&1)*2
+    const int XP = HP * 32;                                       // bytes between two grid columns of a lane
     // "not where the agent is" (minigrid.py:1044): an empty cell under the agent is made non-empty for the duration
     // of the moves, so that a try is valid iff its cell is empty
     const uint32_t ag_sa = st_sa + cell_off(e.ax, e.ay, HP);
     const bool ag_mark = lds_u8(ag_sa) == CODE_EMPTY;
     if (ag_mark) sts_u8(ag_sa, CODE_WALL);
-#pragma unroll DYN_UNROLL
     for (int k = 0; k < nob; ++k) {
-        const uint32_t opos = lds_u16(ob_sa + (uint32_t)((k >> 1) * 128 + (k & 1) * 2));
+        const uint32_t opos = lds_u16(ob_p);
         const int ox = (int)(opos & 0xFF), oy = (int)(opos >> 8);
         const int tx = max(ox - 1, 0), ty = max(oy - 1, 0);
         const uint32_t sx = (uint32_t)(min(tx + 3, W) - tx), sy = (uint32_t)(min(ty + 3, H) - ty);
-        const uint32_t wi = nd - wbase;
-        const bool spec = wi + 2 * DYN_SPEC <= WIN;               // all speculative draws are inside the window
+        const uint32_t colb = st_sa + (uint32_t)(tx * XP);        // column tx of the lane's grid
+        const uint32_t wi = (nd - wbase) >> 1;                    // window word of draw nd
+        const bool spec = wi + DYN_SPEC + par <= WINW;            // all speculative draws are inside the window
         const uint32_t wa = dr_sa + (spec ? wi : 0u) * 128u;
+        uint32_t w[DYN_SPEC + 1];
+#pragma unroll
+        for (int j = 0; j <= DYN_SPEC; ++j) w[j] = lds_u32(wa + j * 128);     // word DYN_SPEC is only used when par
         int sel = -1;
-        uint32_t npos = 0;
+        uint32_t npos = 0, nsa = 0;
 #pragma unroll
         for (int j = DYN_SPEC - 1; j >= 0; --j) {                 // descending: the lowest valid try overwrites
-            const int x = tx + (int)__umulhi(lds_u32(wa + (2 * j) * 128), sx);
-            const int y = ty + (int)__umulhi(lds_u32(wa + (2 * j + 1) * 128), sy);
+            const uint32_t wm = w[j] * DRAW_ODD_MULT;
+            const uint32_t ux = par ? wm : w[j], uy = par ? w[j + 1] : wm;
+            const int dx = (int)__umulhi(ux, sx);
+            const int y = ty + (int)__umulhi(uy, sy);
+            const uint32_t sa = colb + (uint32_t)(dx * XP) + (uint32_t)(y + (y >> 2) * 124);
             // the ball's own cell counts as occupied: it must move (minigrid.py:1040-1041)
-            if (lds_u8(st_sa + cell_off(x, y, HP)) == CODE_EMPTY) { sel = j; npos = (uint32_t)(x | (y << 8)); }
+            if (lds_u8(sa) == CODE_EMPTY) { sel = j; npos = (uint32_t)(dx | (y << 8)); nsa = sa; }
         }
         bool placed = spec && sel >= 0;
         int tries = 0;
@@ -518,24 +542,28 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
             while (tries <= 100) {                                // place_obj(max_tries=100) makes 101 tries (:1028-1031)
                 tries++;
                 int x, y;
-                if (nd - wbase + 2 <= WIN) {
-                    x = tx + (int)__umulhi(lds_u32(dr_sa + (nd - wbase) * 128), sx);
-                    y = ty + (int)__umulhi(lds_u32(dr_sa + (nd - wbase + 1) * 128), sy);
+                if (((nd - wbase + 1) >> 1) < WINW) {             // both draws are inside the window
+                    const uint32_t a = dr_sa + ((nd - wbase) >> 1) * 128u;
+                    const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 128u);
+                    x = tx + (int)__umulhi(par ? w0 * DRAW_ODD_MULT : w0, sx);
+                    y = ty + (int)__umulhi(par ? w1 : w0 * DRAW_ODD_MULT, sy);
                 } else {
                     rg.ndraws = nd;
                     x = rand_int_inl(rg, p, tx, tx + (int)sx);
                     y = rand_int_inl(rg, p, ty, ty + (int)sy);
                 }
                 nd += 2;
-                if (lds_u8(st_sa + cell_off(x, y, HP)) == CODE_EMPTY) { placed = true; npos = (uint32_t)(x | (y << 8)); break; }
+                const uint32_t sa = st_sa + cell_off(x, y, HP);
+                if (lds_u8(sa) == CODE_EMPTY) { placed = true; npos = (uint32_t)((x - tx) | (y << 8)); nsa = sa; break; }
             }
         }
         if (placed) {                                             // a failed placement (RecursionError, swallowed) leaves the ball
             const uint32_t old_sa = st_sa + cell_off(ox, oy, HP);
-            sts_u8(st_sa + cell_off((int)(npos & 0xFF), (int)(npos >> 8), HP), lds_u8(old_sa));
+            sts_u8(nsa, lds_u8(old_sa));
             sts_u8(old_sa, CODE_EMPTY);
-            sts_u16(ob_sa + (uint32_t)((k >> 1) * 128 + (k & 1) * 2), npos);
+            sts_u16(ob_p, npos + (uint32_t)tx);
         }
+        ob_p += (k & 1) ? 126u : 2u;
     }
     if (ag_mark) sts_u8(ag_sa, CODE_EMPTY);
     rg.ndraws = nd;
@@ -570,7 +598,7 @@ __device__ __noinline__ void dynobs_move_tape(uint32_t *st, Env &e, Rng &rg, con
 // the warp's state block: agent at (1,1) facing right (or place_agent() for the -Random- ids), then n_obstacles times
 // place_obj(Ball(), max_tries=100) over the whole grid.  With a uniform random policy an episode lasts ~12 steps, so
 // nearly every warp-step has a lane or two that must reset; doing that inside one lane stalls the other 30.  Here
-// lane t evaluates try t of the new episode's stream (draws 2t, 2t+1: half of Philox block t>>1).  place_obj accepts
+// lane t evaluates try t of the new episode's stream (draws 2t, 2t+1: word t&3 of Philox block t>>2).  place_obj accepts
 // a try iff its cell is free in the static layout, is not the agent's, and does not hold an earlier ball -- i.e. iff
 // it is free and the first try with that position (an earlier try with the same position was either not free, and
 // then neither is this one, or was itself accepted).  So: ballot(free), match_any(position) for "first with that
@@ -589,9 +617,10 @@ __device__ __forceinline__ bool dynobs_coop_reset(uint32_t *st_warp, int src, in
     }
     __syncwarp();
     uint32_t o0, o1, o2, o3;
-    philox4x32_10((uint32_t)(lane >> 1), stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32),
+    philox4x32_10((uint32_t)(lane >> 2), stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32),
                   o0, o1, o2, o3);
-    const uint32_t ux = (lane & 1) ? o2 : o0, uy = (lane & 1) ? o3 : o1;          // draws 2*lane, 2*lane+1
+    const uint32_t wl = (lane & 2) ? ((lane & 1) ? o3 : o2) : ((lane & 1) ? o1 : o0);      // stream word `lane`
+    const uint32_t ux = wl, uy = wl * DRAW_ODD_MULT;                                     // draws 2*lane, 2*lane+1
     auto static_free = [&](int x, int y) { const int i = x * HP + y; return ((__ldg(&p.tmpl[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) == CODE_EMPTY; };
     const uint32_t lt = (1u << lane) - 1u;
     int x = (int)__umulhi(ux, (uint32_t)c.W), y = (int)__umulhi(uy, (uint32_t)c.H);
@@ -1100,7 +1129,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
         // loop invariants spelled out: ptxas otherwise re-derives them from the parameter bank on every step
         // (69 of the occluded kernel's 880 instructions per step were this bookkeeping).  HOIST is off for the
         // see-through kernels: at their 64 registers the extra live values cost more than the bookkeeping (measured -4 %).
-        constexpr bool HOIST = !SEE;
+        constexpr bool HOIST = !SEE || (MGB_DYN_HOIST && GEN == GEN_DYNOBS);
         const bool stepping = p.T > 0, multi = PACKED && p.T > 1;
         const bool w_rew = valid && stepping && p.reward != nullptr, w_done = valid && stepping && p.done != nullptr;
         const bool w_dir = valid && p.dir != nullptr;

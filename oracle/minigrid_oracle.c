@@ -240,6 +240,7 @@ struct orc_vec {
     int *pool_hook;      /* [pool_n][16] or NULL */
 };
 
+#define ORC_DRAW_ODD_MULT 0x9E3779B1u
 static int rand_int(Env *e, int low, int high) {   /* minigrid.py:939-944 */
     if (e->tape) {
         if ((int64_t)e->ndraws >= e->tape_len) { e->err |= 2; return low; }
@@ -247,12 +248,14 @@ static int rand_int(Env *e, int low, int high) {   /* minigrid.py:939-944 */
         if (v < low || v >= high) e->err |= 4;
         return v;
     }
-    /* stream id = index of the current episode = (#resets so far) - 1 */
-    uint32_t ctr[4] = { e->ndraws >> 2, e->episode - 1u, (uint32_t)e->env_id, (uint32_t)((uint64_t)e->env_id >> 32) };
+    /* stream id = index of the current episode = (#resets so far) - 1.  Every Philox word serves two consecutive
+     * draws: draw n = word (n>>1)&3 of block n>>3, multiplied by ORC_DRAW_ODD_MULT when n is odd (DESIGN.md "RNG") */
+    uint32_t ctr[4] = { e->ndraws >> 3, e->episode - 1u, (uint32_t)e->env_id, (uint32_t)((uint64_t)e->env_id >> 32) };
     uint32_t key[2] = { (uint32_t)e->seed, (uint32_t)(e->seed >> 32) };
     uint32_t out[4];
     orc_philox4x32_10(ctr, key, out);
-    uint32_t u = out[e->ndraws & 3];
+    uint32_t u = out[(e->ndraws >> 1) & 3];
+    if (e->ndraws & 1) u *= ORC_DRAW_ODD_MULT;
     e->ndraws++;
     return low + (int)(((uint64_t)u * (uint32_t)(high - low)) >> 32);
 }

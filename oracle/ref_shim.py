@@ -248,9 +248,12 @@ def philox4x32_10(ctr, key):
 class PhiloxShim:
     """Assigned to ``env.np_random`` of a reference env *after* construction.
 
-    Stream = (seed, global env id, episode); draw n uses word n&3 of block
-    n>>2; ``randint(low, high) = low + mulhi32(u32, high-low)``.
+    Stream = (seed, global env id, episode).  Every Philox word serves two consecutive draws: draw n uses word
+    (n>>1)&3 of block n>>3, as it is for even n and times DRAW_ODD_MULT (mod 2^32) for odd n;
+    ``randint(low, high) = low + mulhi32(u32, high-low)``.
     """
+
+    DRAW_ODD_MULT = 0x9E3779B1
 
     def __init__(self, seed, env_id, episode=0):
         self.key = (seed & _MASK, (seed >> 32) & _MASK)
@@ -266,12 +269,14 @@ class PhiloxShim:
         self._blk_idx = -1
 
     def _u32(self):
-        b = self.ndraws >> 2
+        b = self.ndraws >> 3
         if b != self._blk_idx:
             ctr = (b & _MASK, self.episode & _MASK, self.env_id & _MASK, (self.env_id >> 32) & _MASK)
             self._blk = philox4x32_10(ctr, self.key)
             self._blk_idx = b
-        v = self._blk[self.ndraws & 3]
+        v = self._blk[(self.ndraws >> 1) & 3]
+        if self.ndraws & 1:
+            v = (v * self.DRAW_ODD_MULT) & _MASK
         self.ndraws += 1
         return v
 

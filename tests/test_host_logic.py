@@ -154,3 +154,33 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_two_draws_per_philox_word_are_jointly_uniform():
+    """RNG design (DESIGN.md "RNG"): draw 2i is Philox word i, draw 2i+1 is the same word times DRAW_ODD_MULT mod 2^32.
+    The x and y of a placement try are such a pair: their joint histogram over span_x x span_y cells must be flat
+    (chi-square against the uniform distribution), for the 3x3 window of an obstacle move and for a 16x16 / 19x19 grid."""
+    import numpy as np
+    from oracle.ref_shim import PhiloxShim
+    M = PhiloxShim.DRAW_ODD_MULT
+    assert M % 2 == 1
+    rs = np.random.RandomState(7)
+    w = rs.randint(0, 1 << 32, size=1 << 20, dtype=np.uint64)           # stand-in for Philox words (uniform 32-bit)
+    wm = (w * M) & 0xFFFFFFFF
+    for sx, sy in ((3, 3), (2, 3), (16, 16), (19, 19), (64, 64)):
+        x = (w * sx) >> 32
+        y = (wm * sy) >> 32
+        h = np.bincount((x * sy + y).astype(np.int64), minlength=sx * sy).astype(np.float64)
+        e = len(w) / (sx * sy)
+        chi2 = ((h - e) ** 2 / e).sum()
+        dof = sx * sy - 1
+        assert chi2 < dof + 6 * (2 * dof) ** 0.5, (sx, sy, chi2, dof)        # 6 sigma
+    # and exhaustively on the lattice itself for the 3x3 window: every cell gets 2^32/9 words to within 1e-4
+    u = np.arange(0, 1 << 32, 4099, dtype=np.uint64)                       # a coprime stride: 1M lattice points
+    h = np.bincount((((u * 3) >> 32) * 3 + ((((u * M) & 0xFFFFFFFF) * 3) >> 32)).astype(np.int64), minlength=9)
+    assert abs(h / h.sum() - 1 / 9).max() < 2e-3
+    # the shim itself: consecutive randint(0,3) pairs
+    sh = PhiloxShim(123, 5, 0)
+    pairs = np.array([[sh.randint(0, 3), sh.randint(0, 3)] for _ in range(9000)])
+    hh = np.bincount(pairs[:, 0] * 3 + pairs[:, 1], minlength=9)
+    assert ((hh - 1000.0) ** 2 / 1000.0).sum() < 8 + 6 * 4
