@@ -192,7 +192,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
 #endif
     for (int wpb = MAX_WARPS_PER_BLOCK; wpb >= 2; --wpb) {
         if (force && atoi(force) != wpb) continue;
-        const size_t smem = (size_t)(c.see_through ? table_bytes<true>() : table_bytes<false>()) + (size_t)wpb * per_warp;
+        const size_t smem = (size_t)table_bytes(c.gen) + (size_t)wpb * per_warp;
         if (smem > prop.sharedMemPerBlockOptin) continue;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, wpb * 32, smem) != cudaSuccess || nb < 1) continue;

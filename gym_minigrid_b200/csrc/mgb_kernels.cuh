@@ -38,24 +38,22 @@ constexpr int MAX_OBST = 8;
 constexpr int XWORDS = 4;                        // agent, steps/target, episode, ndraws
 constexpr int OBST_WORDS = 4;                    // 8 x (x,y) bytes
 // CTA-shared tables at the start of dynamic shared memory:
-//   LUT: 256 entries at a 24-byte pitch: word0 = type|colour<<8|state<<16 (the 3 output bytes), word1 = opaque
-//   (0/1), word2 = word0|flags<<24 (transition).  The non-power-of-two pitch is deliberate: code*24+base cannot
-//   be an LEA, so the address is an IMAD on the otherwise idle FMA pipe (the ALU pipe bounds this kernel);
-//   8-byte alignment lets the occluded path fetch word0+word1 with one LDS.64.
-//   AXIS tables: shared-memory offset of grid coordinate v (index v+6) along x and along y, out-of-grid
+//   LUT: 256 entries of one word, code -> type | colour<<8 | state<<16 | flags<<24.  The three low bytes are the cell's
+//   output bytes (no PRMT of the pack ever selects byte 3); "opaque" is bit 7 of the flags, i.e. bit 31 of the word, which
+//   is what the occluded path shifts into its row masks; the transition reads the flags.  Entry pitch: 12 bytes -- the
+//   address code*12+base is then an immediate-form IMAD on the otherwise idle FMA pipe, where a 4-byte pitch becomes an
+//   LEA on the ALU pipe that bounds these kernels (and IMAD with the pitch in a uniform register measured 1.3 % slower
+//   than the immediate form) -- except for the Dynamic-Obstacles kernels, whose resident warps are limited by shared
+//   memory: there the 2 KB saved by a 4-byte pitch buy a 16th warp per SM in two evenly filled 8-warp CTAs.  Any 32
+//   consecutive codes map to 32 different banks at either pitch.
+//   AXIS tables: shared-memory offset of grid coordinate v (index v + AXIS_BIAS) along x and along y, out-of-grid
 //   entries = offset of the wall pad word (see observe()).
-// occluded kernels: [x24, x24|opaque<<31, x24|flags<<24] at pitch 3 (one word per cell for the view gather)
-constexpr int LUT_PITCH_OCC = 3;
-constexpr int LUT_PITCH_SEE = 3;   // see-through kernels: [x24, x24|flags<<24, -]; odd pitch -> any 32 consecutive
-                                   // codes map to 32 different banks (pitch 6 makes codes 16 apart collide,
-                                   // e.g. grey wall 57 / green goal 169 -- the two objects of Empty-8x8)
-template <bool SEE> __host__ __device__ constexpr int lut_pitch() { return SEE ? LUT_PITCH_SEE : LUT_PITCH_OCC; }
-template <bool SEE> __host__ __device__ constexpr int lut_fw() { return SEE ? 1 : 2; }     // word index of the flags word
-template <bool SEE> __host__ __device__ constexpr int lut_bytes() { return 256 * lut_pitch<SEE>() * 4; }    // 3072 (6144 at pitch 6)
+__host__ __device__ constexpr int lut_pitch_words(int gen) { return gen == 3 /* GEN_DYNOBS */ ? 1 : 3; }
+__host__ __device__ constexpr int lut_bytes(int gen) { return 256 * 4 * lut_pitch_words(gen); }
 constexpr int AXIS_ENTRIES = 88;                                 // v in [-(V-1), 64+V-2] for V <= 11: index v + AXIS_BIAS
 constexpr int AXIS_BIAS = 10;
 constexpr int MBAR_BYTES = MAX_WARPS_PER_BLOCK * 8;               // one mbarrier per warp (bulk load of the state block)
-template <bool SEE> __host__ __device__ constexpr int table_bytes() { return (lut_bytes<SEE>() + 2 * AXIS_ENTRIES * 4 + MBAR_BYTES + 127) / 128 * 128; }   // 3840 (6912 at pitch 6)
+__host__ __device__ constexpr int table_bytes(int gen) { return (lut_bytes(gen) + 2 * AXIS_ENTRIES * 4 + MBAR_BYTES + 127) / 128 * 128; }   // 3840 / 1792
 
 // minigrid.py:40-52 / 27-35 / 57-61
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
@@ -77,7 +75,7 @@ static_assert(CODE_EMPTY == 0x15, "EMPTY_WORD");
 enum : int { HOOK_NONE = 0, HOOK_PICKUP_TARGET = 1, HOOK_UNLOCK = 2, HOOK_FETCH = 3, HOOK_GOTODOOR = 4, HOOK_GOTOOBJECT = 5,
              HOOK_PUTNEAR = 6, HOOK_REDBLUEDOORS = 7, HOOK_MEMORY = 8 };
 constexpr int POOL_XW = 5;     // pool record = GW grid words + agent word + 4 hook-parameter words
-enum : uint32_t { F_OPAQUE = 1, F_OVERLAP = 2, F_PICKUP = 4, F_TGOAL = 8, F_LAVA = 16 };
+enum : uint32_t { F_OPAQUE = 0x80, F_OVERLAP = 2, F_PICKUP = 4, F_TGOAL = 8, F_LAVA = 16 };   // F_OPAQUE = bit 31 of the LUT word
 
 // code -> type | colour<<8 | state<<16 | flags<<24   (WorldObj.encode + the predicates
 // can_overlap / can_pickup / see_behind, minigrid.py:93-115,164-166,192-193,211-212,233-250,305-343)
@@ -492,6 +490,45 @@ constexpr int DYN_SPEC = 4;
 // byte offset of grid cell (x,y) inside a lane's column: word x*HP/4 + (y>>2) at pitch 128, byte y&3
 __device__ __forceinline__ uint32_t cell_off(int x, int y, int HP) { return (uint32_t)(x * (HP * 32) + y + (y >> 2) * 124); }
 
+// word `widx` of the stream (seed, gid, stream): word widx&3 of Philox block widx>>2 (cold path: one block per call)
+__device__ __forceinline__ uint32_t stream_word(uint32_t widx, uint32_t stream, int64_t gid, uint64_t seed) {
+    uint32_t o0, o1, o2, o3;
+    philox4x32_10(widx >> 2, stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1, o2, o3);
+    return (widx & 2) ? ((widx & 1) ? o3 : o2) : ((widx & 1) ? o1 : o0);
+}
+
+// Rare continuation of one ball's rejection sampling after the speculative tries (divergent: ~1 lane of a warp in a
+// third of the ball steps), one try at a time, out of line so that the hot loop stays small.  Words come from the
+// prefetched window while they last, from a Philox block computed on the spot after that.  Returns the shared-memory
+// address of the accepted cell, or 0 when place_obj's 101 tries are used up (minigrid.py:1028-1031); nd advances by
+// two draws per try.
+struct MoreTries { uint32_t nsa, npos, nd; };
+__device__ __noinline__ MoreTries dynobs_more_tries(uint32_t st_sa, uint32_t dr_sa, uint32_t wbase, uint32_t winw, uint32_t nd, int tries,
+                                                    int tx, int ty, uint32_t sx, uint32_t sy, int HP, uint32_t stream, int64_t gid, uint64_t seed) {
+    MoreTries r;
+    r.nsa = 0; r.npos = 0;
+    const uint32_t par = nd & 1u;
+    for (; tries <= 100; ++tries) {
+        const uint32_t wi = (nd - wbase) >> 1;                    // window word of draw nd
+        uint32_t w0, w1 = 0;
+        if (wi + par < winw) {
+            w0 = lds_u32(dr_sa + wi * 128u);
+            if (par) w1 = lds_u32(dr_sa + wi * 128u + 128u);
+        } else {
+            w0 = stream_word((wbase >> 1) + wi, stream, gid, seed);
+            if (par) w1 = stream_word((wbase >> 1) + wi + 1u, stream, gid, seed);
+        }
+        nd += 2;
+        const uint32_t wm = w0 * DRAW_ODD_MULT;
+        const int x = tx + (int)__umulhi(par ? wm : w0, sx);
+        const int y = ty + (int)__umulhi(par ? w1 : wm, sy);
+        const uint32_t sa = st_sa + cell_off(x, y, HP);
+        if (lds_u8(sa) == CODE_EMPTY) { r.nsa = sa; r.npos = (uint32_t)(x | (y << 8)); break; }
+    }
+    r.nd = nd;
+    return r;
+}
+
 template <int V>
 __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, uint32_t *draws) {
     const DevCfg &c = p.cfg;
@@ -511,8 +548,12 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
     const uint32_t ag_sa = st_sa + cell_off(e.ax, e.ay, HP);
     const bool ag_mark = lds_u8(ag_sa) == CODE_EMPTY;
     if (ag_mark) sts_u8(ag_sa, CODE_WALL);
+    uint32_t opos = lds_u16(ob_p);
     for (int k = 0; k < nob; ++k) {
-        const uint32_t opos = lds_u16(ob_p);
+        // the next ball's record is fetched now (a move only rewrites the mover's own record): its address arithmetic
+        // overlaps this ball's dependent chain instead of starting after the stores below
+        const uint32_t ob_n = ob_p + ((k & 1) ? 126u : 2u);
+        const uint32_t opos_n = lds_u16(ob_n);                    // k = 7: first bytes of the pad row, unused
         const int ox = (int)(opos & 0xFF), oy = (int)(opos >> 8);
         const int tx = max(ox - 1, 0), ty = max(oy - 1, 0);
         const uint32_t sx = (uint32_t)(min(tx + 3, W) - tx), sy = (uint32_t)(min(ty + 3, H) - ty);
@@ -523,7 +564,7 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
         uint32_t w[DYN_SPEC + 1];
 #pragma unroll
         for (int j = 0; j <= DYN_SPEC; ++j) w[j] = lds_u32(wa + j * 128);     // word DYN_SPEC is only used when par
-        int sel = -1;
+        int sel = DYN_SPEC;
         uint32_t npos = 0, nsa = 0;
 #pragma unroll
         for (int j = DYN_SPEC - 1; j >= 0; --j) {                 // descending: the lowest valid try overwrites
@@ -535,35 +576,19 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
             // the ball's own cell counts as occupied: it must move (minigrid.py:1040-1041)
             if (lds_u8(sa) == CODE_EMPTY) { sel = j; npos = (uint32_t)(dx | (y << 8)); nsa = sa; }
         }
-        bool placed = spec && sel >= 0;
-        int tries = 0;
-        if (spec) { nd += placed ? 2 * (sel + 1) : 2 * DYN_SPEC; tries = DYN_SPEC; }
-        if (!placed) {
-            while (tries <= 100) {                                // place_obj(max_tries=100) makes 101 tries (:1028-1031)
-                tries++;
-                int x, y;
-                if (((nd - wbase + 1) >> 1) < WINW) {             // both draws are inside the window
-                    const uint32_t a = dr_sa + ((nd - wbase) >> 1) * 128u;
-                    const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 128u);
-                    x = tx + (int)__umulhi(par ? w0 * DRAW_ODD_MULT : w0, sx);
-                    y = ty + (int)__umulhi(par ? w1 : w0 * DRAW_ODD_MULT, sy);
-                } else {
-                    rg.ndraws = nd;
-                    x = rand_int_inl(rg, p, tx, tx + (int)sx);
-                    y = rand_int_inl(rg, p, ty, ty + (int)sy);
-                }
-                nd += 2;
-                const uint32_t sa = st_sa + cell_off(x, y, HP);
-                if (lds_u8(sa) == CODE_EMPTY) { placed = true; npos = (uint32_t)((x - tx) | (y << 8)); nsa = sa; break; }
-            }
+        npos += (uint32_t)tx;
+        if (spec) nd += 2u * (uint32_t)min(sel + 1, DYN_SPEC);
+        if (!spec || sel == DYN_SPEC) {
+            const MoreTries r = dynobs_more_tries(st_sa, dr_sa, wbase, WINW, nd, spec ? DYN_SPEC : 0, tx, ty, sx, sy, HP, rg.episode - 1u, rg.gid, p.seed);
+            nsa = r.nsa; npos = r.npos; nd = r.nd;
         }
-        if (placed) {                                             // a failed placement (RecursionError, swallowed) leaves the ball
+        if (nsa) {                                                // a failed placement (RecursionError, swallowed) leaves the ball
             const uint32_t old_sa = st_sa + cell_off(ox, oy, HP);
             sts_u8(nsa, lds_u8(old_sa));
             sts_u8(old_sa, CODE_EMPTY);
-            sts_u16(ob_p, npos + (uint32_t)tx);
+            sts_u16(ob_p, npos);
         }
-        ob_p += (k & 1) ? 126u : 2u;
+        ob_p = ob_n; opos = opos_n;
     }
     if (ag_mark) sts_u8(ag_sa, CODE_EMPTY);
     rg.ndraws = nd;
@@ -673,12 +698,13 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
     reward = 0.0; done = false;
     bool not_clear = false;
     if (GEN == GEN_DYNOBS) {                             // envs/dynamicobstacles.py:60-78
-        if (action >= c.n_actions) action = 0;
+        if ((unsigned)action >= 3u) action = 0;                    // n_actions == 3 (mgb_create checks): only left / right / forward exist here,
+                                                          // so the pickup / drop / toggle logic below folds away
         const int dx0 = (e.dir & 1) ? 0 : 1 - e.dir, dy0 = (e.dir & 1) ? 2 - e.dir : 0;
         const int fx0 = e.ax + dx0, fy0 = e.ay + dy0;
         uint32_t front = CODE_WALL;
         if ((unsigned)fx0 < (unsigned)W && (unsigned)fy0 < (unsigned)H) front = cell_rd(st, fx0 * HP + fy0);
-        not_clear = front != CODE_EMPTY && (lut[front * lut_pitch<SEE>() + lut_fw<SEE>()] & 0xFF) != T_GOAL;
+        not_clear = front != CODE_EMPTY && (lut[front * lut_pitch_words(GEN)] & 0xFF) != T_GOAL;
         // Update obstacle positions (dynamicobstacles.py:70-78)
         if (!p.tape) dynobs_move<V>(st, e, rg, p, draws);
         else { Env te = e; Rng tr = rg; dynobs_move_tape(st, te, tr, p); e = te; rg = tr; }     // parity-only mode, out of line
@@ -692,8 +718,8 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
     if (GEN == GEN_POOL) {
         if (c.hook == HOOK_MEMORY && action == A_PICKUP) action = A_TOGGLE;                  // memory.py:89-90
         if (c.hook == HOOK_REDBLUEDOORS) {                                                     // redbluedoors.py:45-46
-            const uint32_t ra = lut[cell_rd(st, (int)((pc.hp1 >> 16) & 0xFF) * HP + (int)(pc.hp1 >> 24)) * lut_pitch<SEE>() + lut_fw<SEE>()];
-            const uint32_t rb = lut[cell_rd(st, (int)(pc.hp2 & 0xFF) * HP + (int)((pc.hp2 >> 8) & 0xFF)) * lut_pitch<SEE>() + lut_fw<SEE>()];
+            const uint32_t ra = lut[cell_rd(st, (int)((pc.hp1 >> 16) & 0xFF) * HP + (int)(pc.hp1 >> 24)) * lut_pitch_words(GEN)];
+            const uint32_t rb = lut[cell_rd(st, (int)(pc.hp2 & 0xFF) * HP + (int)((pc.hp2 >> 8) & 0xFF)) * lut_pitch_words(GEN)];
             red_before = (ra & 0xFF) == T_DOOR && ((ra >> 16) & 0xFF) == 0;
             blue_before = (rb & 0xFF) == T_DOOR && ((rb >> 16) & 0xFF) == 0;
         }
@@ -705,7 +731,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
     const int fidx = fx * HP + fy;
     const bool f_in = (unsigned)fx < (unsigned)W && (unsigned)fy < (unsigned)H;
     if (f_in) fc = cell_rd(st, fidx); else rg.err |= ERR_BOUNDS;
-    const uint32_t fw = lut[fc * lut_pitch<SEE>() + lut_fw<SEE>()];
+    const uint32_t fw = lut[fc * lut_pitch_words(GEN)];
     const uint32_t ff = fw >> 24;
     const int ftype = fw & 0xFF;
     // select form of the action switch (minigrid.py:1245-1318): one rarely-taken branch for grid edits
@@ -722,12 +748,13 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
     if (goal) reward = reward_formula(e.steps, c.max_steps);
     const int ds = (fw >> 16) & 0xFF, dcol = (fw >> 8) & 0xFF;
     const int ns = (ds == 2) ? ((e.carry == code_of(T_KEY, dcol, 0)) ? 0 : 2) : (ds ^ 1);   // Door.toggle :252-262
-    const bool tog = action == A_TOGGLE && f_in;
+    constexpr bool MANIP = GEN != GEN_DYNOBS;               // Dynamic-Obstacles has no pickup / drop / toggle (dynamicobstacles.py:32,62-63)
+    const bool tog = MANIP && action == A_TOGGLE && f_in;
     const bool tog_door = tog && ftype == T_DOOR && ns != ds;
     // default Box (contains None) and default Goal (toggletimes 1) vanish when toggled (:171-177, :355-360)
     const bool tog_vanish = tog && (ftype == T_BOX || (ftype == T_GOAL && !(ff & F_TGOAL)));
-    const bool pick = action == A_PICKUP && (ff & F_PICKUP) && e.carry == 0 && f_in;
-    const bool drop = action == A_DROP && fc == CODE_EMPTY && e.carry != 0 && f_in;
+    const bool pick = MANIP && action == A_PICKUP && (ff & F_PICKUP) && e.carry == 0 && f_in;
+    const bool drop = MANIP && action == A_DROP && fc == CODE_EMPTY && e.carry != 0 && f_in;
     if (pick || drop || tog_door || tog_vanish) {
         uint32_t nv = CODE_EMPTY;
         if (drop) nv = (uint32_t)e.carry;
@@ -748,7 +775,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         const int Cx = (pc.hp2 >> 16) & 0xFF, Cy = pc.hp2 >> 24, Dx = pc.hp3 & 0xFF, Dy = (pc.hp3 >> 8) & 0xFF;
         auto adj4 = [&](int x, int y) { return (e.ax == x && abs(e.ay - y) == 1) || (e.ay == y && abs(e.ax - x) == 1); };
         auto door_open = [&](int x, int y) {
-            const uint32_t w = lut[cell_rd(st, x * HP + y) * lut_pitch<SEE>() + lut_fw<SEE>()];
+            const uint32_t w = lut[cell_rd(st, x * HP + y) * lut_pitch_words(GEN)];
             return (w & 0xFF) == T_DOOR && ((w >> 16) & 0xFF) == 0;
         };
         bool win = false;
@@ -811,11 +838,11 @@ __device__ __forceinline__ uint32_t sel_bit(uint32_t v, uint32_t bit, uint32_t x
     return r;
 }
 
-// code -> LUT word; the address is formed with a multiply-add so that it issues on the (idle) FMA
-// pipe instead of the ALU pipe that bounds this kernel
+// code -> LUT word; the address is formed with a multiply-add (see the LUT comment at the top)
+template <int GEN>
 __device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
     uint32_t a;
-    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(LUT_PITCH_SEE * 4));
+    asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code), "r"(lut_sa), "n"(lut_pitch_words(GEN) * 4));
     return lds_u32(a);
 }
 // Addressing of the view gather: the shared-memory offset of grid cell (x,y) inside a lane's column is
@@ -824,7 +851,7 @@ __device__ __forceinline__ uint32_t lut_ld(uint32_t lut_sa, uint32_t code) {
 // min() clamps it onto the pad -- no per-cell bounds test (minigrid.py:465-469).  offx/offy are tabulated
 // once per CTA (axis tables).
 
-template <bool SEE, int V>
+template <int GEN, bool SEE, int V>
 __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const RolloutParams &p, const uint32_t *lut,
                                         uint32_t *stage_w, int lane) {
     const DevCfg &c = p.cfg;
@@ -842,7 +869,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
     //   even dir: x = ax + sgn*(V-1-vy) (rows)    y = ay + sgn*(vx-V/2) (columns)
     //   odd  dir: x = ax - sgn*(vx-V/2) (columns) y = ay + sgn*(V-1-vy) (rows)
     // P[vx] / Q[vy] = shared-memory offsets of those coordinates, read from the CTA's axis tables
-    const uint32_t ax_sa = (uint32_t)__cvta_generic_to_shared(lut) + lut_bytes<SEE>();      // table of x offsets
+    const uint32_t ax_sa = (uint32_t)__cvta_generic_to_shared(lut) + lut_bytes(GEN);      // table of x offsets
     const uint32_t ay_sa = ax_sa + AXIS_ENTRIES * 4;                                 // table of y offsets
     const int p0 = odd ? e.ax + (V / 2) * sgn : e.ay - (V / 2) * sgn, pstep4 = (odd ? -sgn : sgn) * 4;
     const int q6 = odd ? e.ay : e.ax, qstep4 = sgn * 4;               // row vy = V-1 is the agent's own row
@@ -854,7 +881,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
         P[k] = (int)lds_u32(pa + k * pstep4) + (int)st_sa;            // P carries the column base address
         Q[k] = (int)lds_u32(qa + (V - 1 - k) * qstep4);
     }
-    const uint32_t own = e.carry ? lds_u32(lut_sa + (uint32_t)e.carry * (lut_pitch<SEE>() * 4)) : (uint32_t)T_EMPTY;   // word0: 24-bit (type,colour,state)   // minigrid.py:1349-1356
+    const uint32_t own = e.carry ? lds_u32(lut_sa + (uint32_t)e.carry * (lut_pitch_words(GEN) * 4)) : (uint32_t)T_EMPTY;   // minigrid.py:1349-1356
 
     // Realignment of the record to byte offset lane*147 of the warp's 4704-byte block: block word q+j takes the
     // high bytes of record word j-1 and the low bytes of record word j -- one funnel shift per word.
@@ -890,7 +917,7 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
             for (int i = 0; i < 4; ++i) {
                 const int ci = g * 4 + i;
                 x[i] = 0;
-                if (ci < V * V) x[i] = (ci == AGENT_CI) ? own : lut_ld(lut_sa, code[i]);
+                if (ci < V * V) x[i] = (ci == AGENT_CI) ? own : lut_ld<GEN>(lut_sa, code[i]);
             }
             emit(g * 3, __byte_perm(x[0], x[1], 0x4210));                              // x0.b0 x0.b1 x0.b2 x1.b0
             if (g * 3 + 1 <= FW + 1) emit(g * 3 + 1, __byte_perm(x[1], x[2], 0x5421));     // x1.b1 x1.b2 x2.b0 x2.b1
@@ -909,10 +936,8 @@ __device__ __forceinline__ void observe(const uint32_t *st, const Env &e, const 
             uint32_t o = 0;
 #pragma unroll
             for (int vx = V - 1; vx >= 0; --vx) {
-                // one 32-bit word per cell: 24-bit encoding + "opaque" in bit 31 (never selected by the PRMTs below)
-                uint32_t a;
-                asm("mad.lo.u32 %0, %1, %3, %2;" : "=r"(a) : "r"(code[vx]), "r"(lut_sa + 4u), "n"(LUT_PITCH_OCC * 4));
-                const uint32_t x = lds_u32(a);
+                // one 32-bit word per cell: 24-bit encoding + flags, "opaque" in bit 31 (byte 3 is never selected by the PRMTs below)
+                const uint32_t x = lut_ld<GEN>(lut_sa, code[vx]);
                 xs[vx * V + vy] = x;
                 o = __funnelshift_l(x, o, 1);                             // (o << 1) | (x >> 31)
             }
@@ -1035,10 +1060,14 @@ __device__ __forceinline__ void bulk_commit() {
 // ------------------------------------------------------------------------------------------
 // the persistent rollout kernel (also serves reset and single step)
 // ------------------------------------------------------------------------------------------
+#ifndef MGB_DYN_MIN_BLOCKS
+#define MGB_DYN_MIN_BLOCKS 2
+#endif
+#define MGB_MIN_BLOCKS(GEN) ((GEN) == GEN_DYNOBS ? MGB_DYN_MIN_BLOCKS : 0)     // 0 = no hint
 // NOTE: no minBlocksPerSM argument on purpose -- with it ptxas spends up to 157 registers/thread and the
 // occupancy loss costs more than it gains (measured: profiles/README.md, A/B table)
 template <int GEN, bool SEE, int V>
-__global__ void __launch_bounds__(MAX_THREADS) k_rollout(
+__global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
     const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     constexpr bool PACKED = !SEE;     // rollouts of the occluded kernels hold 32 steps of actions in 4 registers (see below)
@@ -1048,16 +1077,13 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
     // per-lane "waterfall" loop around their uniform-register operands
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
-    uint32_t *axis = lut + lut_bytes<SEE>() / 4;                                           // [2][AXIS_ENTRIES]
-    uint8_t *stage_base = smem_raw + table_bytes<SEE>();
+    uint32_t *axis = lut + lut_bytes(GEN) / 4;                                           // [2][AXIS_ENTRIES]
+    uint8_t *stage_base = smem_raw + table_bytes(GEN);
     constexpr int SB = stage_bytes(V), OB = obs_bytes(V), SB_OBS = GROUP * OB;
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * SB);
     uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + wpb * SB) + warp * ((c.S + 1) * 32);
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const uint32_t le = lut_entry(i);
-        lut[i * lut_pitch<SEE>()] = le & 0x00FFFFFFu;
-        if (!SEE) lut[i * lut_pitch<SEE>() + 1] = (le & 0x00FFFFFFu) | (((le >> 24) & F_OPAQUE) << 31);
-        lut[i * lut_pitch<SEE>() + lut_fw<SEE>()] = le;
+        lut[i * lut_pitch_words(GEN)] = lut_entry(i);
     }
     for (int i = threadIdx.x; i < AXIS_ENTRIES; i += blockDim.x) {
         const int v = i - AXIS_BIAS, wall = c.S * 128;
@@ -1184,7 +1210,7 @@ __global__ void __launch_bounds__(MAX_THREADS) k_rollout(
             if (gobs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
                 __syncwarp();
-                observe<SEE, V>(st, e, p, lut, stage_w, lane);
+                observe<GEN, SEE, V>(st, e, p, lut, stage_w, lane);
                 if (full && ((reinterpret_cast<uintptr_t>(gobs) & 15) == 0)) {
                     fence_proxy_async();
                     __syncwarp();
