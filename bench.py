@@ -43,9 +43,10 @@ def parse():
     ap.add_argument("--rollout-T", type=int, default=32, help="env-steps per launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-python-reference", action="store_true", help="skip timing the unmodified Python reference on the host cores")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short per-GPU runs of the other BASELINE configs")
-    ap.add_argument("--cpu-sample-envs", type=int, default=1 << 14)
-    ap.add_argument("--cpu-sample-T", type=int, default=64)
+    ap.add_argument("--cpu-sample-envs", type=int, default=0, help="CPU-port sample (default: 16384 envs in the b200 arm, --num-envs in the reference arm)")
+    ap.add_argument("--cpu-sample-T", type=int, default=0, help="default: 64 in the b200 arm, --rollout-T in the reference arm")
     return ap.parse_args()
 
 
@@ -103,23 +104,150 @@ def oracle_cfg(env_id):
     return {k: v for k, v in mgb.spec(env_id)["config"].items() if k not in ("mission", "reward_range")}
 
 
-def cpu_leg(env_id, n_envs, T, reps, threads=0):
-    """Times the CPU oracle (the C port of the reference algorithm) on the host cores."""
-    import numpy as np
-    from oracle.oracle import OracleVec
-    cfg = oracle_cfg(env_id)
-    cores = threads or os.cpu_count() or 1
-    orc = OracleVec(cfg, n_envs, seed=0, threads=cores)
-    orc.reset()
-    rs = np.random.RandomState(1234)
-    acts = rs.randint(0, cfg["n_actions"], size=(T, n_envs)).astype(np.uint8)
-    orc.rollout(acts, autoreset=True)                      # warm-up
-    times = []
-    for _ in range(reps):
+def bench_config(env_id, n_envs, T):
+    """`config` of the JSON line -- the same dict for the b200 arm and the reference arm"""
+    return {"workload": env_id + " random-action rollout, auto-reset on, obs+reward+done+dir written every env-step",
+            "envs_per_gpu": n_envs, "env_steps_per_launch": T, "actions": "uniform random, pre-generated, seed 1234",
+            "l2": "outputs per launch (%.1f GB) exceed L2; no flush needed" % (n_envs * T * 157 / 1e9),
+            "parallelism": "env shards by global env id, no collective"}
+
+
+class CpuLeg:
+    """The CPU oracle (the C port of the reference algorithm, oracle/minigrid_oracle.c) on the host cores: one call of
+    run() = one pass of the hot path over n_envs x T env-steps, observations materialised in (re-used) host buffers."""
+
+    def __init__(self, env_id, n_envs, T, threads=0):
+        import numpy as np
+        from oracle.oracle import OracleVec
+        cfg = oracle_cfg(env_id)
+        self.cores = threads or os.cpu_count() or 1
+        self.n, self.T = n_envs, T
+        self.orc = OracleVec(cfg, n_envs, seed=0, threads=self.cores)
+        self.orc.reset()
+        rs = np.random.RandomState(1234)
+        self.acts = rs.randint(0, cfg["n_actions"], size=(T, n_envs)).astype(np.uint8)
+        self.out = self.orc.rollout(self.acts, autoreset=True)             # warm-up; the buffers are touched now
+
+    def run(self):
         t0 = time.perf_counter()
-        orc.rollout(acts, autoreset=True)                  # obs [T,n,147] materialised in host memory
-        times.append(time.perf_counter() - t0)
-    return n_envs * T / min(times), times, cores
+        self.orc.rollout(self.acts, autoreset=True, out=self.out)          # obs [T,n,147] materialised in host memory
+        return time.perf_counter() - t0
+
+
+def cpu_leg(env_id, n_envs, T, reps, threads=0):
+    leg = CpuLeg(env_id, n_envs, T, threads)
+    times = [leg.run() for _ in range(reps)]
+    return n_envs * T / min(times), times, leg.cores
+
+
+def _ref_worker(env_id, idx, warm_s, timed_s, q):
+    """One forked worker of the Python-reference harness: the unmodified reference env, uniform
+    random actions, reset() on done, observation dict built every step."""
+    try:
+        import numpy as np
+        from oracle import ref_shim as R
+        env = R.make(env_id)
+        env.seed(idx)
+        env.reset()
+        n_act = env.action_space.n
+        rs = np.random.RandomState(1000 + idx)
+
+        def run(sec):
+            n, t_end = 0, time.perf_counter() + sec
+            while time.perf_counter() < t_end:
+                for a in rs.randint(0, n_act, size=32):
+                    _, _, d, _ = env.step(int(a))
+                    if d:
+                        env.reset()
+                n += 32
+            return n
+        run(warm_s)
+        t0 = time.perf_counter()
+        n = run(timed_s)
+        q.put((n, time.perf_counter() - t0))
+    except Exception as e:                       # report, never hang the parent
+        q.put(("error", repr(e)))
+
+
+def _ref_rate(env_id, procs, warm_s, timed_s):
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    ws = [ctx.Process(target=_ref_worker, args=(env_id, i, warm_s, timed_s, q)) for i in range(procs)]
+    for w in ws:
+        w.start()
+    res = [q.get(timeout=60 + 4 * (warm_s + timed_s)) for _ in ws]
+    for w in ws:
+        w.join(timeout=10)
+    bad = [r for r in res if r[0] == "error"]
+    if bad:
+        raise RuntimeError(bad[0][1])
+    return sum(n / dt for n, dt in res)
+
+
+def _benchmark_py(env_id):
+    """The three numbers of the reference's own benchmark.py (benchmark.py:22-53), bounded iteration counts."""
+    from oracle import ref_shim as R
+    W = sys.modules["gym_minigrid.wrappers"]
+    env = R.make(env_id)
+    n_reset, n_frames = 100, 300
+    t0 = time.perf_counter()
+    for _ in range(n_reset):
+        env.reset()
+    reset_ms = 1e3 * (time.perf_counter() - t0) / n_reset
+    t0 = time.perf_counter()
+    for _ in range(n_frames):
+        env.render('rgb_array')
+    render_fps = n_frames / (time.perf_counter() - t0)
+    env = W.ImgObsWrapper(W.RGBImgPartialObsWrapper(R.make(env_id)))
+    env.reset()
+    t0 = time.perf_counter()
+    for _ in range(n_frames):
+        env.step(0)
+    view_fps = n_frames / (time.perf_counter() - t0)
+    return {"reset_ms": reset_ms, "render_fps": render_fps, "agent_view_fps": view_fps, "resets": n_reset, "frames": n_frames}
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def python_reference_leg(env_id, others=()):
+    """The UNMODIFIED Python reference timed on this box's host cores: P =
+    os.cpu_count() forked workers, 1 s warm-up + 5 s timed, sum of steps/s; single-process rate; benchmark.py's numbers.
+    Must run before CUDA is initialised in this process (fork).  Returns a dict, or {"value": None, "reason": ...}."""
+    try:
+        from oracle import ref_shim as R
+        root = R.reference_root()
+        if root is None:
+            msg = "reference tree not found: looked at $MGB_REFERENCE, /root/reference, baseline/_ref"
+            print("bench.py: cpu_baseline_python unavailable -- " + msg, file=sys.stderr)
+            return {"value": None, "reason": msg}
+        R.load_reference()
+        P = os.cpu_count() or 1
+        single = _ref_rate(env_id, 1, 0.3, 1.0)
+        total = _ref_rate(env_id, P, 1.0, 5.0)
+        out = {"value": total, "unit": "env-steps/s", "cores": P, "cpu_model": cpu_model(), "single_process": single,
+               "kind": "reference", "reference_root": root,
+               "sample": "%d forked workers x (1 s warm-up + 5 s timed), unmodified reference under the oracle/ref_shim.py gym "
+                         "stub, uniform random actions, reset() on done, obs dict built every step" % P,
+               "other_configs": {}, "benchmark_py": None}
+        for oid in others:
+            out["other_configs"][oid] = _ref_rate(oid, P, 0.5, 2.0)
+        try:
+            out["benchmark_py"] = _benchmark_py(env_id)
+        except Exception as e:
+            out["benchmark_py"] = {"error": repr(e)}
+        return out
+    except Exception as e:
+        print("bench.py: cpu_baseline_python failed -- %r" % (e,), file=sys.stderr)
+        return {"value": None, "reason": repr(e)}
 
 
 def run_reference(args, rank, world):
@@ -127,26 +255,24 @@ def run_reference(args, rank, world):
     task contract the arm times the CPU oracle port with all host threads on the same config."""
     if rank != 0:
         return
-    n, T = args.cpu_sample_envs, args.cpu_sample_T
+    pyref = None if args.no_python_reference else python_reference_leg(args.env_id)
+    # by default the arm runs the b200 arm's own config (same envs per "GPU", same env-steps per bench step)
+    n = args.cpu_sample_envs if args.cpu_sample_envs else args.num_envs
+    T = args.cpu_sample_T if args.cpu_sample_T else args.rollout_T
+    leg = CpuLeg(args.env_id, n, T)
+    cores = leg.cores
     for _ in range(args.warmup):
-        cpu_leg(args.env_id, n, T, 1)
-    t0 = time.perf_counter()
-    best = 0.0
-    per = []
-    cores = os.cpu_count() or 1
-    for _ in range(args.steps):
-        v, ts, cores = cpu_leg(args.env_id, n, T, 1)
-        per.append(ts[0])
-        best = max(best, v)
+        leg.run()
+    per = [leg.run() for _ in range(args.steps)]
     value = n * T * len(per) / sum(per)
     sample = "%d envs x %d env-steps per bench step, C oracle port, %d threads" % (n, T, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(per) / len(per), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.env_id + " random-action rollout, auto-reset on, obs+reward+done+dir written every env-step",
-                   "cpu_sample": sample},
+        "config": bench_config(args.env_id, n, T),       # the b200 arm's config: a bench step of this arm is one pass over the same batch
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline_python": pyref,
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -165,6 +291,11 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    # the unmodified Python reference on this box's host cores, rank 0 at N = 1 only; forks, so it runs before CUDA exists
+    pyref = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.no_python_reference:
+        pyref = python_reference_leg(args.env_id, OTHER_CONFIGS if args.env_id == OTHER_CONFIGS_OF and not args.no_other_configs else ())
 
     import torch
     import torch.distributed as dist
@@ -315,21 +446,19 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, times, cores = cpu_leg(args.env_id, args.cpu_sample_envs, args.cpu_sample_T, 3)
+        cn, cT = args.cpu_sample_envs or (1 << 14), args.cpu_sample_T or 64
+        v, times, cores = cpu_leg(args.env_id, cn, cT, 3)
         cpu = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                "sample": "%d envs x %d env-steps, best of 3, C oracle port (oracle/minigrid_oracle.c), obs materialised"
-                         % (args.cpu_sample_envs, args.cpu_sample_T)}
+                         % (cn, cT)}
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.env_id + " random-action rollout, auto-reset on, obs+reward+done+dir written every env-step",
-                       "envs_per_gpu": N, "env_steps_per_launch": T, "actions": "torch.randint on device, seed 1234",
-                       "l2": "outputs per launch (%.1f GB) exceed L2; no flush needed" % (N * T * 157 / 1e9),
-                       "parallelism": "env shards by global env id, no collective"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "config": bench_config(args.env_id, N, T),
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_python": pyref, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "step_mode_env_steps_per_s_per_gpu": step_mode, "step_mode": step_mode_info, "other_configs_per_gpu": others,
         }))
     if world > 1:

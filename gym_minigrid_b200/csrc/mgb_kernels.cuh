@@ -579,8 +579,26 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
         npos += (uint32_t)tx;
         if (spec) nd += 2u * (uint32_t)min(sel + 1, DYN_SPEC);
         if (!spec || sel == DYN_SPEC) {
-            const MoreTries r = dynobs_more_tries(st_sa, dr_sa, wbase, WINW, nd, spec ? DYN_SPEC : 0, tx, ty, sx, sy, HP, rg.episode - 1u, rg.gid, p.seed);
-            nsa = r.nsa; npos = r.npos; nd = r.nd;
+            // ~1 % of the (lane, ball) pairs -- a ball in a corner or along a wall -- but a third of the warp's ball steps:
+            // a tight loop over the rest of the window for the common case (even draw counter), everything else out of line
+            int tries = spec ? DYN_SPEC : 0;
+            nsa = 0;                                              // !spec: the speculative block looked at the wrong words
+            if (!par) {
+                uint32_t wp = dr_sa + ((nd - wbase) >> 1) * 128u;
+                const uint32_t wend = dr_sa + WINW * 128u;
+                while (wp < wend) {                               // tries <= 100 holds: the window has at most 20 words
+                    const uint32_t w0 = lds_u32(wp);
+                    wp += 128u; nd += 2u; ++tries;
+                    const int dx = (int)__umulhi(w0, sx);
+                    const int y = ty + (int)__umulhi(w0 * DRAW_ODD_MULT, sy);
+                    const uint32_t sa = colb + (uint32_t)(dx * XP) + (uint32_t)(y + (y >> 2) * 124);
+                    if (lds_u8(sa) == CODE_EMPTY) { nsa = sa; npos = (uint32_t)((tx + dx) | (y << 8)); break; }
+                }
+            }
+            if (!nsa) {
+                const MoreTries r = dynobs_more_tries(st_sa, dr_sa, wbase, WINW, nd, tries, tx, ty, sx, sy, HP, rg.episode - 1u, rg.gid, p.seed);
+                nsa = r.nsa; npos = r.npos; nd = r.nd;
+            }
         }
         if (nsa) {                                                // a failed placement (RecursionError, swallowed) leaves the ball
             const uint32_t old_sa = st_sa + cell_off(ox, oy, HP);

@@ -128,14 +128,19 @@ class OracleVec:
         o, r, dn, d = self.rollout(np.asarray(actions, np.uint8).reshape(1, self.n), autoreset)
         return o[0], r[0], dn[0], d[0]
 
-    def rollout(self, actions, autoreset=True, want_obs=True):
+    def rollout(self, actions, autoreset=True, want_obs=True, out=None):
+        """out = (obs, reward, done, dir) from an earlier call: reuse the (already touched) buffers"""
         a = np.ascontiguousarray(actions, np.uint8)
         T = a.shape[0]
         assert a.shape == (T, self.n)
-        obs = np.zeros((T, self.n, self.V, self.V, 3), np.uint8) if want_obs else None
-        r = np.zeros((T, self.n), np.float64)
-        dn = np.zeros((T, self.n), np.uint8)
-        d = np.zeros((T, self.n), np.uint8)
+        if out is not None:
+            obs, r, dn, d = out
+            assert obs.shape == (T, self.n, self.V, self.V, 3) and r.shape == dn.shape == d.shape == (T, self.n)
+        else:
+            obs = np.zeros((T, self.n, self.V, self.V, 3), np.uint8) if want_obs else None
+            r = np.zeros((T, self.n), np.float64)
+            dn = np.zeros((T, self.n), np.uint8)
+            d = np.zeros((T, self.n), np.uint8)
         self._chk(self._L.orc_vec_rollout(self._h, T, _p(a), int(autoreset), _p(obs), _p(r), _p(dn), _p(d)))
         return obs, r, dn, d
 

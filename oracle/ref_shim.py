@@ -26,9 +26,13 @@ import types
 
 import numpy as np
 
+# search order (SURVEY headline fact 4): $MGB_REFERENCE -> /root/reference (the build container) -> baseline/_ref (the
+# unmodified reference pip-installed there by `python -m pip install --no-index --no-build-isolation --no-deps --target
+# baseline/_ref <copy of /root/reference>`; git-ignored, but it travels to the GPU box with the repo snapshot)
 REFERENCE_ROOT_CANDIDATES = [
     os.environ.get("MGB_REFERENCE", ""),
     "/root/reference",
+    os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref"),
 ]
 
 
