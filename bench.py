@@ -397,29 +397,33 @@ def main():
                "numa_node": numa}
         os.sched_setaffinity(0, affinity0)
 
-    # ---- secondary: single-step launches (state round-trips HBM every step) ----
-    Ks = 16
-    a1 = acts[0]
-    o1 = (out[0][0], out[1][0], out[2][0], out[3][0])
-    for t_ in range(3):
-        env.step(a1[t_], out=o1)
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for t_ in range(Ks):
-        env.step(a1[t_ % T], out=o1)
-    s1.record()
-    barrier()
-    step_mode = N * Ks / (s0.elapsed_time(s1) * 1e-3)
-    # bytes a single-step launch must move per env-step: the 158 output/action bytes plus the env's state block read
-    # (S words) and, for an untouched grid, its non-grid words written back
-    hp = (cfg["height"] + 3) // 4 * 4
-    gw = cfg["width"] * hp // 4
-    s_words = gw + 4 + (4 if cfg.get("n_obstacles", 0) > 0 else 0)
-    step_bytes = 158 + 4 * s_words + 4 * (s_words - gw)
-    step_mode_info = {"env_steps_per_s_per_gpu": step_mode, "state_inclusive_bytes_per_env_step": step_bytes,
-                      "state_inclusive_gbs": step_mode * step_bytes / 1e9,
-                      "frac_of_hbm_peak": (step_mode * step_bytes / 1e9) / roofline["peak"] if roofline and roofline.get("peak") else None}
+    # ---- secondary: single-step launches, i.e. the gym API env.step() (state round-trips HBM every step) ----
+    def step_mode_of(e, ecfg, a_TN):
+        Ks = 16
+        o1 = (out[0][0], out[1][0], out[2][0], out[3][0])
+        for t_ in range(3):
+            e.step(a_TN[t_], out=o1)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for t_ in range(Ks):
+            e.step(a_TN[t_ % T], out=o1)
+        s1.record()
+        barrier()
+        rate = N * Ks / (s0.elapsed_time(s1) * 1e-3)
+        # bytes a single-step launch must move per env-step: the 158 output/action bytes plus the env's state block read
+        # (S words) and its non-grid words written back.  Template-grid envs (Empty, Dynamic-Obstacles:
+        # grid = static template + ball list) never move their grid rows: S-GW words in, S-GW words out.
+        hp = (ecfg["height"] + 3) // 4 * 4
+        gw = ecfg["width"] * hp // 4
+        s_words = gw + 4 + (4 if ecfg.get("n_obstacles", 0) > 0 else 0)
+        implied = ecfg["gen"] in (0, 3)
+        sbytes = 158 + 4 * (s_words - gw if implied else s_words) + 4 * (s_words - gw)
+        return {"env_steps_per_s_per_gpu": rate, "state_inclusive_bytes_per_env_step": sbytes, "state_inclusive_gbs": rate * sbytes / 1e9,
+                "frac_of_hbm_peak": (rate * sbytes / 1e9) / peak}
+
+    step_mode_info = step_mode_of(env, cfg, acts[0])
+    step_mode = step_mode_info["env_steps_per_s_per_gpu"]
 
     # ---- secondary: the other BASELINE.json configs on the same kernel family, per GPU (short: 3 warm-up + 5 launches each) ----
     others = None
@@ -434,6 +438,7 @@ def main():
             for _ in range(3):
                 oenv.rollout(oa, out=out)
             barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             for _ in range(5):
                 oenv.rollout(oa, out=out)
@@ -441,7 +446,9 @@ def main():
             barrier()
             ov = N * T * 5 / (s0.elapsed_time(s1) * 1e-3)
             oenv.check_errors()
-            others[oid] = {"env_steps_per_s_per_gpu": ov, "roofline_frac": ov * ALGO_BYTES_PER_STEP / 1e9 / peak}
+            others[oid] = {"env_steps_per_s_per_gpu": ov, "roofline_frac": ov * ALGO_BYTES_PER_STEP / 1e9 / peak,
+                           "step_mode": step_mode_of(oenv, ocfg, oa)}
+            oenv.check_errors()
             del oenv
 
     cpu = None

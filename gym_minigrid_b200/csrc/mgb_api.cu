@@ -29,6 +29,27 @@ static int fail(const char *fmt, ...) {
 
 constexpr int HOST_PIPE_STREAMS = 3;
 
+// Every handle entry point runs on the handle's device and leaves the calling thread's current device as it found it
+// (a process driving several GPUs, or torch's current device being another one).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) { ok = false; return; }
+        if (cur != dev) {
+            if (cudaSetDevice(dev) != cudaSuccess) { ok = false; return; }
+            prev = cur;
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define ON_DEVICE(h)                                                                         \
+    DeviceGuard guard_((h)->device);                                                         \
+    if (!guard_.ok) return fail("cannot switch to device %d: %s", (h)->device, cudaGetErrorString(cudaGetLastError()))
+
 static int elementwise_grid(int64_t total) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -63,6 +84,7 @@ struct mgb_handle {
     // host pipeline (mgb_step_host)
     cudaStream_t pipe[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
     cudaEvent_t pipe_ev[HOST_PIPE_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t order_ev = nullptr;          // recorded after every state-changing launch on the caller's stream (mgb_step_host waits on it)
     uint32_t policy_epoch = 0;               // number of random-policy rollouts so far (counter word of their action stream)
     uint8_t *policy_scratch = nullptr;
     size_t policy_scratch_bytes = 0;
@@ -156,7 +178,8 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail("mgb_create: no CUDA device (there is no CPU fallback)");
     if (device < 0 || device >= ndev) return fail("mgb_create: device %d out of range (%d devices)", device, ndev);
-    CUDA_OK(cudaSetDevice(device));
+    DeviceGuard guard_(device);
+    if (!guard_.ok) return fail("mgb_create: cannot switch to device %d", device);
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("mgb_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
@@ -192,7 +215,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
 #endif
     for (int wpb = MAX_WARPS_PER_BLOCK; wpb >= 2; --wpb) {
         if (force && atoi(force) != wpb) continue;
-        const size_t smem = (size_t)table_bytes(c.gen) + (size_t)wpb * per_warp;
+        const size_t smem = (size_t)table_bytes(c.gen) + (size_t)tmpl_smem_bytes(c.gen, d.GW) + (size_t)wpb * per_warp;
         if (smem > prop.sharedMemPerBlockOptin) continue;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, wpb * 32, smem) != cudaSuccess || nb < 1) continue;
@@ -231,18 +254,21 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     if (cudaMalloc(&h->tmpl, t.size() * 4) != cudaSuccess || cudaMemcpy(h->tmpl, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
         return cleanup(fail("mgb_create: template upload failed"));
     if (cudaMalloc(&h->err, 4) != cudaSuccess || cudaMemset(h->err, 0, 4) != cudaSuccess) return cleanup(fail("mgb_create: err flag alloc failed"));
+    if (cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming) != cudaSuccess) return cleanup(fail("mgb_create: event creation failed"));
+    if (cudaDeviceSynchronize() != cudaSuccess) return cleanup(fail("mgb_create: device synchronisation failed"));   // the memsets above ran on the legacy stream
     *out = h;
     return 0;
 }
 
 int mgb_destroy(mgb_handle *h) {
     if (!h) return 0;
-    cudaSetDevice(h->device);
+    DeviceGuard guard_(h->device);
     cudaFree(h->state); cudaFree(h->tmpl); cudaFree(h->err); cudaFree(h->pool);
     cudaFree(h->policy_scratch);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_dir); cudaFree(h->d_reward);
     for (auto &s : h->pipe) if (s) cudaStreamDestroy(s);
     for (auto &e : h->pipe_ev) if (e) cudaEventDestroy(e);
+    if (h->order_ev) cudaEventDestroy(h->order_ev);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -267,7 +293,7 @@ int mgb_set_rng_tape(mgb_handle *h, const int32_t *draws, const int64_t *offsets
 
 int mgb_set_kernel_timing(mgb_handle *h, int on) {
     if (!h) return fail("null handle");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     h->timing = on ? 1 : 0;
     if (on && !h->ev0) { CUDA_OK(cudaEventCreate(&h->ev0)); CUDA_OK(cudaEventCreate(&h->ev1)); }
     h->ev_valid = false;
@@ -285,7 +311,7 @@ double mgb_last_kernel_ms(mgb_handle *h) {
 // launch over groups [g0, g0+ng)
 static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset, const uint8_t *mask,
                   const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir,
-                  int64_t stride, cudaStream_t stream, bool timed) {
+                  int64_t stride, cudaStream_t stream, bool timed, bool order = true) {
     if (ng <= 0) return 0;
     RolloutParams p;
     p.cfg = h->dc; p.state = h->state; p.tmpl = h->tmpl; p.n_envs = h->n_envs;
@@ -301,18 +327,22 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
     fn<<<grid, sh.warps_per_block * 32, sh.smem_bytes, stream>>>(p);
     CUDA_OK(cudaGetLastError());
     if (timed && h->timing) { CUDA_OK(cudaEventRecord(h->ev1, stream)); h->ev_valid = true; }
+    if (order) CUDA_OK(cudaEventRecord(h->order_ev, stream));
     h->launches++;
     return 0;
 }
 
 int mgb_seed(mgb_handle *h, uint64_t seed) {
     if (!h) return fail("null handle");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     h->seed = seed;
     // rewind the episode counters: word GW+2 of every env
     const DevCfg &d = h->dc;
+    // the memset runs on the legacy default stream, which does not order against non-blocking streams: everything
+    // enqueued before (any stream) is drained first, and the memset is complete before a later reset can be enqueued
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemset2D(h->state + (size_t)(d.GW + 2) * 32, (size_t)d.S * 32 * 4, 0, 2 * 32 * 4, h->n_groups));
+    CUDA_OK(cudaDeviceSynchronize());
     return 0;
 }
 
@@ -321,7 +351,7 @@ int mgb_set_level_pool(mgb_handle *h, int32_t n_levels, const uint8_t *grid, con
     if (!h) return fail("null handle");
     if (h->cfg.gen != MGB_GEN_POOL) return fail("mgb_set_level_pool: handle was not created with MGB_GEN_POOL");
     if (n_levels < 1 || !grid || !agent) return fail("mgb_set_level_pool: need at least one level, grid and agent");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if (h->cfg.hook != 0 && !hook_params) return fail("mgb_set_level_pool: this handle has hook %d and needs hook_params", h->cfg.hook);
     const int PW = h->dc.GW + POOL_XW;
     uint32_t *np = nullptr;
@@ -340,7 +370,7 @@ int mgb_set_level_pool(mgb_handle *h, int32_t n_levels, const uint8_t *grid, con
 static int levels_io(mgb_handle *h, int32_t *out, const int32_t *in, void *stream) {
     if (!h) return fail("null handle");
     if (h->cfg.gen != MGB_GEN_POOL) return fail("levels: handle was not created with MGB_GEN_POOL");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     k_levels<<<(unsigned)((h->n_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->state, h->dc.S, h->dc.GW + XWORDS, h->n_envs, out, in);
     CUDA_OK(cudaGetLastError());
     h->launches++;
@@ -352,14 +382,14 @@ int mgb_set_levels(mgb_handle *h, const int32_t *levels, void *stream) { return 
 int mgb_reset(mgb_handle *h, const uint8_t *mask, uint8_t *obs, uint8_t *dir, void *stream) {
     if (!h) return fail("null handle");
     if (h->cfg.gen == MGB_GEN_POOL && h->pool_n < 1) return fail("mgb_reset: no level pool (call mgb_set_level_pool first)");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     return launch(h, 0, h->n_groups, 0, 1, mask, nullptr, obs, nullptr, nullptr, dir, h->n_envs, (cudaStream_t)stream, false);
 }
 
 int mgb_step(mgb_handle *h, const uint8_t *actions, uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir, void *stream) {
     if (!h) return fail("null handle");
     if (!actions) return fail("mgb_step: actions is NULL");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     return launch(h, 0, h->n_groups, 1, 0, nullptr, actions, obs, reward, done, dir, h->n_envs, (cudaStream_t)stream, true);
 }
 
@@ -367,14 +397,14 @@ int mgb_rollout(mgb_handle *h, int32_t T, const uint8_t *actions, uint8_t *obs, 
     if (!h) return fail("null handle");
     if (T < 1) return fail("mgb_rollout: T must be >= 1");
     if (!actions) return fail("mgb_rollout: actions is NULL");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     return launch(h, 0, h->n_groups, T, 0, nullptr, actions, obs, reward, done, dir, h->n_envs, (cudaStream_t)stream, true);
 }
 
 int mgb_rollout_random(mgb_handle *h, int32_t T, uint8_t *actions_out, uint8_t *obs, double *reward, uint8_t *done, uint8_t *dir, void *stream) {
     if (!h) return fail("null handle");
     if (T < 1) return fail("mgb_rollout_random: T must be >= 1");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     uint8_t *acts = actions_out;
     if (!acts) {                                             // nobody wants to see the actions: private scratch
         const size_t need = (size_t)T * h->n_envs;
@@ -396,7 +426,7 @@ int mgb_rollout_random(mgb_handle *h, int32_t T, uint8_t *actions_out, uint8_t *
 int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host, double *reward_host, uint8_t *done_host, uint8_t *dir_host) {
     if (!h) return fail("null handle");
     if (!actions_host) return fail("mgb_step_host: actions is NULL");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const int64_t N = h->n_envs;
     if (!h->pipe[0]) {
         for (auto &s : h->pipe) CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
@@ -418,16 +448,19 @@ int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host,
 #endif
     int32_t nchunks = forced > 0 ? forced : (G >= 4096 ? 4 : (G >= 1024 ? 2 : 1));
     const int32_t per = (G + nchunks - 1) / nchunks;
-    CUDA_OK(cudaDeviceSynchronize());   // order against whatever the caller enqueued on other streams
+    // Ordering against the caller's earlier work on this handle: every launch records `order_ev` on its stream and the
+    // pipeline streams wait for it -- no device-wide synchronisation, other streams of the process keep running.
+    // (State uploads / level pools synchronise their stream themselves.)
     int used = 0;
     for (int32_t c = 0, g0 = 0; g0 < G; ++c, g0 += per) {
         cudaStream_t s = h->pipe[c % HOST_PIPE_STREAMS];
+        if (c < HOST_PIPE_STREAMS) CUDA_OK(cudaStreamWaitEvent(s, h->order_ev, 0));
         used = std::max(used, c % HOST_PIPE_STREAMS + 1);
         const int32_t ng = std::min(per, G - g0);
         const int64_t e0 = (int64_t)g0 * 32, ne = std::min((int64_t)ng * 32, N - e0);
         CUDA_OK(cudaMemcpyAsync(h->d_actions + e0, actions_host + e0, ne, cudaMemcpyHostToDevice, s));
         if (launch(h, g0, ng, 1, 0, nullptr, h->d_actions, obs_host ? h->d_obs : nullptr, reward_host ? h->d_reward : nullptr,
-                   done_host ? h->d_done : nullptr, dir_host ? h->d_dir : nullptr, N, s, false)) return -1;
+                   done_host ? h->d_done : nullptr, dir_host ? h->d_dir : nullptr, N, s, false, false)) return -1;
         CUDA_OK(cudaEventRecord(h->pipe_ev[c % HOST_PIPE_STREAMS], s));      // the last record per stream is the one waited on
         if (obs_host) CUDA_OK(cudaMemcpyAsync(obs_host + e0 * h->obs_bytes, h->d_obs + e0 * h->obs_bytes, (size_t)ne * h->obs_bytes, cudaMemcpyDeviceToHost, s));
     }
@@ -436,6 +469,7 @@ int mgb_step_host(mgb_handle *h, const uint8_t *actions_host, uint8_t *obs_host,
     if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host, h->d_reward, (size_t)N * 8, cudaMemcpyDeviceToHost, tail));
     if (done_host) CUDA_OK(cudaMemcpyAsync(done_host, h->d_done, N, cudaMemcpyDeviceToHost, tail));
     if (dir_host) CUDA_OK(cudaMemcpyAsync(dir_host, h->d_dir, N, cudaMemcpyDeviceToHost, tail));
+    CUDA_OK(cudaEventRecord(h->order_ev, tail));                 // later launches on any stream are ordered by the host: all pipe streams are drained below
     for (auto &s : h->pipe) CUDA_OK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -445,18 +479,24 @@ static int state_io(mgb_handle *h, bool set, int full_obs, int64_t first, int64_
     if (!h) return fail("null handle");
     if (first < 0 || count < 0 || first + count > h->n_envs) return fail("state range [%lld,+%lld) outside [0,%lld)", (long long)first, (long long)count, (long long)h->n_envs);
     if (count == 0) return 0;
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     StateIO io;
-    io.cfg = h->dc; io.state = h->state; io.first = first; io.count = count;
+    io.cfg = h->dc; io.state = h->state; io.tmpl = h->tmpl; io.first = first; io.count = count;
     io.grid = grid; io.aux = aux; io.agent = agent; io.carrying = carrying;
     io.obstacles = h->dc.n_obst > 0 ? obstacles : nullptr; io.target = target; io.rng = rng; io.err = h->err;
     const int64_t threads = count * h->dc.S;
     const int block = 256;
     const int64_t grid_dim = (threads + block - 1) / block;
     if (grid_dim > 0x7FFFFFFF) return fail("state_io: too many envs for one launch");
-    if (set) k_set_state<<<(unsigned)grid_dim, block, 0, (cudaStream_t)stream>>>(io);
+    if (set) {
+        // a partial upload into envs whose grid is implied (template + balls, DESIGN.md "pristine"): make it explicit first
+        if (template_gen(h->dc.gen) && !(grid && (obstacles || h->dc.n_obst == 0)))
+            k_materialize<<<(unsigned)((count + block - 1) / block), block, 0, (cudaStream_t)stream>>>(h->dc, h->state, h->tmpl, first, count);
+        k_set_state<<<(unsigned)grid_dim, block, 0, (cudaStream_t)stream>>>(io);
+    }
     else k_get_state<<<(unsigned)grid_dim, block, 0, (cudaStream_t)stream>>>(io, full_obs);
     CUDA_OK(cudaGetLastError());
+    if (set) CUDA_OK(cudaEventRecord(h->order_ev, (cudaStream_t)stream));
     h->launches++;
     return 0;
 }
@@ -520,10 +560,10 @@ int mgb_render_full(mgb_handle *h, const uint8_t *obs, const uint8_t *atlas, int
     if (!h || !atlas || !out) return fail("mgb_render_full: null argument");
     if (tile < 8 || tile % 8 != 0) return fail("mgb_render_full: tile must be a multiple of 8");
     if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(atlas)) & 7) return fail("mgb_render_full: out and atlas must be 8-byte aligned");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const int64_t segs = h->n_envs * h->dc.H * tile * h->dc.W;
-    if (segs < ((int64_t)1 << 31) - (1 << 24)) k_render_full<uint32_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, obs, h->view, atlas, tile, out, h->n_envs);
-    else k_render_full<uint64_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, obs, h->view, atlas, tile, out, h->n_envs);
+    if (segs < ((int64_t)1 << 31) - (1 << 24)) k_render_full<uint32_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, h->tmpl, obs, h->view, atlas, tile, out, h->n_envs);
+    else k_render_full<uint64_t><<<elementwise_grid(segs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, h->tmpl, obs, h->view, atlas, tile, out, h->n_envs);
     CUDA_OK(cudaGetLastError());
     h->launches++;
     return 0;
@@ -535,7 +575,7 @@ int mgb_visit_bonus(mgb_handle *h, int32_t by_action, const uint8_t *actions, ui
     if (by_action && !actions) return fail("mgb_visit_bonus: actions is NULL");
     const int64_t need = (int64_t)h->dc.W * h->dc.H * (by_action ? 4 * h->dc.n_actions : 1);
     if (table < need) return fail("mgb_visit_bonus: table must hold W*H%s entries per env", by_action ? "*4*n_actions" : "");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if (h->n_envs == 0) return 0;
     k_visit_bonus<<<elementwise_grid(h->n_envs), 256, 0, (cudaStream_t)stream>>>(h->dc, h->state, by_action, actions, counts, table,
                                                                               reward, h->n_envs, h->err);
@@ -549,7 +589,7 @@ int mgb_dac(mgb_handle *h, int32_t count_ge_max, const uint8_t *done_in, const u
     if (!h || !done_in || !envdone_in || !envdone_out || !reset_dir || !obs || !reward || !done_out || !dir)
         return fail("mgb_dac: null argument");
     if (envdone_in == envdone_out || done_in == done_out) return fail("mgb_dac: in and out buffers must differ");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if (h->n_envs == 0) return 0;
     const int64_t words = (h->n_envs * h->obs_bytes + 3) / 4;
     k_dac<<<elementwise_grid(words), 256, 0, (cudaStream_t)stream>>>(h->n_envs, h->obs_bytes, count_ge_max != 0, done_in, envdone_in,
@@ -597,7 +637,7 @@ int mgb_episode_stats(int64_t N, const double *reward, const uint8_t *done, doub
 
 int mgb_error_flags(mgb_handle *h, void *stream, uint32_t *flags_host) {
     if (!h || !flags_host) return fail("null argument");
-    CUDA_OK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CUDA_OK(cudaMemcpyAsync(flags_host, h->err, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_OK(cudaMemsetAsync(h->err, 0, 4, (cudaStream_t)stream));
     CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));

@@ -54,6 +54,8 @@ constexpr int AXIS_ENTRIES = 88;                                 // v in [-(V-1)
 constexpr int AXIS_BIAS = 10;
 constexpr int MBAR_BYTES = MAX_WARPS_PER_BLOCK * 8;               // one mbarrier per warp (bulk load of the state block)
 __host__ __device__ constexpr int table_bytes(int gen) { return (lut_bytes(gen) + 2 * AXIS_ENTRIES * 4 + MBAR_BYTES + 127) / 128 * 128; }   // 3840 / 1792
+// the template-grid kernels (Empty, Dynamic-Obstacles) keep a copy of the static layout behind the tables (see "pristine")
+__host__ __device__ inline int tmpl_smem_bytes(int gen, int GW) { return (gen == 0 || gen == 3) ? (GW * 4 + 127) / 128 * 128 : 0; }
 
 // minigrid.py:40-52 / 27-35 / 57-61
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
@@ -136,7 +138,11 @@ struct RolloutParams {
 // ------------------------------------------------------------------------------------------
 struct Env {                    // hot: stays in registers (its address never escapes)
     int ax, ay, dir, carry, steps, target;
-    int flags;                  // bit0: grid == template + obstacle balls only (Dynamic-Obstacles fast reset)
+    int flags;                  // bit0 "pristine": the grid equals the static template plus a blue ball at every recorded
+                                // obstacle position.  Set by the Empty / Dynamic-Obstacles generators, cleared by a grid
+                                // edit or an upload.  The grid rows of a pristine env in HBM are DON'T-CARE: loads rebuild
+                                // the grid from the template (L2-resident) and the ball list, write-backs skip it, and the
+                                // state readers (k_get_state, k_render_full) reconstruct it the same way.
     bool dirty;                 // grid words modified since load
 };
 struct PoolCtx {                // GEN_POOL kernels only: the level being played and its hook parameters
@@ -322,6 +328,42 @@ __device__ __forceinline__ void obst_set(uint32_t *st, const DevCfg &c, int k, i
     *q = (*q & ~(0xFFFFu << sh)) | ((uint32_t)(x | (y << 8)) << sh);
 }
 
+constexpr int FLAG_PRISTINE = 1;
+__host__ __device__ constexpr bool template_gen(int gen) { return gen == GEN_EMPTY || gen == GEN_DYNOBS; }
+constexpr uint32_t CODE_BLUE_BALL = (uint32_t)code_of(T_BALL, C_BLUE, 0);
+
+// grid of a pristine env into the lane's shared-memory column: template words + the balls of the obstacle list
+// (which is already in shared memory: words GW+XWORDS..)
+// `tmpl_s`: the CTA's shared-memory copy of the template (all lanes read the same word: a broadcast, no global latency)
+__device__ __forceinline__ void rebuild_pristine_grid(uint32_t *st, const RolloutParams &p, const uint32_t *tmpl_s) {
+    const DevCfg &c = p.cfg;
+    const uint4 *t4 = reinterpret_cast<const uint4 *>(tmpl_s);
+    int k = 0;
+    for (; k + 4 <= c.GW; k += 4) {
+        const uint4 v = t4[k >> 2];
+        st[k * 32] = v.x; st[(k + 1) * 32] = v.y; st[(k + 2) * 32] = v.z; st[(k + 3) * 32] = v.w;
+    }
+    for (; k < c.GW; ++k) st[k * 32] = tmpl_s[k];
+    for (int j = 0; j < c.n_obst; ++j) {
+        int ox, oy;
+        obst_get(st, c, j, ox, oy);
+        cell_wr(st, ox * c.HP + oy, CODE_BLUE_BALL);
+    }
+}
+
+// grid word k of env `base` (column of the state block in HBM) as the state readers must see it
+__device__ __forceinline__ uint32_t grid_word(const DevCfg &c, const uint32_t *base, const uint32_t *tmpl, int k) {
+    const bool pristine = template_gen(c.gen) && ((base[(c.GW + 1) * 32] >> 24) & FLAG_PRISTINE);
+    if (!pristine) return base[k * 32];
+    uint32_t w = tmpl[k];
+    for (int j = 0; j < c.n_obst; ++j) {
+        const uint32_t o = base[(c.GW + XWORDS + (j >> 1)) * 32] >> ((j & 1) * 16);
+        const int idx = (int)(o & 0xFF) * c.HP + (int)((o >> 8) & 0xFF);
+        if ((idx >> 2) == k) { const int sh = (idx & 3) * 8; w = (w & ~(0xFFu << sh)) | (CODE_BLUE_BALL << sh); }
+    }
+    return w;
+}
+
 // ------------------------------------------------------------------------------------------
 // layout generators (reset): the static part comes from the template, the random part mirrors
 // the reference draw for draw.
@@ -365,7 +407,7 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
         return;
     }
     // Grid(width,height) + static walls/goal
-    if (GEN == GEN_DYNOBS && (e.flags & 1)) {
+    if (GEN == GEN_DYNOBS && (e.flags & FLAG_PRISTINE)) {
         // nothing but the balls ever changes in this env (actions >= 3 are clamped, dynamicobstacles.py:62-63):
         // removing the old balls restores the template
         for (int k = 0; k < c.n_obst; ++k) { int ox, oy; obst_get(st, c, k, ox, oy); cell_wr(st, ox * HP + oy, CODE_EMPTY); }
@@ -382,6 +424,7 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
     if (GEN == GEN_EMPTY) {                              // envs/empty.py:30-57 (extra == 0)
         if (!c.random_start) { e.ax = 1; e.ay = 1; e.dir = 0; }
         else ok = place_agent(st, e, rg, p, 0, 0, W, H, -1);
+        e.flags |= FLAG_PRISTINE;
     } else if (GEN == GEN_DOORKEY) {                     // envs/doorkey.py:15-44
         const int split = rand_int(rg, p, 2, W - 2);
         for (int j = 0; j < H; ++j) cell_wr(st, split * HP + j, CODE_WALL);
@@ -402,10 +445,14 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
         if (!c.random_start) { e.ax = 1; e.ay = 1; e.dir = 0; }
         else ok = place_agent(st, e, rg, p, 0, 0, W, H, -1);
         for (int k = 0; k < c.n_obst; ++k) {
-            ok = place_obj<true>(st, e, rg, p, code_of(T_BALL, C_BLUE, 0), 0, 0, W, H, false, 100, true, x, y) && ok;   // resets are frequent here: inline Philox
-            obst_set(st, c, k, x, y);
+            const bool placed = place_obj<true>(st, e, rg, p, code_of(T_BALL, C_BLUE, 0), 0, 0, W, H, false, 100, true, x, y);   // resets are frequent here: inline Philox
+            // 101 rejected tries (the reference raises RecursionError): no position to record -- the ball is parked on the
+            // agent's start cell record-wise (a move from there finds no free neighbour or steps off normally) and the
+            // failure is flagged
+            obst_set(st, c, k, placed ? x : e.ax, placed ? y : e.ay);
+            ok = ok && placed;
         }
-        e.flags |= 1;
+        e.flags |= FLAG_PRISTINE;
     } else if (GEN == GEN_KEYCORRIDOR) {                 // roomgrid.py:118-169 + envs/keycorridor.py:26-49
         Rooms R;
         const int rs = c.room_size, rows = c.num_rows;
@@ -780,6 +827,7 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         if (tog_vanish && fc >= CODE_KEYBOX0) nv = (uint32_t)code_of(T_KEY, (int)fc - CODE_KEYBOX0, 0);   // Box.toggle: cell := contents (:355-360)
         cell_wr(st, fidx, nv);
         e.dirty = true;
+        e.flags &= ~FLAG_PRISTINE;
         e.carry = pick ? (int)fc : (drop ? 0 : e.carry);
     }
     if (e.steps >= c.max_steps) done = true;
@@ -1096,7 +1144,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xFFFFFFFFu, (int)(threadIdx.x >> 5), 0), wpb = blockDim.x >> 5;
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);                       // 256 words
     uint32_t *axis = lut + lut_bytes(GEN) / 4;                                           // [2][AXIS_ENTRIES]
-    uint8_t *stage_base = smem_raw + table_bytes(GEN);
+    uint32_t *tmpl_s = reinterpret_cast<uint32_t *>(smem_raw + table_bytes(GEN));
+    uint8_t *stage_base = smem_raw + table_bytes(GEN) + tmpl_smem_bytes(GEN, c.GW);
+    if (template_gen(GEN))
+        for (int i = threadIdx.x; i < c.GW; i += blockDim.x) tmpl_s[i] = __ldg(&p.tmpl[i]);
     constexpr int SB = stage_bytes(V), OB = obs_bytes(V), SB_OBS = GROUP * OB;
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * SB);
     uint32_t *st_warp = reinterpret_cast<uint32_t *>(stage_base + wpb * SB) + warp * ((c.S + 1) * 32);
@@ -1115,6 +1166,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
     const int S = c.S, GW = c.GW;
     const int64_t stride = p.stride;
     uint32_t phase = 0;
+    bool cols_hold_template = false;       // warp-uniform: every column of the warp's state block holds exactly the template grid
     for (int g = blockIdx.x * wpb + warp; g < p.n_groups; g += gridDim.x * wpb) {
         const int group = p.group0 + g;
         uint32_t *gst = p.state + (size_t)group * S * 32 + lane;
@@ -1127,9 +1179,37 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         const uint8_t *arow_p = p.actions + (int64_t)lane * p.stride + (int64_t)group * 32;
         const bool afast = ((p.stride & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.actions) & 15) == 0) && ((int64_t)group * 32 + 32 <= p.n_envs);
         if (PACKED && p.T > 1) actions_issue(arow, arow_p, lane < p.T, afast);
+        // Single-step launches are bound by the latency of the state round trip.  For the Empty kernels (4 rows of state per
+        // group once the grid is implied) the rows and actions of the warp's NEXT group are pulled into L2 now, so that its
+        // bulk load and action load are L2 hits: +3 %.  Measured and rejected for the kernels with large state blocks, which
+        // are HBM-bound in this mode (DoorKey-16x16 -16 %, FourRooms -10 %, Dynamic-Obstacles -1.5 %).
+        if (GEN == GEN_EMPTY && p.T <= 1) {
+            const int gn = g + gridDim.x * wpb;
+            if (gn < p.n_groups) {
+                const uint32_t *nb = p.state + (size_t)(p.group0 + gn) * S * 32;
+                for (int r = GW + lane; r < S; r += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)r * 32));
+                if (lane == 0 && p.T > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + (int64_t)(p.group0 + gn) * 32));
+            }
+        }
         // ---- load the group's state block: S coalesced 128-byte rows -> bank == lane ----
-        load_state_block((uint32_t)__cvta_generic_to_shared(st_warp), p.state + (size_t)group * S * 32, (uint32_t)S * 128u, mbar_sa, phase, lane);
-        phase ^= 1u;
+        // Single-step launches of the template-grid kernels (Empty, Dynamic-Obstacles) first fetch only the non-grid rows;
+        // when every env of the group is pristine -- the normal case -- the grid rows never cross HBM at all (they are
+        // rebuilt below), which cuts the state round trip of a step from S to S-GW rows.
+        const uint32_t st_warp_sa = (uint32_t)__cvta_generic_to_shared(st_warp);
+        const uint32_t *gblock = p.state + (size_t)group * S * 32;
+        if (template_gen(GEN) && p.T <= 1) {
+            load_state_block(st_warp_sa + (uint32_t)GW * 128u, gblock + (size_t)GW * 32, (uint32_t)(S - GW) * 128u, mbar_sa, phase, lane);
+            phase ^= 1u;
+            if (!__all_sync(0xFFFFFFFFu, (st_warp[(GW + 1) * 32 + lane] >> 24) & FLAG_PRISTINE)) {      // rare: an uploaded / edited grid
+                load_state_block(st_warp_sa, gblock, (uint32_t)GW * 128u, mbar_sa, phase, lane);
+                phase ^= 1u;
+                cols_hold_template = false;
+            }
+        } else {
+            load_state_block(st_warp_sa, gblock, (uint32_t)S * 128u, mbar_sa, phase, lane);
+            phase ^= 1u;
+            cols_hold_template = false;
+        }
         st_warp[S * 32 + lane] = (uint32_t)CODE_WALL * 0x01010101u;        // out-of-grid pad (minigrid.py:469)
         Env e;
         Rng rg;
@@ -1155,6 +1235,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         }
         rg.rblk = 0xFFFFFFFFu; rg.err = 0; e.dirty = false;
         rg.rb0 = rg.rb1 = rg.rb2 = rg.rb3 = 0;
+        if (template_gen(GEN)) {
+            // the grid rows of a pristine env in HBM are don't-care: rebuild.  An Empty grid IS the template, so once a warp's
+            // columns hold it (left there by the previous all-pristine group of a single-step launch) there is nothing to do.
+            if ((e.flags & FLAG_PRISTINE) && !(GEN == GEN_EMPTY && cols_hold_template)) rebuild_pristine_grid(st, p, tmpl_s);
+        }
 
         const bool full = ((int64_t)group * 32 + 32) <= p.n_envs;
         const int nvalid = full ? 32 : (int)max((int64_t)0, p.n_envs - (int64_t)group * 32);
@@ -1209,7 +1294,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
                     need_reset = done && p.autoreset;
                 }
                 if (GEN == GEN_DYNOBS) {                        // frequent resets: regenerate finished envs with the whole warp
-                    uint32_t rm = __ballot_sync(0xFFFFFFFFu, need_reset && !p.tape && (e.flags & 1));
+                    uint32_t rm = __ballot_sync(0xFFFFFFFFu, need_reset && !p.tape && (e.flags & FLAG_PRISTINE));
                     while (rm) {
                         const int src = __ffs((int)rm) - 1;
                         rm &= rm - 1;
@@ -1260,7 +1345,8 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         st[(GW + 2) * 32] = rg.episode;
         st[(GW + 3) * 32] = rg.ndraws;
         if (GEN == GEN_POOL) st[(GW + XWORDS) * 32] = (uint32_t)pc.level;
-        const bool any_dirty = __any_sync(0xFFFFFFFFu, e.dirty);
+        // grid rows go back only for envs whose grid is not implied by the template and the ball list
+        const bool any_dirty = __any_sync(0xFFFFFFFFu, e.dirty && !(template_gen(GEN) && (e.flags & FLAG_PRISTINE)));
         const int k0 = any_dirty ? 0 : GW;                            // an untouched grid stays where it is
         if (any_dirty || p.T > 1) {      // a clean single step writes 4-5 rows: the loop is cheaper
             // one bulk copy (rows k0..S-1 are contiguous here and in HBM) instead of a 7-instruction loop per word;
@@ -1275,6 +1361,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
             __syncwarp();
             for (int k = k0; k < S; ++k) gst[k * 32] = st_warp[k * 32 + lane];
         }
+        if (GEN == GEN_EMPTY) cols_hold_template = __all_sync(0xFFFFFFFFu, e.flags & FLAG_PRISTINE);
         if (rg.err) atomicOr(p.err, rg.err);
         __syncwarp();
     }
@@ -1287,6 +1374,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
 struct StateIO {
     DevCfg cfg;
     uint32_t *state;
+    const uint32_t *tmpl;
     int64_t first, count;
     uint8_t *grid;        // [count][W][H][3]
     uint8_t *aux;         // [count][W][H]
@@ -1311,6 +1399,19 @@ __device__ __forceinline__ int encode_cell(int t, int c, int s, int auxbits, uin
         return CODE_KEYBOX0 + ((auxbits >> 1) & 7) - 1;
     }
     return code_of(t, c, s);
+}
+
+// Before a partial upload: the grid rows of pristine envs in [first, first+count) become real (template + balls) and the
+// envs stop being pristine, so that whatever k_set_state leaves untouched is what a reader saw before.  One thread per env.
+__global__ void k_materialize(DevCfg c, uint32_t *state, const uint32_t *__restrict__ tmpl, int64_t first, int64_t count) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= count || !template_gen(c.gen)) return;
+    const int64_t env = first + n;
+    uint32_t *base = state + (env >> 5) * c.S * 32 + (env & 31);
+    const uint32_t fw = base[(c.GW + 1) * 32];
+    if (!((fw >> 24) & FLAG_PRISTINE)) return;
+    for (int k = 0; k < c.GW; ++k) base[k * 32] = grid_word(c, base, tmpl, k);
+    base[(c.GW + 1) * 32] = fw & ~((uint32_t)FLAG_PRISTINE << 24);
 }
 
 // one thread per (env, state word)
@@ -1355,7 +1456,7 @@ __global__ void k_set_state(const StateIO io) {
         *dst = w;
     } else if (k == c.GW + 1) {
         uint32_t w = *dst;
-        if (io.grid) w &= 0x00FFFFFFu;                      // flags: an uploaded grid is no longer 'template + balls'
+        if (io.grid || io.obstacles) w &= 0x00FFFFFFu;      // flags: an uploaded grid / ball list ends 'template + balls' (state_io materialises the grid first)
         if (io.agent) w = (w & 0xFFFF0000u) | (uint32_t)(io.agent[n * 4 + 3] & 0xFFFF);
         if (io.target) {
             const uint8_t *q = io.target + n * 2;
@@ -1385,7 +1486,7 @@ __global__ void k_get_state(const StateIO io, int full_obs) {
     if (n >= io.count) return;
     const int64_t env = io.first + n;
     const uint32_t *base = io.state + (env >> 5) * c.S * 32 + (env & 31);
-    const uint32_t w = base[k * 32];
+    const uint32_t w = k < c.GW ? grid_word(c, base, io.tmpl, k) : base[k * 32];
     const int cells = c.W * c.H;
     const int HW = c.HP >> 2;
     if (k < c.GW) {
@@ -1555,7 +1656,7 @@ __global__ void k_render_partial(const uint8_t *__restrict__ obs, int V, const u
 // agent's view and is visible there; visibility is read off the partial observation (type != unseen, as Grid.decode
 // does, minigrid.py:613), view cell (vx,vy) of world cell p being  vx = (p-agent).r + V/2,  vy = V-1 - (p-agent).f.
 template <typename IDX>
-__global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, const uint8_t *__restrict__ obs, int V,
+__global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, const uint32_t *__restrict__ tmpl, const uint8_t *__restrict__ obs, int V,
                               const uint8_t *__restrict__ atlas, int tile, uint8_t *__restrict__ out, int64_t N) {
     const IDX rows = (IDX)(c.H * tile), uW = (IDX)c.W;
     const IDX total = (IDX)N * rows * uW;
@@ -1567,7 +1668,7 @@ __global__ void k_render_full(DevCfg c, const uint32_t *__restrict__ state, cons
         const int cy = row / tile, py = row - cy * tile;
         const uint32_t *base = state + (size_t)(n >> 5) * c.S * 32 + (n & 31);
         const int cidx = cx * c.HP + cy;
-        const uint32_t cc = (base[(cidx >> 2) * 32] >> ((cidx & 3) * 8)) & 0xFF;
+        const uint32_t cc = (grid_word(c, base, tmpl, cidx >> 2) >> ((cidx & 3) * 8)) & 0xFF;
         const uint32_t x = lut_entry((int)cc);                  // (type, colour, state) of the real object
         const int code = (int)(x & 0xFF) * 21 + (int)((x >> 8) & 0xFF) * 3 + (int)((x >> 16) & 0xFF);
         const uint32_t w0 = base[c.GW * 32];

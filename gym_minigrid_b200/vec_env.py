@@ -75,8 +75,40 @@ def _philox4x32_10(ctr, key):
     return c0, c1, c2, c3
 
 
+class BatchedGrid:
+    """`env.grid` of a batched env: nothing is copied until a method is called."""
+
+    def __init__(self, env):
+        self._env = env
+        self.width, self.height = env.width, env.height
+
+    def encode(self, vis_mask=None):
+        """Grid.encode (minigrid.py:571-594) for every env: uint8 [N, width, height, 3]; vis_mask: bool [N, W, H] or [W, H]"""
+        g = self._env.get_state(("grid",))["grid"]
+        if vis_mask is not None:
+            m = torch.as_tensor(vis_mask, device=g.device).to(torch.bool)
+            g = g * m.expand(g.shape[:3]).unsqueeze(-1).to(g.dtype)
+        return g
+
+    def get(self, i, j):
+        """Grid.get (minigrid.py:417-420) as encodings: uint8 [N, 3] = (type, colour, state) of cell (i, j); empty = (1, 0, 0)"""
+        assert 0 <= i < self.width and 0 <= j < self.height
+        return self.encode()[:, i, j]
+
+    def __contains__(self, key):
+        """(colour, type) in grid (minigrid.py:377-391) -- true if ANY env of the batch holds such an object"""
+        c, t = key
+        g = self.encode()
+        m = torch.ones(g.shape[:3], dtype=torch.bool, device=g.device)
+        if t is not None:
+            m &= g[..., 0] == OBJECT_TO_IDX[t]
+        if c is not None:
+            m &= g[..., 1] == COLOR_TO_IDX[c]
+        return bool(m.any())
+
+
 class VecMiniGridEnv:
-    metadata = {'render.modes': [], 'video.frames_per_second': 10}
+    metadata = {'render.modes': ['rgb_array'], 'video.frames_per_second': 10}    # minigrid.py:725-728; no window ('human')
     Actions = Actions
 
     def __init__(self, spec, num_envs=1, device=None, seed=1337, env_id_base=0, autoreset=True, agent_view_size=7):
@@ -117,12 +149,6 @@ class VecMiniGridEnv:
         if not autoreset:
             self.set_autoreset(False)
         self._tape = None
-        N = self.num_envs
-        with torch.cuda.device(self.device):
-            self._obs = torch.empty((N, V, V, 3), dtype=torch.uint8, device=self.device)
-            self._dir = torch.empty((N,), dtype=torch.uint8, device=self.device)
-            self._rew = torch.empty((N,), dtype=torch.float64, device=self.device)
-            self._done = torch.empty((N,), dtype=torch.uint8, device=self.device)
         self._host = None
         self._render_scratch = None
 
@@ -140,6 +166,14 @@ class VecMiniGridEnv:
         if tuple(a.shape) != tuple(shape):
             raise ValueError("actions must have shape %s, got %s" % (tuple(shape), tuple(a.shape)))
         return a
+
+    def _new_out(self):
+        """fresh (obs, reward, done, dir) tensors: like the reference, reset() / step() hand out new arrays on every
+        call, so an `obs` kept by the caller is never overwritten by a later step.  Allocation only (the kernel writes
+        straight into them); pass `out=` to step() / rollout() to reuse buffers instead."""
+        N, V, dev = self.num_envs, self.agent_view_size, self.device
+        return (torch.empty((N, V, V, 3), dtype=torch.uint8, device=dev), torch.empty((N,), dtype=torch.float64, device=dev),
+                torch.empty((N,), dtype=torch.uint8, device=dev), torch.empty((N,), dtype=torch.uint8, device=dev))
 
     def _obs_dict(self, image, direction):
         return {'image': image, 'direction': direction, 'mission': MissionBatch(self)}
@@ -194,13 +228,16 @@ class VecMiniGridEnv:
         if mask is not None:
             m = torch.as_tensor(mask).to(self.device).to(torch.uint8).contiguous()
             assert m.shape == (self.num_envs,)
-        _lib.check(self._L.mgb_reset(self._h, _ptr(m), _ptr(self._obs), _ptr(self._dir), self._stream()))
-        return self._obs_dict(self._obs, self._dir)
+        obs, _, _, d = self._new_out()
+        _lib.check(self._L.mgb_reset(self._h, _ptr(m), _ptr(obs), _ptr(d), self._stream()))
+        return self._obs_dict(obs, d)
 
     def step(self, actions, out=None):
-        """MiniGridEnv.step for every env.  `out` = optional (obs, reward, done, dir) tensors to write into."""
+        """MiniGridEnv.step for every env.  Returns fresh tensors on every call (as the reference returns fresh arrays);
+        `out` = optional (obs, reward, done, dir) tensors to write into instead (zero-allocation loop: the caller then
+        owns the aliasing)."""
         a = self._actions(actions, (self.num_envs,))
-        obs, reward, done, d = out if out is not None else (self._obs, self._rew, self._done, self._dir)
+        obs, reward, done, d = out if out is not None else self._new_out()
         _lib.check(self._L.mgb_step(self._h, _ptr(a), _ptr(obs), _ptr(reward), _ptr(done), _ptr(d), self._stream()))
         return self._obs_dict(obs, d), reward, done.view(torch.bool), {}
 
@@ -312,6 +349,12 @@ class VecMiniGridEnv:
         self._pool_missions = list(missions) if missions is not None else None
         self.check_errors()
 
+    def level_index_device(self):
+        """which pool level each env is currently playing, int32 [N] on the device"""
+        lv = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)
+        _lib.check(self._L.mgb_get_levels(self._h, _ptr(lv), self._stream()))
+        return lv
+
     def level_index(self, first=0, count=None):
         """which pool level each env is currently playing"""
         lv = torch.empty((self.num_envs,), dtype=torch.int32, device=self.device)
@@ -394,6 +437,12 @@ class VecMiniGridEnv:
     @property
     def carrying(self):
         return self.get_state(("carrying",))["carrying"]
+
+    @property
+    def grid(self):
+        """env.grid, batched (minigrid.py:366-615): a lazy view of the device state with the Grid methods that make sense
+        for a batch -- width, height, encode(), get(i, j)."""
+        return BatchedGrid(self)
 
     # ------------------------------------------------------------------ MiniGridEnv geometry helpers, batched
     # (minigrid.py:1092-1225).  Scalars broadcast over the batch; "None" results become a boolean mask.

@@ -196,12 +196,25 @@ class FlatObsWrapper(ObservationWrapper):
         u = env.unwrapped
         tmpl = u._mission
         # every mission string this env can produce: one for the static ones, one per target colour for
-        # KeyCorridor ("pick up the <colour> ball", keycorridor.py:49); row index = colour id
-        if "%s" in tmpl:
+        # KeyCorridor ("pick up the <colour> ball", keycorridor.py:49; row index = colour id), and for the level-pool
+        # ids whose mission names the level's target (Fetch, GoToDoor, GoToObject, PutNear ...) the distinct
+        # strings of the uploaded pool (row index = _lvl2row[level the env is playing])
+        self._per_colour = False
+        self._lvl2row = None
+        if u._pool_missions is not None:
+            uniq = sorted(set(u._pool_missions))
+            if len(uniq) > 256:
+                raise _lib.MgbError("FlatObsWrapper: %d distinct missions in the level pool (at most 256)" % len(uniq))
+            row = {m: k for k, m in enumerate(uniq)}
+            self._lvl2row = torch.as_tensor(np.array([row[m] for m in u._pool_missions], np.uint8)).to(u.device)
+            missions = uniq
+        elif u._pool_n and "(per level)" in tmpl:
+            raise _lib.MgbError("FlatObsWrapper: this level-pool env has per-level missions but none were uploaded "
+                                "(set_level_pool(..., missions=[...]))")
+        elif "%s" in tmpl:
             self._per_colour = True
             missions = [tmpl % (IDX_TO_COLOR[c], IDX_TO_OBJECT[6]) for c in range(len(COLOR_TO_IDX))]
         else:
-            self._per_colour = False
             missions = [tmpl]
         table = np.stack([self._encode(m) for m in missions])
         self._table = torch.as_tensor(table).to(u.device)
@@ -227,6 +240,8 @@ class FlatObsWrapper(ObservationWrapper):
         midx = None
         if self._per_colour:
             midx = u.get_state(("target",))["target"][:, 1].contiguous()
+        elif self._lvl2row is not None:
+            midx = self._lvl2row[u.level_index_device().long()].contiguous()
         mlen = self._table.shape[1]
         out = torch.empty((N, self._img_bytes + mlen), dtype=torch.float32, device=img.device)
         with torch.cuda.device(img.device):
@@ -336,7 +351,8 @@ class _TakesOverAutoReset(Wrapper):
         if not self._autoreset:
             return obs
         u = self.unwrapped
-        _lib.check(u._L.mgb_reset(u._h, _ptr(done.view(torch.uint8)), _ptr(u._obs), _ptr(u._dir), u._stream()))
+        # in place: the step's own (fresh) observation tensors receive the first observation of the new episodes
+        _lib.check(u._L.mgb_reset(u._h, _ptr(done.view(torch.uint8)), _ptr(obs['image']), _ptr(obs['direction']), u._stream()))
         return obs
 
 

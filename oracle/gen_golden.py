@@ -615,7 +615,9 @@ def hook_traces():
             env.seed(200 + k)
             obs = env.reset()
             s = R.snapshot(env)
-            levels.append(dict(grid=s["grid"], aux=s["aux"], agent=s["agent"][:3].copy(), mission=obs["mission"],
+            # the reference's own FlatObsWrapper on the level's first observation: image ++ one-hot of THIS level's mission
+            flat0 = np.asarray(sys.modules["gym_minigrid.wrappers"].FlatObsWrapper(env).observation(obs), np.float32)
+            levels.append(dict(grid=s["grid"], aux=s["aux"], agent=s["agent"][:3].copy(), mission=obs["mission"], flat0=flat0,
                                hp=hook_params_of(env.unwrapped, hook), env=copy.deepcopy(env.unwrapped)))
         idx = [8, 123]
         tr = dict(obs=[], dir=[], reward=[], done=[], actions=[], obs0=[], dir0=[], lvl=[], grid_end=[], agent_end=[])
@@ -665,6 +667,7 @@ def hook_traces():
                             level_agent=np.stack([l["agent"] for l in levels]).astype(np.int32),
                             level_hook=np.array([l["hp"] for l in levels], np.int32),
                             level_mission=np.array([l["mission"] for l in levels]), sc_len=sc_len,
+                            level_flat=np.stack([l["flat0"] for l in levels]),
                             **{k: np.stack(v) for k, v in tr.items()}, **extra)
         print("%-44s %6.1f KB hook=%d episodes=%s rewards(random)=%d scenarios=%d (reward>0: %d, done: %d)" % (
             os.path.basename(path), os.path.getsize(path) / 1024, hook, [int((l >= 0).sum()) for l in tr["lvl"]],

@@ -405,3 +405,114 @@ def test_invalid_action_inside_a_rollout_is_flagged():
         env.rollout(a)
         with pytest.raises(Exception, match="unknown action"):
             env.check_errors()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Batched replays of the golden traces: every trace of a fixture file in ONE handle of full 32-env groups, the whole
+# trace in ONE persistent launch -- the bulk-copy (TMA) observation path, the packed action path and the
+# warp-cooperative Dynamic-Obstacles reset are compared with the reference's bytes directly.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", golden_files("tape_"), ids=os.path.basename)
+def test_batched_tape_replay_matches_reference(path):
+    """RNG-tape mode: env j of a 64-env handle replays trace j mod n (its own copy of the reference's MT19937 draws)."""
+    mgb = _mgb()
+    d = load(path)
+    n, T = d["actions"].shape[:2]
+    N = 64
+    which = np.arange(N) % n
+    tapes = [d["tape"][int(d["tape_offsets"][k]):int(d["tape_offsets"][k + 1])] for k in which]
+    offs = np.concatenate([[0], np.cumsum([len(t) for t in tapes])]).astype(np.int64)
+    env = mgb.make(d["env_id"], num_envs=N, seed=int(d["seed"]))
+    env.set_rng_tape(np.concatenate(tapes) if offs[-1] else np.zeros(0, np.int32), offs)
+    obs = env.reset()
+    tag = os.path.basename(path)
+    assert_same(tag + " obs0", _np(obs["image"]), d["obs0"][which])
+    assert_same(tag + " dir0", _np(obs["direction"]), d["dir0"][which].astype(np.uint8))
+    o, r, dn, dr = env.rollout(torch.as_tensor(d["actions"][which].T.copy()))
+    assert_same(tag + " done", _np(dn).T.astype(np.uint8), d["done"][which])
+    assert_same(tag + " obs", _np(o).transpose(1, 0, 2, 3, 4), d["obs"][which])
+    assert_same(tag + " dir", _np(dr).T, d["dir"][which])
+    assert_same(tag + " reward bits", bits(_np(r).T.copy()), bits(d["reward"][which]))
+    env.check_errors()
+    env.close()
+
+
+@pytest.mark.parametrize("path", golden_files("philox_"), ids=os.path.basename)
+def test_batched_philox_replay_matches_reference(path):
+    """Philox mode: one handle covers the global env ids of all traces of the file (the others idle on action 'done'),
+    so that the traces run on the device generators, the auto-reset and the bulk-copy path of full groups."""
+    mgb = _mgb()
+    d = load(path)
+    ids = [int(i) for i in d["env_indices"]]
+    keep = [k for k, i in enumerate(ids) if i < (1 << 20)]                     # the id beyond 2^32 has its own single-env test
+    base = min(ids[k] for k in keep)
+    N = (max(ids[k] for k in keep) - base + 1 + 31) // 32 * 32
+    T = d["actions"].shape[1]
+    n_act = int(d["cfg"]["n_actions"])
+    acts = np.full((T, N), min(6, n_act - 1), np.uint8)                        # idle envs: 'done' (or the last action that exists)
+    for k in keep:
+        acts[:, ids[k] - base] = d["actions"][k]
+    env = mgb.make(d["env_id"], num_envs=N, seed=int(d["seed"]), env_id_base=base)
+    obs = env.reset()
+    tag = os.path.basename(path)
+    cols = [ids[k] - base for k in keep]
+    assert_same(tag + " obs0", _np(obs["image"])[cols], d["obs0"][keep])
+    o, r, dn, dr = env.rollout(torch.as_tensor(acts))
+    assert_same(tag + " done", _np(dn)[:, cols].T.astype(np.uint8), d["done"][keep])
+    assert_same(tag + " obs", _np(o)[:, cols].transpose(1, 0, 2, 3, 4), d["obs"][keep])
+    assert_same(tag + " dir", _np(dr)[:, cols].T, d["dir"][keep])
+    assert_same(tag + " reward bits", bits(_np(r)[:, cols].T.copy()), bits(d["reward"][keep]))
+    env.check_errors()
+    env.close()
+
+
+def test_step_and_reset_return_fresh_tensors():
+    """like the reference (fresh numpy arrays per call), obs from reset()/step() must survive later steps"""
+    mgb = _mgb()
+    env = mgb.make("MiniGrid-DoorKey-8x8-v0", num_envs=96, seed=3)
+    o0 = env.reset()
+    keep0 = o0["image"].clone()
+    a = torch.randint(0, 7, (96,), dtype=torch.uint8)
+    o1, r1, d1, _ = env.step(a)
+    keep1, keepr = o1["image"].clone(), r1.clone()
+    o2, r2, d2, _ = env.step(torch.full((96,), 2, dtype=torch.uint8))
+    env.gen_obs(); env.agent_sees(1, 1)
+    assert torch.equal(o0["image"], keep0) and torch.equal(o1["image"], keep1) and torch.equal(r1, keepr)
+    assert o1["image"].data_ptr() != o2["image"].data_ptr() != o0["image"].data_ptr()
+    # out= is the zero-allocation path: the caller's buffers are written
+    out = env._new_out()
+    o3, r3, d3, _ = env.step(a, out=out)
+    assert o3["image"].data_ptr() == out[0].data_ptr() and r3.data_ptr() == out[1].data_ptr()
+
+
+def test_env_grid_and_metadata():
+    """env.grid (SURVEY 8b attribute list): lazy batched view with encode()/get(); render.modes lists rgb_array"""
+    mgb = _mgb()
+    env = mgb.make("MiniGrid-Empty-8x8-v0", num_envs=40)
+    env.reset()
+    g = env.grid
+    assert (g.width, g.height) == (8, 8)
+    enc = _np(g.encode())
+    assert enc.shape == (40, 8, 8, 3)
+    assert_same("grid == get_state", enc, _np(env.get_state(("grid",))["grid"]))
+    assert_same("goal", _np(g.get(6, 6)), np.tile(np.array([8, 1, 0], np.uint8), (40, 1)))
+    assert_same("wall", _np(g.get(0, 3)), np.tile(np.array([2, 5, 0], np.uint8), (40, 1)))
+    assert ('green', 'goal') in g and ('red', 'key') not in g
+    m = np.zeros((8, 8), bool); m[6, 6] = True
+    assert int(_np(g.encode(vis_mask=m))[:, :, :, 0].sum()) == 40 * 8
+    assert 'rgb_array' in env.metadata['render.modes']
+    assert env.render('rgb_array').shape == (40, 64, 64, 3)
+
+
+def test_handle_calls_leave_the_current_device_alone():
+    """entry points run on the handle's device and restore the caller's current device"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    mgb = _mgb()
+    torch.cuda.set_device(0)
+    env = mgb.make("MiniGrid-Empty-8x8-v0", num_envs=64, device="cuda:1")
+    env.reset()
+    env.step(torch.zeros(64, dtype=torch.uint8))
+    assert torch.cuda.current_device() == 0
+    x = torch.ones(4, device="cuda")
+    assert x.device.index == 0

@@ -58,7 +58,7 @@ def test_onehot_partial_and_reseed():
     a = torch.randint(0, 7, (257,), dtype=torch.uint8)
     for _ in range(5):
         obs, _, _, _ = env.step(a)
-    img = _np(env.unwrapped._obs)
+    img = _np(env.unwrapped.gen_obs()["image"])      # the raw observation of the current state
     want = np.zeros((257, 7, 7, 21), np.uint8)
     n, i, j = np.meshgrid(np.arange(257), np.arange(7), np.arange(7), indexing="ij")
     want[n, i, j, img[..., 0]] = 1
@@ -90,5 +90,38 @@ def test_wrapper_kernels_full_size():
     assert o.shape == (N, 16, 16, 11 + 4) and bool((o.sum(-1) == 2).all())
     fl = W.FlatObsWrapper(base)
     f = fl.observation(base.reset())
-    assert torch.equal(f[:, :147].to(torch.uint8).reshape(N, 7, 7, 3), base._obs)
+    assert torch.equal(f[:, :147].to(torch.uint8).reshape(N, 7, 7, 3), base.gen_obs()["image"])
     assert bool((f[:, 147:] == f[0, 147:]).all()) and float(f[0, 147:].sum()) == len(base._mission)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hook_fetch_8x8_n3.npz", "hook_gotodoor_6x6.npz", "hook_putnear_8x8_n3.npz", "hook_gotoobject_8x8_n2.npz"])
+def test_flat_obs_encodes_each_levels_own_mission(name):
+    """FlatObsWrapper on a level-pool id must one-hot the mission of the level each env is playing
+    (fetch.py:63-72 etc. name the target), not the registry placeholder.  level_flat = the reference's own
+    FlatObsWrapper output on each level's first observation."""
+    import os
+    import numpy as np
+    import torch
+    import gym_minigrid_b200 as mgb
+    from gym_minigrid_b200 import wrappers as W
+    from helpers import load, assert_same
+    d = load(os.path.join(os.path.dirname(__file__), "golden", name))
+    levels = dict(grid=d["level_grid"], aux=d["level_aux"], agent=d["level_agent"], missions=[str(m) for m in d["level_mission"]],
+                  hook_params=d["level_hook"] if d["cfg"]["hook"] else None)
+    N = 200
+    env = W.FlatObsWrapper(mgb.make(d["env_id"], num_envs=N, seed=5, levels=levels))
+    flat = env.reset()
+    for step in range(6):
+        lv = env.unwrapped.level_index()
+        got = flat.cpu().numpy()
+        assert got.shape == (N, 147 + 27 * 96) and got.dtype == np.float32
+        assert_same("mission one-hot", got[:, 147:], d["level_flat"][lv][:, 147:])
+        if step == 0:        # at reset the image part is the level's first observation too
+            assert_same("image part", got[:, :147], d["level_flat"][lv][:, :147])
+        assert len(set(lv.tolist())) > 1
+        flat, _, _, _ = env.step(torch.randint(0, 7, (N,), dtype=torch.uint8))
+    # without missions the wrapper refuses instead of encoding the placeholder
+    bare = mgb.make(d["env_id"], num_envs=4, levels={k: v for k, v in levels.items() if k != "missions"})
+    with pytest.raises(mgb.MgbError):
+        W.FlatObsWrapper(bare)
