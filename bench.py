@@ -395,6 +395,30 @@ def main():
         e2e = {"value": world * N * Ke / float(te.item()), "unit": "env-steps/s", "h2d_bytes_per_step": N,
                "d2h_bytes_per_step": N * (147 + 8 + 1 + 1), "steps": Ke, "api": "VecMiniGridEnv.step_host -> mgb_step_host",
                "numa_node": numa}
+        # The ceiling of this number: the same bytes per step as BARE pinned copies (no kernel), all ranks at the same time.
+        # e2e is PCIe/host-bound; `frac_of_copy_ceiling` says how much of what the box can copy the pipeline delivers.
+        d2h_bytes = N * (147 + 8 + 1 + 1)
+        dbuf = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+        hbuf = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+        dact = torch.empty(N, dtype=torch.uint8, device=dev)
+        for i in range(2 + Ke):
+            if i == 2:
+                barrier()
+                t0 = time.perf_counter()
+            dact.copy_(hacts[i % 2], non_blocking=True)
+            hbuf.copy_(dbuf, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        tc = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        ceil_steps = world * N * Ke / float(tc.item())
+        e2e.update({"copy_ceiling_env_steps_per_s": ceil_steps, "copy_ceiling_gbs": ceil_steps * 158 / 1e9,
+                    "achieved_gbs": e2e["value"] * 158 / 1e9, "frac_of_copy_ceiling": e2e["value"] / ceil_steps})
+        try:
+            e2e["numa_nodes_online"] = open("/sys/devices/system/node/online").read().strip()
+        except OSError:
+            pass
+        del dbuf, hbuf, dact
         os.sched_setaffinity(0, affinity0)
 
     # ---- secondary: single-step launches, i.e. the gym API env.step() (state round-trips HBM every step) ----
