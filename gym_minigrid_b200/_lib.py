@@ -23,7 +23,7 @@ ERROR_BITS = {
 class MgbConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "gen", "width", "height", "max_steps", "see_through", "n_actions",
-        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1", "agent_view_size", "hook")]
+        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1", "agent_view_size", "hook", "gen_param0", "gen_param1")]
 
 
 # name -> (restype, argtypes); the single source of truth checked against include/mgb200.h by the tests

@@ -106,6 +106,8 @@ static rollout_fn pick_kernel_v(const mgb_config &c) {
     case MGB_GEN_DYNOBS: return c.see_through ? k_rollout<GEN_DYNOBS, true, V> : nullptr;
     case MGB_GEN_KEYCORRIDOR: return c.see_through ? nullptr : k_rollout<GEN_KEYCORRIDOR, false, V>;
     case MGB_GEN_POOL: return c.see_through ? k_rollout<GEN_POOL, true, V> : k_rollout<GEN_POOL, false, V>;
+    case MGB_GEN_CROSSING: case MGB_GEN_LAVAGAP: case MGB_GEN_MULTIROOM:
+        return c.see_through ? nullptr : k_rollout<GEN_PROC, false, V>;
     }
     return nullptr;
 }
@@ -131,7 +133,7 @@ static std::vector<uint32_t> build_template(const mgb_config &c, int GW, int HP)
         for (int j = 0; j < h; ++j) { set(x0, y0 + j, CODE_WALL); set(x0 + w - 1, y0 + j, CODE_WALL); }
     };
     switch (c.gen) {
-    case MGB_GEN_EMPTY: case MGB_GEN_DOORKEY: case MGB_GEN_DYNOBS:
+    case MGB_GEN_EMPTY: case MGB_GEN_DOORKEY: case MGB_GEN_DYNOBS: case MGB_GEN_CROSSING: case MGB_GEN_LAVAGAP:   // crossing.py:31-38, lavagap.py:28-37
         wall_rect(0, 0, W, H);
         set(W - 2, H - 2, CODE_GOAL);                      // empty.py:48, doorkey.py:23, dynamicobstacles.py:43
         break;
@@ -169,6 +171,13 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
         if (c.num_rows < 1 || c.num_rows > 3 || c.room_size < 3) return fail("mgb_create: bad RoomGrid shape");
         if (c.width != (c.room_size - 1) * 3 + 1 || c.height != (c.room_size - 1) * c.num_rows + 1) return fail("mgb_create: RoomGrid size mismatch (roomgrid.py:85-86)");
     }
+    if (c.gen == MGB_GEN_CROSSING) {
+        if ((c.width & 1) == 0 || (c.height & 1) == 0 || c.width < 5 || c.height < 5) return fail("mgb_create: Crossing needs an odd grid size (crossing.py:25)");
+        if (c.gen_param0 < 0 || (c.gen_param1 & 3) > 2 || (c.gen_param1 & ~7)) return fail("mgb_create: bad Crossing parameters");
+    }
+    if (c.gen == MGB_GEN_LAVAGAP && (c.width < 5 || c.height < 5)) return fail("mgb_create: LavaGap needs at least 5x5 (lavagap.py:22)");
+    if (c.gen == MGB_GEN_MULTIROOM && (c.gen_param0 < 1 || c.gen_param0 > 8 || c.gen_param1 < 4 || c.gen_param1 > 32 || c.width != c.height))
+        return fail("mgb_create: bad MultiRoom parameters (1..8 rooms, maxRoomSize 4..32, square grid)");
     if (c.hook < 0 || c.hook > MGB_HOOK_MEMORY || (c.hook != 0 && c.gen != MGB_GEN_POOL)) return fail("mgb_create: hook %d needs a level-pool handle (MGB_GEN_POOL)", c.hook);
     if (c.gen == MGB_GEN_DYNOBS && c.n_actions != 3) return fail("mgb_create: Dynamic-Obstacles has 3 actions");
     if (c.gen != MGB_GEN_DYNOBS && c.n_actions != 7) return fail("mgb_create: n_actions must be 7");
@@ -192,7 +201,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     DevCfg &d = h->dc;
     d.gen = c.gen; d.W = c.width; d.H = c.height; d.max_steps = c.max_steps; d.see_through = c.see_through;
     d.n_actions = c.n_actions; d.n_obst = c.n_obstacles; d.room_size = c.room_size; d.num_rows = c.num_rows;
-    d.random_start = c.random_start; d.lava_v1 = c.lava_v1; d.hook = c.hook;
+    d.random_start = c.random_start; d.lava_v1 = c.lava_v1; d.hook = c.hook; d.gp0 = c.gen_param0; d.gp1 = c.gen_param1;
     d.HP = (c.height + 3) / 4 * 4;
     d.GW = c.width * d.HP / 4;
     d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0) + (c.gen == MGB_GEN_POOL ? 1 : 0);   // pool: + level word

@@ -62,7 +62,11 @@ enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_K
              T_BOX = 7, T_GOAL = 8, T_LAVA = 9, T_AGENT = 10 };
 enum : int { C_RED = 0, C_GREEN = 1, C_BLUE = 2, C_PURPLE = 3, C_YELLOW = 4, C_GREY = 5, C_WHITE = 6 };
 enum : int { A_LEFT = 0, A_RIGHT = 1, A_FORWARD = 2, A_PICKUP = 3, A_DROP = 4, A_TOGGLE = 5, A_DONE = 6 };
-enum : int { GEN_EMPTY = 0, GEN_DOORKEY = 1, GEN_FOURROOMS = 2, GEN_DYNOBS = 3, GEN_KEYCORRIDOR = 4, GEN_POOL = 5 };
+enum : int { GEN_EMPTY = 0, GEN_DOORKEY = 1, GEN_FOURROOMS = 2, GEN_DYNOBS = 3, GEN_KEYCORRIDOR = 4, GEN_POOL = 5,
+             // kernel template value for the three procedural generators with the base step (the hot loop is the same;
+             // generate<GEN_PROC> switches on DevCfg::gen, which keeps the precise id below)
+             GEN_PROC = 6,
+             GEN_CROSSING = 6, GEN_LAVAGAP = 7, GEN_MULTIROOM = 8 };
 enum : uint32_t { ERR_ACTION = 1, ERR_TAPE_END = 2, ERR_TAPE_RANGE = 4, ERR_SAMPLING = 8, ERR_BOUNDS = 16, ERR_CODE = 32, ERR_NO_POOL = 64 };
 
 __host__ __device__ constexpr int code_of(int t, int c, int s) { return t * 21 + c * 3 + s; }
@@ -102,6 +106,7 @@ __host__ __device__ inline uint32_t lut_entry(int code) {
 
 struct DevCfg {
     int32_t gen, W, H, max_steps, see_through, n_actions, n_obst, room_size, num_rows, random_start, lava_v1, hook;
+    int32_t gp0, gp1;   // generator parameters (mgb_config.gen_param0/1)
     int32_t HP;   // grid column pitch in cells: H rounded up to a multiple of 4 (one column = HP/4 words)
     int32_t GW;   // grid words per env = W*HP/4; cell (x,y) = byte (y&3) of word x*HP/4 + (y>>2)
     int32_t S;    // state words per env
@@ -386,6 +391,140 @@ __device__ __forceinline__ void add_door(uint32_t *st, const DevCfg &c, Rooms &R
     R.doors[room_nb(r, k, c.num_rows)][(k + 2) & 3] = 1;
 }
 
+// ---- procedural generators of the stock env files with the base step: crossing.py, lavagap.py,
+// multiroom.py.  np_random.shuffle / choice are defined on the stream like numpy defines them (DESIGN.md "RNG"): Fisher-Yates
+// from the back with one randint(0, i+1) per position; choice(range(a, b)) = a + randint(0, b - a).
+__device__ __forceinline__ void rand_shuffle(Rng &rg, const RolloutParams &p, uint8_t *x, int n) {
+    for (int i = n - 1; i >= 1; --i) {
+        const int j = rand_int(rg, p, 0, i + 1);
+        const uint8_t t = x[i]; x[i] = x[j]; x[j] = t;
+    }
+}
+__device__ __forceinline__ void sort_small(uint8_t *x, int n) {
+    for (int i = 1; i < n; ++i) { const uint8_t v = x[i]; int j = i; while (j > 0 && x[j - 1] > v) { x[j] = x[j - 1]; --j; } x[j] = v; }
+}
+
+// envs/crossing.py:24-99 (walls and goal come from the template).  A river is direction*64 + position, direction 0 = a column.
+__device__ __forceinline__ void gen_crossing(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p) {
+    const DevCfg &c = p.cfg;
+    const int W = c.W, H = c.H, HP = c.HP, ori = c.gp1 & 3;
+    const uint32_t obstacle = (c.gp1 & 4) ? (uint32_t)CODE_WALL : (uint32_t)code_of(T_LAVA, C_RED, 0);
+    e.ax = 1; e.ay = 1; e.dir = 0;
+    uint8_t rivers[64], rv[32], rh[32], path[64], lim_v[34], lim_h[34];
+    int nr = 0, nv = 0, nh = 0, np = 0;
+    if (ori != 0) for (int i = 2; i < H - 2 && nr < 31; i += 2) rivers[nr++] = (uint8_t)i;            // (v, i), :46-49
+    if (ori != 1) for (int j = 2; j < W - 2 && nr < 62; j += 2) rivers[nr++] = (uint8_t)(64 + j);     // (h, j), :44,50
+    rand_shuffle(rg, p, rivers, nr);                                                                  // :53
+    nr = min(nr, c.gp0);                                                                              // :54
+    for (int k = 0; k < nr; ++k) { if (rivers[k] < 64) rv[nv++] = rivers[k]; else rh[nh++] = rivers[k] - 64; }
+    sort_small(rv, nv); sort_small(rh, nh);                                                           // :55-56
+    for (int k = 0; k < nh; ++k) for (int i = 1; i < W - 1; ++i) cell_wr(st, i * HP + rh[k], obstacle);   // :57-62 (rows first, then
+    for (int k = 0; k < nv; ++k) for (int j = 1; j < H - 1; ++j) cell_wr(st, rv[k] * HP + j, obstacle);   //  columns: same cells, same object)
+    for (int k = 0; k < nv; ++k) path[np++] = 1;                                                      // :65: h = 1, v = 0
+    for (int k = 0; k < nh; ++k) path[np++] = 0;
+    rand_shuffle(rg, p, path, np);                                                                    // :66
+    lim_v[0] = 0; for (int k = 0; k < nv; ++k) lim_v[k + 1] = rv[k]; lim_v[nv + 1] = (uint8_t)(H - 1);   // :69-70
+    lim_h[0] = 0; for (int k = 0; k < nh; ++k) lim_h[k + 1] = rh[k]; lim_h[nh + 1] = (uint8_t)(W - 1);
+    int room_i = 0, room_j = 0;
+    for (int k = 0; k < np; ++k) {                                                                    // :72-85
+        int i, j;
+        if (path[k]) { i = lim_v[room_i + 1]; j = lim_h[room_j] + 1 + rand_int(rg, p, 0, lim_h[room_j + 1] - lim_h[room_j] - 1); ++room_i; }
+        else { i = lim_v[room_i] + 1 + rand_int(rg, p, 0, lim_v[room_i + 1] - lim_v[room_i] - 1); j = lim_h[room_j + 1]; ++room_j; }
+        cell_wr(st, i * HP + j, CODE_EMPTY);
+    }
+}
+
+// envs/lavagap.py:21-60
+__device__ __forceinline__ void gen_lavagap(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p) {
+    const DevCfg &c = p.cfg;
+    const int W = c.W, H = c.H, HP = c.HP;
+    const uint32_t obstacle = c.gp1 ? (uint32_t)CODE_WALL : (uint32_t)code_of(T_LAVA, C_RED, 0);
+    e.ax = 1; e.ay = 1; e.dir = 0;
+    const int gx = c.gp0 ? W / 2 : rand_int(rg, p, 2, W - 2);                                         // :40-49
+    const int gy = rand_int(rg, p, 1, H - 1);
+    for (int j = 1; j <= H - 2; ++j) cell_wr(st, gx * HP + j, obstacle);                              // :52
+    cell_wr(st, gx * HP + gy, CODE_EMPTY);                                                            // :55
+}
+
+// envs/multiroom.py:41-241.  _placeRoom recurses, but never backtracks: a call either fails before appending its room, or
+// appends it and tries up to 8 times to place the next one -- the first success ends every loop above it.  So a chain of
+// rooms grows one room at a time; it is grown here in a loop.
+struct MRoom { int8_t topX, topY, sizeX, sizeY, entryX, entryY, entryWall; };
+__device__ __forceinline__ bool mr_try_room(Rng &rg, const RolloutParams &p, MRoom *list, int &n, int maxSz, int wall, int ex, int ey) {   // :123-186
+    const DevCfg &c = p.cfg;
+    const int sizeX = rand_int(rg, p, 4, maxSz + 1), sizeY = rand_int(rg, p, 4, maxSz + 1);
+    int topX, topY;
+    if (n == 0) { topX = ex; topY = ey; }
+    else if (wall == 0) { topX = ex - sizeX + 1; topY = rand_int(rg, p, ey - sizeY + 2, ey); }
+    else if (wall == 1) { topX = rand_int(rg, p, ex - sizeX + 2, ex); topY = ey - sizeY + 1; }
+    else if (wall == 2) { topX = ex; topY = rand_int(rg, p, ey - sizeY + 2, ey); }
+    else { topX = rand_int(rg, p, ex - sizeX + 2, ex); topY = ey; }
+    if (topX < 0 || topY < 0) return false;                                                           // :164-167
+    if (topX + sizeX > c.W || topY + sizeY >= c.H) return false;
+    for (int k = 0; k + 1 < n; ++k) {                                                                 // :170-178: roomList[:-1]
+        const MRoom &r = list[k];
+        const bool nonOverlap = topX + sizeX < r.topX || r.topX + r.sizeX <= topX || topY + sizeY < r.topY || r.topY + r.sizeY <= topY;
+        if (!nonOverlap) return false;
+    }
+    MRoom &m = list[n++];
+    m.topX = (int8_t)topX; m.topY = (int8_t)topY; m.sizeX = (int8_t)sizeX; m.sizeY = (int8_t)sizeY;
+    m.entryX = (int8_t)ex; m.entryY = (int8_t)ey; m.entryWall = (int8_t)wall;
+    return true;
+}
+__device__ __forceinline__ bool gen_multiroom(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p) {
+    const DevCfg &c = p.cfg;
+    const int W = c.W, HP = c.HP, maxSz = c.gp1;
+    MRoom best[8], cur[8];
+    int nbest = 0;
+    const int numRooms = min(rand_int(rg, p, c.gp0, c.gp0 + 1), 8);                                   // :44
+    for (int guard = 0; nbest < numRooms; ++guard) {                                                  // :46-64
+        if (guard > 100000 || (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE))) return false;
+        int ncur = 0;
+        const int ex0 = rand_int(rg, p, 0, W - 2), ey0 = rand_int(rg, p, 0, W - 2);
+        bool grow = mr_try_room(rg, p, cur, ncur, maxSz, 2, ex0, ey0);
+        while (grow && ncur < numRooms) {                                                             // a placed room with numLeft > 1: :193-239
+            const MRoom r = cur[ncur - 1];
+            grow = false;
+            for (int i = 0; i < 8 && !grow; ++i) {
+                const int pick = rand_int(rg, p, 0, 3);                                               // _rand_elem(sorted(wallSet - {entryDoorWall}))
+                const int exitWall = pick + (pick >= r.entryWall ? 1 : 0);
+                const int nextEntryWall = (exitWall + 2) & 3;
+                int dx, dy;
+                if (exitWall == 0) { dx = r.topX + r.sizeX - 1; dy = r.topY + rand_int(rg, p, 1, r.sizeY - 1); }
+                else if (exitWall == 1) { dx = r.topX + rand_int(rg, p, 1, r.sizeX - 1); dy = r.topY + r.sizeY - 1; }
+                else if (exitWall == 2) { dx = r.topX; dy = r.topY + rand_int(rg, p, 1, r.sizeY - 1); }
+                else { dx = r.topX + rand_int(rg, p, 1, r.sizeX - 1); dy = r.topY; }
+                if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) return false;
+                grow = mr_try_room(rg, p, cur, ncur, maxSz, nextEntryWall, dx, dy);
+            }
+        }
+        if (ncur > nbest) { for (int k = 0; k < ncur; ++k) best[k] = cur[k]; nbest = ncur; }
+    }
+    int prev = -1;                                                                                    // prevDoorColor, :77-108
+    for (int idx = 0; idx < nbest; ++idx) {
+        const MRoom r = best[idx];
+        for (int i = 0; i < r.sizeX; ++i) { cell_wr(st, (r.topX + i) * HP + r.topY, CODE_WALL); cell_wr(st, (r.topX + i) * HP + r.topY + r.sizeY - 1, CODE_WALL); }
+        for (int j = 0; j < r.sizeY; ++j) { cell_wr(st, r.topX * HP + r.topY + j, CODE_WALL); cell_wr(st, (r.topX + r.sizeX - 1) * HP + r.topY + j, CODE_WALL); }
+        if (idx > 0) {
+            // sorted(doorColors): COLOR_NAMES (sorted) without the previous door's colour
+            const int k = rand_int(rg, p, 0, prev < 0 ? 7 : 6);
+            int color = -1;
+            for (int q = 0, seen = 0; q < 7; ++q) {
+                const int cq = (int)((0x4603512u >> (4 * q)) & 0xF);                                  // COLOR_NAMES order -> colour index
+                if (cq == prev) continue;
+                if (seen++ == k) { color = cq; break; }
+            }
+            cell_wr(st, r.entryX * HP + r.entryY, (uint32_t)code_of(T_DOOR, color, 1));               // Door(color): closed, unlocked
+            prev = color;
+        }
+    }
+    const MRoom f = best[0], l = best[nbest - 1];
+    bool ok = place_agent(st, e, rg, p, f.topX, f.topY, f.sizeX, f.sizeY, -1);                        // :111
+    int x, y;
+    ok = ok && place_obj(st, e, rg, p, CODE_GOAL, l.topX, l.topY, l.sizeX, l.sizeY, false, -1, true, x, y);   // :114
+    return ok;
+}
+
 template <int GEN>
 __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, PoolCtx *pc) {
     const DevCfg &c = p.cfg;
@@ -453,6 +592,10 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
             ok = ok && placed;
         }
         e.flags |= FLAG_PRISTINE;
+    } else if (GEN == GEN_PROC) {                        // crossing.py / lavagap.py / multiroom.py
+        if (c.gen == GEN_CROSSING) gen_crossing(st, e, rg, p);
+        else if (c.gen == GEN_LAVAGAP) gen_lavagap(st, e, rg, p);
+        else ok = gen_multiroom(st, e, rg, p);
     } else if (GEN == GEN_KEYCORRIDOR) {                 // roomgrid.py:118-169 + envs/keycorridor.py:26-49
         Rooms R;
         const int rs = c.room_size, rows = c.num_rows;

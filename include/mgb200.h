@@ -38,9 +38,14 @@ enum {
     MGB_GEN_FOURROOMS = 2,    /* envs/fourrooms.py:19-69 */
     MGB_GEN_DYNOBS = 3,       /* envs/dynamicobstacles.py:35-89 */
     MGB_GEN_KEYCORRIDOR = 4,  /* roomgrid.py:118-359 + envs/keycorridor.py:26-59 */
-    MGB_GEN_POOL = 5          /* no on-device generator: reset draws one of the uploaded levels (mgb_set_level_pool).
-                                 For envs whose step() is the base MiniGridEnv.step: envs/{crossing,lavagap,multiroom,
-                                 distshift,simpleroom}.py -- SURVEY §8(f) rank 2 */
+    MGB_GEN_POOL = 5,         /* no on-device generator: reset draws one of the uploaded levels (mgb_set_level_pool).
+                                 For envs whose step() is the base MiniGridEnv.step or one of the MGB_HOOK_* rules
+                                 -- SURVEY §8(f) rank 2 */
+    MGB_GEN_CROSSING = 6,     /* envs/crossing.py:24-99: gen_param0 = num_crossings, gen_param1 = ori (0 h, 1 v, 2 both) | 4 if the
+                                 obstacles are walls (SimpleCrossing) instead of lava */
+    MGB_GEN_LAVAGAP = 7,      /* envs/lavagap.py:21-60: gen_param0 = const (gap column fixed at width/2), gen_param1 = 1 if walls */
+    MGB_GEN_MULTIROOM = 8     /* envs/multiroom.py:41-241: gen_param0 = number of rooms (min == max in every registered id),
+                                 gen_param1 = maxRoomSize */
 };
 
 /* static per-env-id configuration: what the reference bakes into constructor kwargs
@@ -59,6 +64,8 @@ typedef struct {
     int32_t agent_view_size;/* minigrid.py:776,795 / ViewSizeWrapper (wrappers.py:579-608): 0 or 7 = default; 3, 5, 9, 11
                                also built.  Every obs buffer is [..][V][V][3], i.e. 3*V*V bytes per env-step */
     int32_t hook;           /* MGB_HOOK_*: subclass step() post-hook for MGB_GEN_POOL handles (0 = base step only) */
+    int32_t gen_param0;     /* generator parameters of MGB_GEN_CROSSING / LAVAGAP / MULTIROOM (see the enum), else 0 */
+    int32_t gen_param1;
 } mgb_config;
 
 /* step() post-hooks of the stock env files that only add a success/failure rule on top of MiniGridEnv.step.

@@ -38,7 +38,21 @@ SNAP_EVERY = 50
 
 HOOK_OF_CLASS = {"UnlockPickup": 1, "BlockedUnlockPickup": 1, "ObstructedMazeEnv": 1, "Unlock": 2, "FetchEnv": 3, "GoToDoorEnv": 4, "GoToObjectEnv": 5,
                  "PutNearEnv": 6, "RedBlueDoorEnv": 7, "MemoryEnv": 8}
-GEN_OF_CLASS = {"EmptyEnv": 0, "DoorKeyEnv": 1, "FourRoomsEnv": 2, "DynamicObstaclesEnv": 3, "KeyCorridor": 4}
+GEN_OF_CLASS = {"EmptyEnv": 0, "DoorKeyEnv": 1, "FourRoomsEnv": 2, "DynamicObstaclesEnv": 3, "KeyCorridor": 4,
+                "CrossingEnv": 6, "LavaGapEnv": 7, "MultiRoomEnv": 8}
+
+
+def gen_params_of(env, gen):
+    """generator parameters (include/mgb200.h gen_param0/1) read off the live reference env"""
+    mg = sys.modules["gym_minigrid.minigrid"]
+    if gen == 6:      # crossing.py:11-22
+        return int(env.num_crossings), int(env.ori) | (4 if env.obstacle_type is mg.Wall else 0)
+    if gen == 7:      # lavagap.py:10-19
+        return int(bool(env.const)), int(env.obstacle_type is mg.Wall)
+    if gen == 8:      # multiroom.py:21-39
+        assert env.minNumRooms == env.maxNumRooms
+        return int(env.minNumRooms), int(env.maxRoomSize)
+    return 0, 0
 
 
 def config_of(env):
@@ -60,7 +74,9 @@ def config_of(env):
             any(n in ("LockedRoom", "PlaygroundV0") for n in names), \
             "%s overrides step() with an unknown hook: not a level-pool env" % type(env).__name__
         gen = 5
+    gp0, gp1 = gen_params_of(env, gen)
     return dict(hook=HOOK_OF_CLASS.get(next((k.__name__ for k in type(env).__mro__ if k.__name__ in HOOK_OF_CLASS), ""), 0),
+        gen_param0=gp0, gen_param1=gp1,
         **dict(
         gen=gen, width=env.width, height=env.height, max_steps=env.max_steps,
         see_through=int(bool(env.see_through_walls)), n_actions=env.action_space.n,
@@ -258,7 +274,14 @@ VARIANTS = [
     "MiniGrid-Dynamic-Obstacles-8x8-v0",
     "MiniGrid-KeyCorridorS3R1-v0", "MiniGrid-KeyCorridorS3R2-v0", "MiniGrid-KeyCorridorS3R3-v0",
     "MiniGrid-KeyCorridorS4R3-v0", "MiniGrid-KeyCorridorS5R3-v0",
+    # on-device generators of round 2 (crossing.py, lavagap.py, multiroom.py): np_random.shuffle / choice / randint injected
+    "MiniGrid-LavaCrossingS9N1-v0", "MiniGrid-LavaCrossingS9N0-v0", "MiniGrid-LavaCrossingS9N3-v0", "MiniGrid-LavaCrossingS11N5-v0",
+    "MiniGrid-SimpleCrossingS9N2-v0", "MiniGrid-SimpleCrossingS11N5-v0",
+    "MiniGrid-LavaGapS5-v0", "MiniGrid-LavaGapS7-v0", "MiniGrid-NormalGapS6-v0", "MiniGrid-LavaGapS6-v1",
+    "MiniGrid-MultiRoom-N2-S4-v0", "MiniGrid-MultiRoom-N4-S5-v0", "MiniGrid-MultiRoom-N6-v0",
 ]
+# RNG-tape traces (the reference's own MT19937 draws through TapeRecorder.randint / shuffle / choice) for the same files
+TAPE_VARIANTS = ["MiniGrid-LavaCrossingS9N2-v0", "MiniGrid-SimpleCrossingS9N3-v0", "MiniGrid-LavaGapS6-v0", "MiniGrid-MultiRoom-N6-v0"]
 
 
 def short(env_id):
@@ -287,6 +310,13 @@ def main():
         acts = [2000, 2001, 2002]
         traces = [run_trace(env_id, seed + 1, i, 300, a, "philox") for i, a in zip(idx, acts)]
         p = save_traces("philox_%s" % short(env_id), env_id, traces, seed + 1, idx, acts)
+        print("%-60s %7.1f KB  episodes=%s  [%.0fs]" % (os.path.basename(p), os.path.getsize(p) / 1024,
+              [t["n_episodes"] for t in traces], time.time() - t0), flush=True)
+    for env_id in TAPE_VARIANTS:
+        idx = [9, 31, 640]
+        acts = [2100, 2101, 2102]
+        traces = [run_trace(env_id, seed + 2, i, 300, a, "tape") for i, a in zip(idx, acts)]
+        p = save_traces("tape_%s" % short(env_id), env_id, traces, seed + 2, idx, acts)
         print("%-60s %7.1f KB  episodes=%s  [%.0fs]" % (os.path.basename(p), os.path.getsize(p) / 1024,
               [t["n_episodes"] for t in traces], time.time() - t0), flush=True)
     # scenes: see-through (Empty classes) and occluded (DoorKey classes, FourRooms 19x19)
@@ -357,7 +387,7 @@ def pool_traces():
                              ("MiniGrid-DistShift2-v0", 500, 2), ("MiniGrid-SimpleRoom-v0", 300, 2),
                              ("MiniGrid-Empty-6x6-v2", 400, 2), ("MiniGrid-Empty-Random-10x10-v0", 450, 2)):
         env = R.make(env_id)
-        cfg = config_of(env)
+        cfg = dict(config_of(env), gen=5, gen_param0=0, gen_param1=0)      # played from an uploaded pool, whatever generator the id has
         levels = []
         for k in range(K):
             env.seed(100 + k)

@@ -487,6 +487,143 @@ static void gen_keycorridor(Env *e) {
     e->target_type = T_BALL; e->target_color = (uint8_t)obj_color;
 }
 
+/* ---- the RandomState methods crossing.py calls besides randint, as oracle/ref_shim.py defines them on the stream:
+ * shuffle = Fisher-Yates from the back, one randint(0, i+1) per position; choice(range(a, b)) = a + randint(0, b-a) ---- */
+static void rand_shuffle(Env *e, int *x, int n) {
+    for (int i = n - 1; i >= 1; i--) {
+        int j = rand_int(e, 0, i + 1);
+        int t = x[i]; x[i] = x[j]; x[j] = t;
+    }
+}
+static int rand_choice_range(Env *e, int lo, int hi) { return lo + rand_int(e, 0, hi - lo); }
+static void sort_ints(int *x, int n) {
+    for (int i = 1; i < n; i++) { int v = x[i], j = i; while (j > 0 && x[j - 1] > v) { x[j] = x[j - 1]; j--; } x[j] = v; }
+}
+
+/* envs/crossing.py:24-99.  A river is (direction, position): direction v (vertical, a column) = 0, h (a row) = 1. */
+static void gen_crossing(Env *e) {
+    Grid *g = &e->grid; int W = g->w, H = g->h;
+    const int num_crossings = e->cfg.gen_param0, ori = e->cfg.gen_param1 & 3;
+    const Obj obstacle = (e->cfg.gen_param1 & 4) ? mk_wall() : mk(T_LAVA, C_RED);
+    wall_rect(g, 0, 0, W, H);                                    /* :31 */
+    e->ax = 1; e->ay = 1; e->adir = 0; e->has_agent = 1;         /* :34-35 */
+    grid_set(g, W - 2, H - 2, mk_goal(1));                       /* :38 */
+    int rivers[64], nr = 0;                                      /* :44-52, encoded dir*64 + pos */
+    if (ori == 0) { for (int j = 2; j < W - 2; j += 2) rivers[nr++] = 64 + j; }
+    else if (ori == 1) { for (int i = 2; i < H - 2; i += 2) rivers[nr++] = i; }
+    else { for (int i = 2; i < H - 2; i += 2) rivers[nr++] = i; for (int j = 2; j < W - 2; j += 2) rivers[nr++] = 64 + j; }
+    rand_shuffle(e, rivers, nr);                                 /* :53 */
+    if (nr > num_crossings) nr = num_crossings;                  /* :54 */
+    int rv[32], rh[32], nv = 0, nh = 0;
+    for (int k = 0; k < nr; k++) { if (rivers[k] < 64) rv[nv++] = rivers[k]; else rh[nh++] = rivers[k] - 64; }
+    sort_ints(rv, nv); sort_ints(rh, nh);                        /* :55-56 */
+    for (int i = 1; i < W - 1; i++) for (int k = 0; k < nh; k++) grid_set(g, i, rh[k], obstacle);   /* :57-62: product(range(1, width-1), rivers_h) */
+    for (int k = 0; k < nv; k++) for (int j = 1; j < H - 1; j++) grid_set(g, rv[k], j, obstacle);   /*          product(rivers_v, range(1, height-1)) */
+    int path[64], np = 0;                                        /* :65: [h] * len(rivers_v) + [v] * len(rivers_h) */
+    for (int k = 0; k < nv; k++) path[np++] = 1;
+    for (int k = 0; k < nh; k++) path[np++] = 0;
+    rand_shuffle(e, path, np);                                   /* :66 */
+    int limits_v[34], limits_h[34];                              /* :69-70 */
+    limits_v[0] = 0; for (int k = 0; k < nv; k++) limits_v[k + 1] = rv[k]; limits_v[nv + 1] = H - 1;
+    limits_h[0] = 0; for (int k = 0; k < nh; k++) limits_h[k + 1] = rh[k]; limits_h[nh + 1] = W - 1;
+    int room_i = 0, room_j = 0;
+    for (int k = 0; k < np; k++) {                               /* :72-85 */
+        int i, j;
+        if (path[k] == 1) {                                      /* direction is h */
+            i = limits_v[room_i + 1];
+            j = rand_choice_range(e, limits_h[room_j] + 1, limits_h[room_j + 1]);
+            room_i++;
+        } else {
+            i = rand_choice_range(e, limits_v[room_i] + 1, limits_v[room_i + 1]);
+            j = limits_h[room_j + 1];
+            room_j++;
+        }
+        grid_set(g, i, j, NONE);
+    }
+}
+
+/* envs/lavagap.py:21-60 */
+static void gen_lavagap(Env *e) {
+    Grid *g = &e->grid; int W = g->w, H = g->h;
+    const Obj obstacle = e->cfg.gen_param1 ? mk_wall() : mk(T_LAVA, C_RED);
+    wall_rect(g, 0, 0, W, H);
+    e->ax = 1; e->ay = 1; e->adir = 0; e->has_agent = 1;
+    grid_set(g, W - 2, H - 2, mk_goal(1));
+    int gx, gy;
+    if (!e->cfg.gen_param0) { gx = rand_int(e, 2, W - 2); gy = rand_int(e, 1, H - 1); }     /* :40-44 */
+    else { gx = W / 2; gy = rand_int(e, 1, H - 1); }                                         /* :45-49 */
+    for (int j = 0; j < H - 2; j++) grid_set(g, gx, 1 + j, obstacle);                        /* :52 vert_wall(x, 1, height-2, obstacle_type) */
+    grid_set(g, gx, gy, NONE);                                                               /* :55 */
+}
+
+/* envs/multiroom.py:41-241 */
+typedef struct { int topX, topY, sizeX, sizeY, entryX, entryY; } MRoom;
+static int mr_place_room(Env *e, int numLeft, MRoom *list, int *n, int minSz, int maxSz, int entryDoorWall, int ex, int ey) {  /* :123-241 */
+    Grid *g = &e->grid;
+    int sizeX = rand_int(e, minSz, maxSz + 1);
+    int sizeY = rand_int(e, minSz, maxSz + 1);
+    int topX, topY;
+    if (*n == 0) { topX = ex; topY = ey; }
+    else if (entryDoorWall == 0) { topX = ex - sizeX + 1; topY = rand_int(e, ey - sizeY + 2, ey); }
+    else if (entryDoorWall == 1) { topX = rand_int(e, ex - sizeX + 2, ex); topY = ey - sizeY + 1; }
+    else if (entryDoorWall == 2) { topX = ex; topY = rand_int(e, ey - sizeY + 2, ey); }
+    else { topX = rand_int(e, ex - sizeX + 2, ex); topY = ey; }
+    if (e->err & 6) return 0;
+    if (topX < 0 || topY < 0) return 0;                                            /* :164-167 */
+    if (topX + sizeX > g->w || topY + sizeY >= g->h) return 0;
+    for (int k = 0; k + 1 < *n; k++) {                                             /* :170-178: roomList[:-1] */
+        const MRoom *r = &list[k];
+        int nonOverlap = topX + sizeX < r->topX || r->topX + r->sizeX <= topX || topY + sizeY < r->topY || r->topY + r->sizeY <= topY;
+        if (!nonOverlap) return 0;
+    }
+    MRoom m = { topX, topY, sizeX, sizeY, ex, ey };
+    list[(*n)++] = m;                                                              /* :181-186 */
+    if (numLeft == 1) return 1;                                                    /* :189-190 */
+    for (int i = 0; i < 8; i++) {                                                  /* :193-239 */
+        int walls[3], nw = 0;
+        for (int w = 0; w < 4; w++) if (w != entryDoorWall) walls[nw++] = w;       /* sorted(wallSet) */
+        int exitDoorWall = walls[rand_int(e, 0, 3)];
+        int nextEntryWall = (exitDoorWall + 2) % 4;
+        int dx, dy;
+        if (exitDoorWall == 0) { dx = topX + sizeX - 1; dy = topY + rand_int(e, 1, sizeY - 1); }
+        else if (exitDoorWall == 1) { dx = topX + rand_int(e, 1, sizeX - 1); dy = topY + sizeY - 1; }
+        else if (exitDoorWall == 2) { dx = topX; dy = topY + rand_int(e, 1, sizeY - 1); }
+        else { dx = topX + rand_int(e, 1, sizeX - 1); dy = topY; }
+        if (e->err & 6) return 1;
+        if (mr_place_room(e, numLeft - 1, list, n, minSz, maxSz, nextEntryWall, dx, dy)) break;
+    }
+    return 1;
+}
+static void gen_multiroom(Env *e) {
+    Grid *g = &e->grid; int W = g->w;
+    const int numRooms = e->cfg.gen_param0, maxRoomSize = e->cfg.gen_param1;       /* :44: _rand_int(min, max+1) */
+    MRoom best[8], cur[8];
+    int nbest = 0;
+    const int nr = rand_int(e, numRooms, numRooms + 1);
+    for (int guard = 0; nbest < nr; guard++) {                                     /* :46-64 */
+        if (guard > 100000 || (e->err & 6)) { e->err |= 8; return; }
+        int ncur = 0;
+        int ex = rand_int(e, 0, W - 2), ey = rand_int(e, 0, W - 2);
+        mr_place_room(e, nr, cur, &ncur, 4, maxRoomSize, 2, ex, ey);
+        if (ncur > nbest) { memcpy(best, cur, sizeof(MRoom) * (size_t)ncur); nbest = ncur; }
+    }
+    int prev = -1;                                                                 /* prevDoorColor */
+    for (int idx = 0; idx < nbest; idx++) {                                        /* :77-108 */
+        const MRoom *r = &best[idx];
+        for (int i = 0; i < r->sizeX; i++) { grid_set(g, r->topX + i, r->topY, mk_wall()); grid_set(g, r->topX + i, r->topY + r->sizeY - 1, mk_wall()); }
+        for (int j = 0; j < r->sizeY; j++) { grid_set(g, r->topX, r->topY + j, mk_wall()); grid_set(g, r->topX + r->sizeX - 1, r->topY + j, mk_wall()); }
+        if (idx > 0) {
+            int cols[7], nc = 0;                                                   /* sorted(doorColors): COLOR_NAMES order minus the previous one */
+            for (int k = 0; k < 7; k++) if (COLOR_NAMES_IDX[k] != prev) cols[nc++] = COLOR_NAMES_IDX[k];
+            int color = cols[rand_int(e, 0, nc)];
+            grid_set(g, r->entryX, r->entryY, mk_door((uint8_t)color, 0, 0));
+            prev = color;
+        }
+    }
+    if (place_agent(e, 1, best[0].topX, best[0].topY, 1, best[0].sizeX, best[0].sizeY, -1)) e->err |= 8;          /* :111 */
+    if (place_obj(e, mk_goal(1), 1, best[nbest - 1].topX, best[nbest - 1].topY, 1, best[nbest - 1].sizeX, best[nbest - 1].sizeY, 0, -1, NULL, NULL)) e->err |= 8;   /* :114 */
+}
+
 static void gen_pool(Env *e);
 /* reset (minigrid.py:831-858) */
 static void gen_obs(Env *e, uint8_t *obs, uint8_t *dir);
@@ -503,6 +640,9 @@ static void env_reset(Env *e, uint8_t *obs, uint8_t *dir) {
     case ORC_GEN_DYNOBS: gen_dynobs(e); break;
     case ORC_GEN_KEYCORRIDOR: gen_keycorridor(e); break;
     case ORC_GEN_POOL: gen_pool(e); break;
+    case ORC_GEN_CROSSING: gen_crossing(e); break;
+    case ORC_GEN_LAVAGAP: gen_lavagap(e); break;
+    case ORC_GEN_MULTIROOM: gen_multiroom(e); break;
     }
     e->carrying = NONE;
     e->step_count = 0;

@@ -27,7 +27,10 @@ enum {
     ORC_GEN_FOURROOMS = 2,   /* envs/fourrooms.py:19-69      */
     ORC_GEN_DYNOBS = 3,      /* envs/dynamicobstacles.py:35-58 */
     ORC_GEN_KEYCORRIDOR = 4, /* roomgrid.py:118-169 + envs/keycorridor.py:26-49 */
-    ORC_GEN_POOL = 5         /* reset = one of the uploaded reference layouts (base MiniGridEnv.step only) */
+    ORC_GEN_POOL = 5,        /* reset = one of the uploaded reference layouts (base MiniGridEnv.step only) */
+    ORC_GEN_CROSSING = 6,    /* envs/crossing.py:24-99; gen_param0 = num_crossings, gen_param1 = ori | 4 * (obstacle_type == Wall) */
+    ORC_GEN_LAVAGAP = 7,     /* envs/lavagap.py:21-60; gen_param0 = const, gen_param1 = (obstacle_type == Wall) */
+    ORC_GEN_MULTIROOM = 8    /* envs/multiroom.py:41-241; gen_param0 = minNumRooms == maxNumRooms, gen_param1 = maxRoomSize */
 };
 
 typedef struct {
@@ -45,6 +48,7 @@ typedef struct {
     int32_t hook;           /* ORC_GEN_POOL only: 1 pickup target (unlockpickup.py:34-42) 2 unlock (unlock.py:33-41)
                                3 fetch (fetch.py:74-86) 4 gotodoor (gotodoor.py:72-93) 5 gotoobject (gotoobject.py:68-84)
                                6 putnear (putnear.py:91-112) 7 redbluedoors (redbluedoors.py:44-66) 8 memory (memory.py:88-100) */
+    int32_t gen_param0, gen_param1;   /* see ORC_GEN_CROSSING / LAVAGAP / MULTIROOM */
 } orc_config;
 
 #define ORC_OBS_BYTES 147

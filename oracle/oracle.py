@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libminigrid_oracle.so")
 
-GEN_EMPTY, GEN_DOORKEY, GEN_FOURROOMS, GEN_DYNOBS, GEN_KEYCORRIDOR, GEN_POOL = range(6)
+GEN_EMPTY, GEN_DOORKEY, GEN_FOURROOMS, GEN_DYNOBS, GEN_KEYCORRIDOR, GEN_POOL, GEN_CROSSING, GEN_LAVAGAP, GEN_MULTIROOM = range(9)
 OBS_BYTES = 147
 MAX_OBST = 8
 
@@ -20,7 +20,7 @@ MAX_OBST = 8
 class OrcConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "gen", "width", "height", "max_steps", "see_through", "n_actions",
-        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1", "view_size", "hook")]
+        "n_obstacles", "room_size", "num_rows", "random_start", "lava_v1", "view_size", "hook", "gen_param0", "gen_param1")]
 
 
 def build(force=False):

@@ -291,9 +291,30 @@ class PhiloxShim:
         assert span > 0
         return int(low) + ((self._u32() * span) >> 32)
 
+    # The two other RandomState methods the stock env files call (crossing.py:53,66,75-80), expressed through randint so
+    # that the device generators can mirror them draw for draw: numpy's own algorithms (Fisher-Yates from the back;
+    # one bounded integer for a 1-D choice) on this object's stream.
+    def shuffle(self, x):
+        _shuffle(self, x)
+
+    def choice(self, a):
+        return _choice(self, a)
+
+
+def _shuffle(rng, x):
+    for i in reversed(range(1, len(x))):
+        j = rng.randint(0, i + 1)
+        x[i], x[j] = x[j], x[i]
+
+
+def _choice(rng, a):
+    a = list(range(a)) if isinstance(a, (int, np.integer)) else list(a)
+    return a[rng.randint(0, len(a))]
+
 
 class TapeRecorder:
-    """Wraps the reference's own RandomState; records every ``randint`` result."""
+    """Wraps the reference's own RandomState; records every ``randint`` result.  shuffle / choice run the same
+    algorithms as PhiloxShim on the recorded draws."""
 
     def __init__(self, rs):
         self.rs = rs
@@ -303,6 +324,12 @@ class TapeRecorder:
         v = int(self.rs.randint(low, high))
         self.tape.append(v)
         return v
+
+    def shuffle(self, x):
+        _shuffle(self, x)
+
+    def choice(self, a):
+        return _choice(self, a)
 
 
 # --------------------------------------------------------------------------

@@ -23,10 +23,10 @@ def _levels(d):
 def test_cuda_pool_matches_reference(path):
     import gym_minigrid_b200 as mgb
     d = load(path)
-    for key, val in d["cfg"].items():
-        assert int(mgb.spec(d["env_id"])["config"][key]) == val, key
     for k, idx in enumerate(d["env_indices"]):
         env = mgb.make(d["env_id"], num_envs=1, seed=int(d["seed"]), env_id_base=int(idx), levels=_levels(d))
+        for key, val in d["cfg"].items():          # ids with a device generator run in pool mode when levels= is given
+            assert int(env._cfg[key]) == val, key
         tag = "%s[%d]" % (os.path.basename(path), k)
         obs = env.reset()
         assert_same(tag + " obs0", _np(obs["image"])[0], d["obs0"][k])
@@ -74,6 +74,6 @@ def test_cuda_pool_matches_oracle_batch(name):
 def test_pool_requires_levels():
     import gym_minigrid_b200 as mgb
     with pytest.raises(ValueError, match="level-pool"):
-        mgb.make("MiniGrid-MultiRoom-N6-v0", num_envs=4)
+        mgb.make("MiniGrid-DistShift1-v0", num_envs=4)
     with pytest.raises(ValueError, match="only for level-pool"):
         mgb.make("MiniGrid-Empty-8x8-v0", num_envs=4, levels=dict(grid=np.zeros((1, 8, 8, 3), np.uint8), agent=np.zeros((1, 3))))

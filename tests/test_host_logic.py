@@ -25,14 +25,21 @@ def header_functions():
 def test_registry_contract():
     for i in HEADLINE:
         assert i in mgb.env_list
-    assert len(mgb.env_list) == len(set(mgb.env_list)) == 81      # 24 with device generators + 57 level-pool ids
+    assert len(mgb.env_list) == len(set(mgb.env_list)) == 81      # 42 with device generators + 39 level-pool-only ids
+    assert sum(1 for i in mgb.env_list if mgb.spec(i)["config"]["gen"] != 5) == 42
     with pytest.raises(AssertionError):            # register.py:12  id must start with "MiniGrid-"
         mgb.register("Foo-v0", "gym_minigrid.envs:EmptyEnv")
     with pytest.raises(AssertionError):            # register.py:13  ids are unique
         mgb.register("MiniGrid-Empty-8x8-v0", "gym_minigrid.envs:EmptyEnv")
     with pytest.raises(KeyError):
         mgb.spec("MiniGrid-MinimapForSparky-v0")    # out of scope (SAR env): loud, not silent
-    assert mgb.spec("MiniGrid-MultiRoom-N6-v0")["config"]["gen"] == 5     # level-pool id
+    assert mgb.spec("MiniGrid-DistShift1-v0")["config"]["gen"] == 5       # level-pool id
+    c = mgb.spec("MiniGrid-MultiRoom-N6-v0")["config"]                    # multiroom.py:255-262: on-device generator
+    assert (c["gen"], c["gen_param0"], c["gen_param1"], c["width"], c["max_steps"]) == (8, 6, 10, 25, 120)
+    c = mgb.spec("MiniGrid-SimpleCrossingS11N5-v0")["config"]             # crossing.py:135-137
+    assert (c["gen"], c["gen_param0"], c["gen_param1"]) == (6, 5, 2 | 4)
+    c = mgb.spec("MiniGrid-LavaGapS6-v1")["config"]                       # lavagap.py:78-80 ('v1' in the class name)
+    assert (c["gen"], c["gen_param0"], c["gen_param1"], c["lava_v1"]) == (7, 1, 0, 1)
     c = mgb.spec("MiniGrid-Dynamic-Obstacles-16x16-v0")["config"]
     assert (c["n_actions"], c["n_obstacles"], c["reward_range"], c["lava_v1"]) == (3, 8, (-1, 1), 1)
     assert mgb.spec("MiniGrid-KeyCorridorS6R3-v0")["config"]["max_steps"] == 1080
