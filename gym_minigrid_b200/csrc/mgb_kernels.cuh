@@ -738,16 +738,25 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
     const uint32_t ag_sa = st_sa + cell_off(e.ax, e.ay, HP);
     const bool ag_mark = lds_u8(ag_sa) == CODE_EMPTY;
     if (ag_mark) sts_u8(ag_sa, CODE_WALL);
-    uint32_t opos = lds_u16(ob_p);
+    // The next ball's record and address arithmetic are computed one ball ahead (a move only rewrites the mover's own
+    // record), next to this ball's dependent chain instead of behind its stores.
+    struct Ball { int ox, oy, tx, ty; uint32_t sx, sy, colb, old_sa; };
+    auto ball_of = [&](uint32_t opos) {
+        Ball b;
+        b.ox = (int)(opos & 0xFF); b.oy = (int)(opos >> 8);
+        b.tx = max(b.ox - 1, 0); b.ty = max(b.oy - 1, 0);
+        b.sx = (uint32_t)(min(b.tx + 3, W) - b.tx); b.sy = (uint32_t)(min(b.ty + 3, H) - b.ty);
+        b.colb = st_sa + (uint32_t)(b.tx * XP);                   // column tx of the lane's grid
+        b.old_sa = st_sa + cell_off(b.ox, b.oy, HP);
+        return b;
+    };
+    Ball nb = ball_of(lds_u16(ob_p));
     for (int k = 0; k < nob; ++k) {
-        // the next ball's record is fetched now (a move only rewrites the mover's own record): its address arithmetic
-        // overlaps this ball's dependent chain instead of starting after the stores below
+        const Ball b = nb;
         const uint32_t ob_n = ob_p + ((k & 1) ? 126u : 2u);
-        const uint32_t opos_n = lds_u16(ob_n);                    // k = 7: first bytes of the pad row, unused
-        const int ox = (int)(opos & 0xFF), oy = (int)(opos >> 8);
-        const int tx = max(ox - 1, 0), ty = max(oy - 1, 0);
-        const uint32_t sx = (uint32_t)(min(tx + 3, W) - tx), sy = (uint32_t)(min(ty + 3, H) - ty);
-        const uint32_t colb = st_sa + (uint32_t)(tx * XP);        // column tx of the lane's grid
+        nb = ball_of(lds_u16(ob_n));                              // k = nob-1: the row behind the records, unused
+        const uint32_t oldcode = lds_u8(b.old_sa);                // the ball's own code, moved with it
+        uint32_t npos = 0, nsa = 0;
         const uint32_t wi = (nd - wbase) >> 1;                    // window word of draw nd
         const bool spec = wi + DYN_SPEC + par <= WINW;            // all speculative draws are inside the window
         const uint32_t wa = dr_sa + (spec ? wi : 0u) * 128u;
@@ -755,48 +764,45 @@ __device__ __forceinline__ void dynobs_move(uint32_t *st, Env &e, Rng &rg, const
 #pragma unroll
         for (int j = 0; j <= DYN_SPEC; ++j) w[j] = lds_u32(wa + j * 128);     // word DYN_SPEC is only used when par
         int sel = DYN_SPEC;
-        uint32_t npos = 0, nsa = 0;
 #pragma unroll
         for (int j = DYN_SPEC - 1; j >= 0; --j) {                 // descending: the lowest valid try overwrites
             const uint32_t wm = w[j] * DRAW_ODD_MULT;
             const uint32_t ux = par ? wm : w[j], uy = par ? w[j + 1] : wm;
-            const int dx = (int)__umulhi(ux, sx);
-            const int y = ty + (int)__umulhi(uy, sy);
-            const uint32_t sa = colb + (uint32_t)(dx * XP) + (uint32_t)(y + (y >> 2) * 124);
+            const int dx = (int)__umulhi(ux, b.sx);
+            const int y = b.ty + (int)__umulhi(uy, b.sy);
+            const uint32_t sa = b.colb + (uint32_t)(dx * XP) + (uint32_t)(y + (y >> 2) * 124);
             // the ball's own cell counts as occupied: it must move (minigrid.py:1040-1041)
             if (lds_u8(sa) == CODE_EMPTY) { sel = j; npos = (uint32_t)(dx | (y << 8)); nsa = sa; }
         }
-        npos += (uint32_t)tx;
+        npos += (uint32_t)b.tx;
         if (spec) nd += 2u * (uint32_t)min(sel + 1, DYN_SPEC);
         if (!spec || sel == DYN_SPEC) {
-            // ~1 % of the (lane, ball) pairs -- a ball in a corner or along a wall -- but a third of the warp's ball steps:
-            // a tight loop over the rest of the window for the common case (even draw counter), everything else out of line
+            // a tight loop over the rest of the window, one try at a time (a second speculative round measured 4 % slower: it
+            // costs the whole warp a round's instructions for the one or two lanes that need it); the rest out of line
             int tries = spec ? DYN_SPEC : 0;
             nsa = 0;                                              // !spec: the speculative block looked at the wrong words
-            if (!par) {
-                uint32_t wp = dr_sa + ((nd - wbase) >> 1) * 128u;
-                const uint32_t wend = dr_sa + WINW * 128u;
-                while (wp < wend) {                               // tries <= 100 holds: the window has at most 20 words
-                    const uint32_t w0 = lds_u32(wp);
-                    wp += 128u; nd += 2u; ++tries;
-                    const int dx = (int)__umulhi(w0, sx);
-                    const int y = ty + (int)__umulhi(w0 * DRAW_ODD_MULT, sy);
-                    const uint32_t sa = colb + (uint32_t)(dx * XP) + (uint32_t)(y + (y >> 2) * 124);
-                    if (lds_u8(sa) == CODE_EMPTY) { nsa = sa; npos = (uint32_t)((tx + dx) | (y << 8)); break; }
-                }
+            uint32_t wp = dr_sa + ((nd - wbase) >> 1) * 128u;
+            const uint32_t wend = dr_sa + (WINW - par) * 128u;
+            while (wp < wend) {                                   // tries <= 100 holds: the window has at most 20 words
+                const uint32_t w0 = lds_u32(wp), w1 = lds_u32(wp + 128u);
+                wp += 128u; nd += 2u; ++tries;
+                const uint32_t wm = w0 * DRAW_ODD_MULT;
+                const int dx = (int)__umulhi(par ? wm : w0, b.sx);
+                const int y = b.ty + (int)__umulhi(par ? w1 : wm, b.sy);
+                const uint32_t sa = b.colb + (uint32_t)(dx * XP) + (uint32_t)(y + (y >> 2) * 124);
+                if (lds_u8(sa) == CODE_EMPTY) { nsa = sa; npos = (uint32_t)((b.tx + dx) | (y << 8)); break; }
             }
             if (!nsa) {
-                const MoreTries r = dynobs_more_tries(st_sa, dr_sa, wbase, WINW, nd, tries, tx, ty, sx, sy, HP, rg.episode - 1u, rg.gid, p.seed);
+                const MoreTries r = dynobs_more_tries(st_sa, dr_sa, wbase, WINW, nd, tries, b.tx, b.ty, b.sx, b.sy, HP, rg.episode - 1u, rg.gid, p.seed);
                 nsa = r.nsa; npos = r.npos; nd = r.nd;
             }
         }
         if (nsa) {                                                // a failed placement (RecursionError, swallowed) leaves the ball
-            const uint32_t old_sa = st_sa + cell_off(ox, oy, HP);
-            sts_u8(nsa, lds_u8(old_sa));
-            sts_u8(old_sa, CODE_EMPTY);
+            sts_u8(nsa, oldcode);
+            sts_u8(b.old_sa, CODE_EMPTY);
             sts_u16(ob_p, npos);
         }
-        ob_p = ob_n; opos = opos_n;
+        ob_p = ob_n;
     }
     if (ag_mark) sts_u8(ag_sa, CODE_EMPTY);
     rg.ndraws = nd;
@@ -838,7 +844,7 @@ __device__ __noinline__ void dynobs_move_tape(uint32_t *st, Env &e, Rng &rg, con
 // position", and the n_obstacles lowest accepted lanes each write their own ball.  No loop.
 // Returns false (nothing but the removal of the old balls done) if 32 tries were not enough; the caller then runs the
 // scalar generator, which replays the same stream from its start.
-__device__ __forceinline__ bool dynobs_coop_reset(uint32_t *st_warp, int src, int lane, const RolloutParams &p, int64_t gid,
+__device__ __forceinline__ bool dynobs_coop_reset(uint32_t *st_warp, int src, int lane, const RolloutParams &p, const uint32_t *tmpl_s, int64_t gid,
                                                   uint32_t stream, uint32_t &consumed, uint32_t &agent) {
     const DevCfg &c = p.cfg;
     const int HP = c.HP, nob = c.n_obst;
@@ -854,7 +860,8 @@ __device__ __forceinline__ bool dynobs_coop_reset(uint32_t *st_warp, int src, in
                   o0, o1, o2, o3);
     const uint32_t wl = (lane & 2) ? ((lane & 1) ? o3 : o2) : ((lane & 1) ? o1 : o0);      // stream word `lane`
     const uint32_t ux = wl, uy = wl * DRAW_ODD_MULT;                                     // draws 2*lane, 2*lane+1
-    auto static_free = [&](int x, int y) { const int i = x * HP + y; return ((__ldg(&p.tmpl[i >> 2]) >> ((i & 3) * 8)) & 0xFFu) == CODE_EMPTY; };
+    // the static layout is read from the CTA's shared-memory copy of the template (no global-memory latency on this path)
+    auto static_free = [&](int x, int y) { const int i = x * HP + y; return ((tmpl_s[i >> 2] >> ((i & 3) * 8)) & 0xFFu) == CODE_EMPTY; };
     const uint32_t lt = (1u << lane) - 1u;
     int x = (int)__umulhi(ux, (uint32_t)c.W), y = (int)__umulhi(uy, (uint32_t)c.H);
     uint32_t eligible = 0xFFFFFFFFu;                              // lanes whose try is a ball try
@@ -1443,7 +1450,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
                         rm &= rm - 1;
                         uint32_t consumed = 0, agent = 0;
                         const uint32_t stream = __shfl_sync(0xFFFFFFFFu, rg.episode, src);
-                        if (dynobs_coop_reset(st_warp, src, lane, p, p.env_id_base + (int64_t)group * 32 + src, stream, consumed, agent) && lane == src) {
+                        if (dynobs_coop_reset(st_warp, src, lane, p, tmpl_s, p.env_id_base + (int64_t)group * 32 + src, stream, consumed, agent) && lane == src) {
                             e.ax = (int)(agent & 0xFF); e.ay = (int)((agent >> 8) & 0xFF); e.dir = (int)(agent >> 16);
                             e.carry = 0; e.steps = 0; e.target = 0; e.dirty = true;
                             rg.episode++; rg.ndraws = consumed; rg.rblk = 0xFFFFFFFFu;
