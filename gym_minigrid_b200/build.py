@@ -38,12 +38,28 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in DEPS)
 
 
+def source_stamp():
+    """git revision of the sources the library is built from ("+dirty" when csrc/ or include/ differ from it), so that
+    every profile taken with a library can name the exact code (mgb_version() carries it)."""
+    try:
+        sha = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short=12", "HEAD"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                             text=True, timeout=10).stdout.strip()
+        if not sha:
+            return "unknown"
+        dirty = subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "--", "gym_minigrid_b200/csrc", "include"],
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout.strip()
+        return sha + ("+dirty" if dirty else "")
+    except Exception:
+        return "unknown"
+
+
 def build(force=False, verbose=False, defines=(), out=None):
-    """defines/out: build an experimental variant (e.g. defines=["MGB_STITCH_IMAD=1"]) next to the product .so"""
+    """defines/out: build an experimental variant (e.g. defines=["MGB_DYN_BLOCKS=6"]) next to the product .so"""
     if not force and not needs_build() and not defines:
         return SO
     target = out or SO
-    cmd = [find_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-I", os.path.join(ROOT, "include"), "-o", target] + SOURCES
+    stamp = ["-DMGB_BUILD_SHA=\"%s\"" % source_stamp(), "-DMGB_BUILD_DEFINES=\"%s\"" % (" ".join("-D" + d for d in defines) or "none")]
+    cmd = [find_nvcc()] + NVCC_FLAGS + stamp + ["-D" + d for d in defines] + ["-I", os.path.join(ROOT, "include"), "-o", target] + SOURCES
     env = dict(os.environ)
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]

@@ -156,7 +156,14 @@ static std::vector<uint32_t> build_template(const mgb_config &c, int GW, int HP)
 
 extern "C" {
 
-const char *mgb_version(void) { return "mgb200 0.1 (sm_100a)"; }
+#ifndef MGB_BUILD_SHA
+#define MGB_BUILD_SHA "unknown"
+#endif
+#ifndef MGB_BUILD_DEFINES
+#define MGB_BUILD_DEFINES "none"
+#endif
+// carries the source revision and the -D switches of the build: every file under profiles/ quotes it
+const char *mgb_version(void) { return "mgb200 0.2 (sm_100a) src=" MGB_BUILD_SHA " defines=" MGB_BUILD_DEFINES; }
 const char *mgb_last_error(void) { return g_err; }
 
 int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t seed, int64_t env_id_base, mgb_handle **out) {

@@ -41,11 +41,24 @@ def num(s):
 
 def main():
     rep, tag, ksub, n_envs, T = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5])
+    so = sys.argv[sys.argv.index("--lib") + 1] if "--lib" in sys.argv else os.path.join(ROOT, "gym_minigrid_b200", "libmgb200.so")
+    # the library the capture was taken with names its own source revision and -D switches (mgb_version()); capture.sh stores
+    # it next to the report.  A by-line join is only valid against that very library.
+    stamp_file = os.path.splitext(rep)[0] + "_stamp.txt"
+    import ctypes
+    lib = ctypes.CDLL(so)
+    lib.mgb_version.restype = ctypes.c_char_p
+    lib_stamp = lib.mgb_version().decode()
+    cap_stamp = open(stamp_file).read().strip() if os.path.exists(stamp_file) else None
+    if cap_stamp is not None and cap_stamp != lib_stamp:
+        sys.exit("summarize.py: %s was captured with [%s] but %s is [%s]: rebuild that revision (--lib) for a valid join" % (
+            os.path.basename(rep), cap_stamp, so, lib_stamp))
+    stamp = "# library: %s%s" % (lib_stamp, "" if cap_stamp else "  (no capture stamp: join unverified)")
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d, u = dict(zip(hdr, vals)), dict(zip(hdr, units))
-    lines = ["# %s  (kernel %s, %d envs x T=%d, from %s)" % (tag, d.get("Kernel Name", "?"), n_envs, T, os.path.basename(rep))]
+    lines = ["# %s  (kernel %s, %d envs x T=%d, from %s)" % (tag, d.get("Kernel Name", "?"), n_envs, T, os.path.basename(rep)), stamp]
     for k in KEYS:
         if k in d:
             lines.append("%-72s %s %s" % (k, d[k], u[k]))
@@ -65,14 +78,19 @@ def main():
             if v and v > 0.1:
                 lines.append("  %-40s %.3f" % (k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], v))
     open(os.path.join(PROFILES, tag + "_metrics.txt"), "w").write("\n".join(lines) + "\n")
-    so = os.path.join(ROOT, "gym_minigrid_b200", "libmgb200.so")
     bl = subprocess.run([sys.executable, os.path.join(HERE, "sass_by_line.py"), rep, so, ksub, str(wsteps)],
                         stdout=subprocess.PIPE, text=True).stdout
-    open(os.path.join(PROFILES, tag + "_by_line.txt"), "w").write(bl)
+    open(os.path.join(PROFILES, tag + "_by_line.txt"), "w").write(stamp + "\n" + bl)
+    bf = subprocess.run([sys.executable, os.path.join(HERE, "by_function.py"), rep, so, ksub, str(wsteps)],
+                        stdout=subprocess.PIPE, text=True).stdout
+    open(os.path.join(PROFILES, tag + "_by_function.txt"), "w").write(stamp + "\n" + bf)
+    ls = subprocess.run([sys.executable, os.path.join(HERE, "line_stalls.py"), rep, so, ksub, str(wsteps)],
+                        stdout=subprocess.PIPE, text=True).stdout
+    open(os.path.join(PROFILES, tag + "_line_stalls.txt"), "w").write(stamp + "\n" + ls)
     if "--traffic" in sys.argv:
         env_id = sys.argv[sys.argv.index("--traffic") + 1]
         json.dump({"env_id": env_id, "num_envs": n_envs, "rollout_T": T, "dram_bytes_per_launch": rd + wr,
-                   "dram_bytes_read": rd, "dram_bytes_write": wr, "source": os.path.basename(rep)},
+                   "dram_bytes_read": rd, "dram_bytes_write": wr, "source": os.path.basename(rep), "library": lib_stamp},
                   open(os.path.join(PROFILES, "traffic.json"), "w"), indent=1)
     print("\n".join(lines))
 
