@@ -195,20 +195,39 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 constexpr uint32_t DRAW_ODD_MULT = 0x9E3779B1u;
 __device__ __forceinline__ uint32_t draw_word(uint32_t w, uint32_t n) { return (n & 1u) ? w * DRAW_ODD_MULT : w; }
 
+// One Philox block of a stream, out of line and PURE (arguments and result in registers, no memory): the layout
+// generators call it through rand_int_inl below.
+__device__ __noinline__ uint4 philox_block(uint32_t blk, uint32_t stream, uint32_t gid_lo, uint32_t gid_hi, uint32_t seed_lo, uint32_t seed_hi) {
+    uint4 o;
+    philox4x32_10(blk, stream, gid_lo, gid_hi, seed_lo, seed_hi, o.x, o.y, o.z, o.w);
+    return o;
+}
+// the tape entry of RNG-tape mode (parity against the reference's own MT19937 draws), out of line
+__device__ __noinline__ int tape_draw(const RolloutParams &p, int64_t lid, uint32_t &ndraws, uint32_t &err, int low, int high) {
+    const int64_t off = p.tape_off[lid], len = p.tape_off[lid + 1] - off;
+    if ((int64_t)ndraws >= len) { err |= ERR_TAPE_END; return low; }
+    const int v = p.tape[off + ndraws++];
+    if (v < low || v >= high) err |= ERR_TAPE_RANGE;
+    return v;
+}
+
 // MiniGridEnv._rand_int (minigrid.py:939-944): low + mulhi32(u32, high-low) on the stream
 // (seed, global env id, episode); or the next tape entry in RNG-tape mode.
+// The Rng it works on must be a LOCAL of the caller (registers): the generators used to reach their Rng through a
+// reference across an out-of-line rand_int -- half a dozen local-memory accesses per draw, and with ~220 KB of each SM
+// carved out as shared memory there is next to no L1 left, so each was an L2 round trip (KeyCorridor: 11 ms to
+// regenerate 2^20 layouts, 9 launches' worth of stepping).
 __device__ __forceinline__ int rand_int_inl(Rng &e, const RolloutParams &p, int low, int high) {
     if (p.tape) {
-        const int64_t off = p.tape_off[e.lid], len = p.tape_off[e.lid + 1] - off;
-        if ((int64_t)e.ndraws >= len) { e.err |= ERR_TAPE_END; return low; }
-        const int v = p.tape[off + e.ndraws++];
-        if (v < low || v >= high) e.err |= ERR_TAPE_RANGE;
+        uint32_t nd = e.ndraws, er = e.err;
+        const int v = tape_draw(p, e.lid, nd, er, low, high);
+        e.ndraws = nd; e.err = er;
         return v;
     }
     const uint32_t blk = e.ndraws >> 3;
     if (blk != e.rblk) {
-        philox4x32_10(blk, e.episode - 1u, (uint32_t)e.gid, (uint32_t)((uint64_t)e.gid >> 32),
-                      (uint32_t)p.seed, (uint32_t)(p.seed >> 32), e.rb0, e.rb1, e.rb2, e.rb3);
+        const uint4 o = philox_block(blk, e.episode - 1u, (uint32_t)e.gid, (uint32_t)((uint64_t)e.gid >> 32), (uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+        e.rb0 = o.x; e.rb1 = o.y; e.rb2 = o.z; e.rb3 = o.w;
         e.rblk = blk;
     }
     const uint32_t sel = (e.ndraws >> 1) & 3;
@@ -216,10 +235,7 @@ __device__ __forceinline__ int rand_int_inl(Rng &e, const RolloutParams &p, int 
     e.ndraws++;
     return low + (int)__umulhi(u, (uint32_t)(high - low));
 }
-// out-of-line copy for the (cold) layout generators; the per-step obstacle moves inline the body
-__device__ __noinline__ int rand_int(Rng &e, const RolloutParams &p, int low, int high) {
-    return rand_int_inl(e, p, low, high);
-}
+__device__ __forceinline__ int rand_int(Rng &e, const RolloutParams &p, int low, int high) { return rand_int_inl(e, p, low, high); }
 
 // Dynamic-Obstacles consumes 2 draws (one stream word) per ball try, ~11 tries per step.  Instead of computing a Philox
 // block inside the (divergent) try loop, a lane pre-computes DYN_BLOCKS consecutive blocks of its stream in
@@ -373,9 +389,14 @@ __device__ __forceinline__ uint32_t grid_word(const DevCfg &c, const uint32_t *b
 // layout generators (reset): the static part comes from the template, the random part mirrors
 // the reference draw for draw.
 // ------------------------------------------------------------------------------------------
-struct Rooms {                       // RoomGrid bookkeeping (roomgrid.py:14-37), room r = j*3 + i
-    uint8_t dpx[9][4], dpy[9][4], has[9][4], doors[9][4], locked[9];
-};
+// RoomGrid bookkeeping (roomgrid.py:14-37) for the <= 3 x 3 rooms of KeyCorridor, room r = j*3 + i, sides k = right, down,
+// left, up -- all of it in registers (a struct of byte arrays indexed at run time lives in local memory, and with the
+// shared-memory carve-out of these kernels local memory is an L2 round trip per access):
+//   dpr / dpd: 6 bits per room, the random coordinate of the room's right-side / down-side door position (the other
+//              coordinate is the wall's; the left / up positions are the neighbour's right / down ones, roomgrid.py:151-168)
+//   doors:     bit k*16 + r: side k of room r has a door or an opening;  locked: bit r
+// `door_pos[k] is not None` (has) is geometry: right i < 2, down j < rows-1, left i > 0, up j > 0.
+struct Rooms { uint64_t dpr, dpd, doors; uint32_t locked; };
 __device__ __forceinline__ int room_nb(int r, int k, int rows) {   // right, down, left, up
     const int i = r % 3, j = r / 3;
     if (k == 0) return i < 2 ? r + 1 : -1;
@@ -383,12 +404,22 @@ __device__ __forceinline__ int room_nb(int r, int k, int rows) {   // right, dow
     if (k == 2) return i > 0 ? r - 1 : -1;
     return j > 0 ? r - 3 : -1;
 }
+__device__ __forceinline__ bool room_has(int r, int k, int rows) { return room_nb(r, k, rows) >= 0; }
+__device__ __forceinline__ bool room_door(const Rooms &R, int r, int k) { return (R.doors >> (k * 16 + r)) & 1u; }
+__device__ __forceinline__ void room_door_pos(const Rooms &R, int r, int k, int rs, int &x, int &y) {
+    if (k == 2) { r -= 1; k = 0; }
+    if (k == 3) { r -= 3; k = 1; }
+    const int i = r % 3, j = r / 3;
+    if (k == 0) { x = i * (rs - 1) + rs - 1; y = (int)((R.dpr >> (6 * r)) & 63u); }
+    else { x = (int)((R.dpd >> (6 * r)) & 63u); y = j * (rs - 1) + rs - 1; }
+}
 __device__ __forceinline__ void add_door(uint32_t *st, const DevCfg &c, Rooms &R, int r, int k, int color, bool locked) {
     // roomgrid.py:212-246 with door_idx, colour and locked given
-    R.locked[r] = locked;
-    cell_wr(st, R.dpx[r][k] * c.HP + R.dpy[r][k], (uint32_t)code_of(T_DOOR, color, locked ? 2 : 1));
-    R.doors[r][k] = 1;
-    R.doors[room_nb(r, k, c.num_rows)][(k + 2) & 3] = 1;
+    R.locked = (R.locked & ~(1u << r)) | ((uint32_t)locked << r);
+    int x, y;
+    room_door_pos(R, r, k, c.room_size, x, y);
+    cell_wr(st, x * c.HP + y, (uint32_t)code_of(T_DOOR, color, locked ? 2 : 1));
+    R.doors |= (1ull << (k * 16 + r)) | (1ull << (((k + 2) & 3) * 16 + room_nb(r, k, c.num_rows)));
 }
 
 // ---- procedural generators of the stock env files with the base step: crossing.py, lavagap.py,
@@ -449,8 +480,24 @@ __device__ __forceinline__ void gen_lavagap(uint32_t *st, Env &e, Rng &rg, const
 // envs/multiroom.py:41-241.  _placeRoom recurses, but never backtracks: a call either fails before appending its room, or
 // appends it and tries up to 8 times to place the next one -- the first success ends every loop above it.  So a chain of
 // rooms grows one room at a time; it is grown here in a loop.
-struct MRoom { int8_t topX, topY, sizeX, sizeY, entryX, entryY, entryWall; };
-__device__ __forceinline__ bool mr_try_room(Rng &rg, const RolloutParams &p, MRoom *list, int &n, int maxSz, int wall, int ex, int ey) {   // :123-186
+// The two room lists (the chain being grown, the longest so far: 2 x 8 rooms x 8 bytes) live in the lane's column of the
+// warp's staging block -- shared memory, bank == lane -- which is idle between two observations (k_rollout waits for the
+// previous block's bulk store before a reset of this kernel).  Arrays indexed at run time would otherwise sit in local
+// memory, an L2 round trip per access under these kernels' shared-memory carve-out.
+struct MRoom { int topX, topY, sizeX, sizeY, entryX, entryY, entryWall; };
+__device__ __forceinline__ void mr_put(uint32_t *scr, int slot, const MRoom &m) {
+    scr[(2 * slot) * 32] = (uint32_t)(m.topX & 0xFF) | ((uint32_t)(m.topY & 0xFF) << 8) | ((uint32_t)m.sizeX << 16) | ((uint32_t)m.sizeY << 24);
+    scr[(2 * slot + 1) * 32] = (uint32_t)(m.entryX & 0xFF) | ((uint32_t)(m.entryY & 0xFF) << 8) | ((uint32_t)m.entryWall << 16);
+}
+__device__ __forceinline__ MRoom mr_get(const uint32_t *scr, int slot) {
+    const uint32_t a = scr[(2 * slot) * 32], b = scr[(2 * slot + 1) * 32];
+    MRoom m;
+    m.topX = (int)(a & 0xFF); m.topY = (int)((a >> 8) & 0xFF); m.sizeX = (int)((a >> 16) & 0xFF); m.sizeY = (int)(a >> 24);
+    m.entryX = (int)(b & 0xFF); m.entryY = (int)((b >> 8) & 0xFF); m.entryWall = (int)((b >> 16) & 0xFF);
+    return m;
+}
+// one _placeRoom call up to the point where the room is appended (multiroom.py:123-186); list = slots base .. base+n-1
+__device__ __forceinline__ bool mr_try_room(Rng &rg, const RolloutParams &p, uint32_t *scr, int base, int &n, int maxSz, int wall, int ex, int ey) {
     const DevCfg &c = p.cfg;
     const int sizeX = rand_int(rg, p, 4, maxSz + 1), sizeY = rand_int(rg, p, 4, maxSz + 1);
     int topX, topY;
@@ -462,28 +509,31 @@ __device__ __forceinline__ bool mr_try_room(Rng &rg, const RolloutParams &p, MRo
     if (topX < 0 || topY < 0) return false;                                                           // :164-167
     if (topX + sizeX > c.W || topY + sizeY >= c.H) return false;
     for (int k = 0; k + 1 < n; ++k) {                                                                 // :170-178: roomList[:-1]
-        const MRoom &r = list[k];
+        const MRoom r = mr_get(scr, base + k);
         const bool nonOverlap = topX + sizeX < r.topX || r.topX + r.sizeX <= topX || topY + sizeY < r.topY || r.topY + r.sizeY <= topY;
         if (!nonOverlap) return false;
     }
-    MRoom &m = list[n++];
-    m.topX = (int8_t)topX; m.topY = (int8_t)topY; m.sizeX = (int8_t)sizeX; m.sizeY = (int8_t)sizeY;
-    m.entryX = (int8_t)ex; m.entryY = (int8_t)ey; m.entryWall = (int8_t)wall;
+    MRoom m;
+    m.topX = topX; m.topY = topY; m.sizeX = sizeX; m.sizeY = sizeY; m.entryX = ex; m.entryY = ey; m.entryWall = wall;
+    mr_put(scr, base + n, m);
+    ++n;
     return true;
 }
-__device__ __forceinline__ bool gen_multiroom(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p) {
+__device__ __noinline__ bool gen_multiroom(uint32_t *st, Env &e_, Rng &rg_, const RolloutParams &p, uint32_t *scr) {
+    Env e = e_; Rng rg = rg_;                                     // register copies: see rand_int_inl
     const DevCfg &c = p.cfg;
     const int W = c.W, HP = c.HP, maxSz = c.gp1;
-    MRoom best[8], cur[8];
+    constexpr int BEST = 0, CUR = 8;                              // slot ranges of the two lists
     int nbest = 0;
+    bool ok = true;
     const int numRooms = min(rand_int(rg, p, c.gp0, c.gp0 + 1), 8);                                   // :44
     for (int guard = 0; nbest < numRooms; ++guard) {                                                  // :46-64
-        if (guard > 100000 || (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE))) return false;
+        if (guard > 100000 || (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE))) { ok = false; break; }
         int ncur = 0;
         const int ex0 = rand_int(rg, p, 0, W - 2), ey0 = rand_int(rg, p, 0, W - 2);
-        bool grow = mr_try_room(rg, p, cur, ncur, maxSz, 2, ex0, ey0);
+        bool grow = mr_try_room(rg, p, scr, CUR, ncur, maxSz, 2, ex0, ey0);
         while (grow && ncur < numRooms) {                                                             // a placed room with numLeft > 1: :193-239
-            const MRoom r = cur[ncur - 1];
+            const MRoom r = mr_get(scr, CUR + ncur - 1);
             grow = false;
             for (int i = 0; i < 8 && !grow; ++i) {
                 const int pick = rand_int(rg, p, 0, 3);                                               // _rand_elem(sorted(wallSet - {entryDoorWall}))
@@ -494,39 +544,58 @@ __device__ __forceinline__ bool gen_multiroom(uint32_t *st, Env &e, Rng &rg, con
                 else if (exitWall == 1) { dx = r.topX + rand_int(rg, p, 1, r.sizeX - 1); dy = r.topY + r.sizeY - 1; }
                 else if (exitWall == 2) { dx = r.topX; dy = r.topY + rand_int(rg, p, 1, r.sizeY - 1); }
                 else { dx = r.topX + rand_int(rg, p, 1, r.sizeX - 1); dy = r.topY; }
-                if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) return false;
-                grow = mr_try_room(rg, p, cur, ncur, maxSz, nextEntryWall, dx, dy);
+                if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) { ok = false; break; }
+                grow = mr_try_room(rg, p, scr, CUR, ncur, maxSz, nextEntryWall, dx, dy);
             }
+            if (!ok) break;
         }
-        if (ncur > nbest) { for (int k = 0; k < ncur; ++k) best[k] = cur[k]; nbest = ncur; }
-    }
-    int prev = -1;                                                                                    // prevDoorColor, :77-108
-    for (int idx = 0; idx < nbest; ++idx) {
-        const MRoom r = best[idx];
-        for (int i = 0; i < r.sizeX; ++i) { cell_wr(st, (r.topX + i) * HP + r.topY, CODE_WALL); cell_wr(st, (r.topX + i) * HP + r.topY + r.sizeY - 1, CODE_WALL); }
-        for (int j = 0; j < r.sizeY; ++j) { cell_wr(st, r.topX * HP + r.topY + j, CODE_WALL); cell_wr(st, (r.topX + r.sizeX - 1) * HP + r.topY + j, CODE_WALL); }
-        if (idx > 0) {
-            // sorted(doorColors): COLOR_NAMES (sorted) without the previous door's colour
-            const int k = rand_int(rg, p, 0, prev < 0 ? 7 : 6);
-            int color = -1;
-            for (int q = 0, seen = 0; q < 7; ++q) {
-                const int cq = (int)((0x4603512u >> (4 * q)) & 0xF);                                  // COLOR_NAMES order -> colour index
-                if (cq == prev) continue;
-                if (seen++ == k) { color = cq; break; }
-            }
-            cell_wr(st, r.entryX * HP + r.entryY, (uint32_t)code_of(T_DOOR, color, 1));               // Door(color): closed, unlocked
-            prev = color;
+        if (!ok) break;
+        if (ncur > nbest) {
+            for (int k = 0; k < ncur; ++k) { scr[(2 * (BEST + k)) * 32] = scr[(2 * (CUR + k)) * 32]; scr[(2 * (BEST + k) + 1) * 32] = scr[(2 * (CUR + k) + 1) * 32]; }
+            nbest = ncur;
         }
     }
-    const MRoom f = best[0], l = best[nbest - 1];
-    bool ok = place_agent(st, e, rg, p, f.topX, f.topY, f.sizeX, f.sizeY, -1);                        // :111
-    int x, y;
-    ok = ok && place_obj(st, e, rg, p, CODE_GOAL, l.topX, l.topY, l.sizeX, l.sizeY, false, -1, true, x, y);   // :114
+    if (ok) {
+        int prev = -1;                                                                                // prevDoorColor, :77-108
+        for (int idx = 0; idx < nbest; ++idx) {
+            const MRoom r = mr_get(scr, BEST + idx);
+            for (int i = 0; i < r.sizeX; ++i) { cell_wr(st, (r.topX + i) * HP + r.topY, CODE_WALL); cell_wr(st, (r.topX + i) * HP + r.topY + r.sizeY - 1, CODE_WALL); }
+            for (int j = 0; j < r.sizeY; ++j) { cell_wr(st, r.topX * HP + r.topY + j, CODE_WALL); cell_wr(st, (r.topX + r.sizeX - 1) * HP + r.topY + j, CODE_WALL); }
+            if (idx > 0) {
+                // sorted(doorColors): COLOR_NAMES (sorted) without the previous door's colour
+                const int k = rand_int(rg, p, 0, prev < 0 ? 7 : 6);
+                int color = -1;
+                for (int q = 0, seen = 0; q < 7; ++q) {
+                    const int cq = (int)((0x4603512u >> (4 * q)) & 0xF);                              // COLOR_NAMES order -> colour index
+                    if (cq == prev) continue;
+                    if (seen++ == k) { color = cq; break; }
+                }
+                cell_wr(st, r.entryX * HP + r.entryY, (uint32_t)code_of(T_DOOR, color, 1));           // Door(color): closed, unlocked
+                prev = color;
+            }
+        }
+        const MRoom f = mr_get(scr, BEST), l = mr_get(scr, BEST + nbest - 1);
+        ok = place_agent(st, e, rg, p, f.topX, f.topY, f.sizeX, f.sizeY, -1);                         // :111
+        int x, y;
+        ok = ok && place_obj(st, e, rg, p, CODE_GOAL, l.topX, l.topY, l.sizeX, l.sizeY, false, -1, true, x, y);   // :114
+    }
+    e_ = e; rg_ = rg;
     return ok;
 }
 
 template <int GEN>
-__device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, PoolCtx *pc) {
+__device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, PoolCtx *pc, uint32_t *scr);
+// out of line; works on register copies of the caller's Env / Rng (see rand_int_inl)
+template <int GEN>
+__device__ __noinline__ void generate(uint32_t *st, Env &e_, Rng &rg_, const RolloutParams &p, PoolCtx *pc, uint32_t *scr) {
+    Env e = e_;
+    Rng rg = rg_;
+    generate_body<GEN>(st, e, rg, p, pc, scr);
+    e_ = e;
+    rg_ = rg;
+}
+template <int GEN>
+__device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, PoolCtx *pc, uint32_t *scr) {
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP;
     if (GEN == GEN_POOL) {
@@ -595,29 +664,24 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
     } else if (GEN == GEN_PROC) {                        // crossing.py / lavagap.py / multiroom.py
         if (c.gen == GEN_CROSSING) gen_crossing(st, e, rg, p);
         else if (c.gen == GEN_LAVAGAP) gen_lavagap(st, e, rg, p);
-        else ok = gen_multiroom(st, e, rg, p);
+        else ok = gen_multiroom(st, e, rg, p, scr);
     } else if (GEN == GEN_KEYCORRIDOR) {                 // roomgrid.py:118-169 + envs/keycorridor.py:26-49
         Rooms R;
+        R.dpr = R.dpd = R.doors = 0; R.locked = 0;
         const int rs = c.room_size, rows = c.num_rows;
-        for (int r = 0; r < 9; ++r) {
-            R.locked[r] = 0;
-            for (int k = 0; k < 4; ++k) { R.has[r][k] = 0; R.doors[r][k] = 0; R.dpx[r][k] = 0; R.dpy[r][k] = 0; }
-        }
         for (int j = 0; j < rows; ++j)
-            for (int i = 0; i < 3; ++i) {
+            for (int i = 0; i < 3; ++i) {                              // roomgrid.py:139-168: door positions, row-major draw order
                 const int r = j * 3 + i, tx = i * (rs - 1), ty = j * (rs - 1);
                 const int x_l = tx + 1, y_l = ty + 1, x_m = tx + rs - 1, y_m = ty + rs - 1;
-                if (i < 2) { R.dpx[r][0] = x_m; R.dpy[r][0] = rand_int(rg, p, y_l, y_m); R.has[r][0] = 1; }
-                if (j < rows - 1) { R.dpx[r][1] = rand_int(rg, p, x_l, x_m); R.dpy[r][1] = y_m; R.has[r][1] = 1; }
-                if (i > 0) { R.dpx[r][2] = R.dpx[r - 1][0]; R.dpy[r][2] = R.dpy[r - 1][0]; R.has[r][2] = R.has[r - 1][0]; }
-                if (j > 0) { R.dpx[r][3] = R.dpx[r - 3][1]; R.dpy[r][3] = R.dpy[r - 3][1]; R.has[r][3] = R.has[r - 3][1]; }
+                if (i < 2) R.dpr |= (uint64_t)rand_int(rg, p, y_l, y_m) << (6 * r);
+                if (j < rows - 1) R.dpd |= (uint64_t)rand_int(rg, p, x_l, x_m) << (6 * r);
             }
         e.ax = 1 * (rs - 1) + rs / 2; e.ay = (rows / 2) * (rs - 1) + rs / 2; e.dir = 0;
         // remove_wall(1, j, 3) (roomgrid.py:248-282)
         for (int j = 1; j < rows; ++j) {
             const int r = j * 3 + 1, tx = rs - 1, ty = j * (rs - 1);
             for (int m = 1; m < rs - 1; ++m) cell_wr(st, (tx + m) * HP + ty, CODE_EMPTY);
-            R.doors[r][3] = 1; R.doors[r - 3][1] = 1;
+            R.doors |= (1ull << (3 * 16 + r)) | (1ull << (1 * 16 + r - 3));
         }
         const int room_idx = rand_int(rg, p, 0, rows);
         const int door_color = rand_color(rg, p);                     // add_door(2, room_idx, 2, locked=True)
@@ -634,29 +698,28 @@ __device__ __noinline__ void generate(uint32_t *st, Env &e, Rng &rg, const Rollo
             const uint32_t f = cell_rd(st, (e.ax + dx) * HP + (e.ay + dy));
             if (f == CODE_EMPTY || f / 21 == T_WALL) break;
         }
-        // connect_all (roomgrid.py:305-359)
+        // connect_all (roomgrid.py:305-359).  Reachability (:312-327) as a fixpoint on 9-bit room masks: a reached room with
+        // a door on its right / down / left / up side reaches room r+1 / r+3 / r-1 / r-3.
         const int start = (e.ay / (rs - 1)) * 3 + e.ax / (rs - 1);
+        const uint32_t all_rooms = (1u << (rows * 3)) - 1u;
         for (int it = 0; ok; ++it) {
             if (it > 5000) { ok = false; break; }
             uint32_t reach = 1u << start;
-            for (bool grew = true; grew;) {
-                grew = false;
-                for (int r = 0; r < rows * 3; ++r)
-                    if ((reach >> r) & 1)
-                        for (int k = 0; k < 4; ++k)
-                            if (R.doors[r][k]) {
-                                const uint32_t b = 1u << room_nb(r, k, rows);
-                                if (!(reach & b)) { reach |= b; grew = true; }
-                            }
+            for (;;) {
+                const uint32_t d0 = (uint32_t)R.doors & 0x1FFu, d1 = (uint32_t)(R.doors >> 16) & 0x1FFu;
+                const uint32_t d2 = (uint32_t)(R.doors >> 32) & 0x1FFu, d3 = (uint32_t)(R.doors >> 48) & 0x1FFu;
+                const uint32_t nr = (reach | ((reach & d0) << 1) | ((reach & d1) << 3) | ((reach & d2) >> 1) | ((reach & d3) >> 3)) & all_rooms;
+                if (nr == reach) break;
+                reach = nr;
             }
-            if (__popc(reach) == rows * 3) break;
+            if (reach == all_rooms) break;
             const int i = rand_int(rg, p, 0, 3);
             const int j = rand_int(rg, p, 0, rows);
             const int k = rand_int(rg, p, 0, 4);
             if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) { ok = false; break; }
             const int r = j * 3 + i;
-            if (!R.has[r][k] || R.doors[r][k]) continue;
-            if (R.locked[r] || R.locked[room_nb(r, k, rows)]) continue;
+            if (!room_has(r, k, rows) || room_door(R, r, k)) continue;
+            if (((R.locked >> r) & 1u) || ((R.locked >> room_nb(r, k, rows)) & 1u)) continue;
             const int color = rand_color(rg, p);
             add_door(st, c, R, r, k, color, false);
         }
@@ -1396,7 +1459,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
 
         if (p.do_reset) {
             const bool m = valid && (!p.reset_mask || p.reset_mask[lid]);
-            if (m) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }   // copy-in/out keeps e, rg in registers
+            if (GEN == GEN_PROC && c.gen == GEN_MULTIROOM && __any_sync(0xFFFFFFFFu, m)) {   // the MultiRoom generator scribbles in the staging block
+                if (lane == 0) bulk_store_wait_read();
+                __syncwarp();
+            }
+            if (m) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, stage_w + lane); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }   // copy-in/out keeps e, rg in registers
         }
         const int nsteps = p.T > 0 ? p.T : 1;
         int a_next = 0;
@@ -1458,7 +1525,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
                         }
                     }
                 }
-                if (need_reset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
+                if (GEN == GEN_PROC && c.gen == GEN_MULTIROOM && __any_sync(0xFFFFFFFFu, need_reset)) {   // the MultiRoom generator scribbles in the staging block
+                    if (lane == 0) bulk_store_wait_read();
+                    __syncwarp();
+                }
+                if (need_reset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, stage_w + lane); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
             }
             if (gobs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory

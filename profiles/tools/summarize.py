@@ -42,6 +42,9 @@ def num(s):
 def main():
     rep, tag, ksub, n_envs, T = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4]), int(sys.argv[5])
     so = sys.argv[sys.argv.index("--lib") + 1] if "--lib" in sys.argv else os.path.join(ROOT, "gym_minigrid_b200", "libmgb200.so")
+    global PROFILES
+    if "--out" in sys.argv:                      # e.g. gpurun_out/ when run on the GPU box (reports are too large to bring back)
+        PROFILES = sys.argv[sys.argv.index("--out") + 1]
     # the library the capture was taken with names its own source revision and -D switches (mgb_version()); capture.sh stores
     # it next to the report.  A by-line join is only valid against that very library.
     stamp_file = os.path.splitext(rep)[0] + "_stamp.txt"
