@@ -236,6 +236,10 @@ __device__ __forceinline__ int rand_int_inl(Rng &e, const RolloutParams &p, int 
     return low + (int)__umulhi(u, (uint32_t)(high - low));
 }
 __device__ __forceinline__ int rand_int(Rng &e, const RolloutParams &p, int low, int high) { return rand_int_inl(e, p, low, high); }
+// out-of-line copy working through the reference: only for the Empty kernels' random-start generator, whose (headline)
+// hot loop is sensitive to how much code and register pressure the cold reset path carries (measured: -1.1 % with the
+// inline form there); its three draws per reset do not matter
+__device__ __noinline__ int rand_int_ool(Rng &e, const RolloutParams &p, int low, int high) { return rand_int_inl(e, p, low, high); }
 
 // Dynamic-Obstacles consumes 2 draws (one stream word) per ball try, ~11 tries per step.  Instead of computing a Philox
 // block inside the (divergent) try loop, a lane pre-computes DYN_BLOCKS consecutive blocks of its stream in
@@ -298,7 +302,7 @@ constexpr int HARD_TRY_CAP = 1 << 16;   // the reference would spin forever; we 
 
 // MiniGridEnv.place_obj (minigrid.py:1003-1061).  max_tries < 0 == math.inf.
 // check_agent: "don't place the object where the agent is" (agent_pos may be None -> false).
-template <bool INL = false>
+template <bool INL = false, bool OOL = false>
 __device__ __forceinline__ bool place_obj(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, int code, int topx, int topy,
                                           int sx, int sy, bool reject_next_to, int max_tries,
                                           bool check_agent, int &ox, int &oy) {
@@ -309,8 +313,8 @@ __device__ __forceinline__ bool place_obj(uint32_t *st, Env &e, Rng &rg, const R
     for (;;) {
         if ((max_tries >= 0 && tries > max_tries) || tries > HARD_TRY_CAP) return false;
         tries++;
-        x = INL ? rand_int_inl(rg, p, topx, hx) : rand_int(rg, p, topx, hx);
-        y = INL ? rand_int_inl(rg, p, topy, hy) : rand_int(rg, p, topy, hy);
+        x = OOL ? rand_int_ool(rg, p, topx, hx) : rand_int(rg, p, topx, hx);
+        y = OOL ? rand_int_ool(rg, p, topy, hy) : rand_int(rg, p, topy, hy);
         if (rg.err & (ERR_TAPE_END | ERR_TAPE_RANGE)) return false;
         if (cell_rd(st, x * HP + y) != CODE_EMPTY) continue;
         if (check_agent && x == e.ax && y == e.ay) continue;
@@ -323,12 +327,13 @@ __device__ __forceinline__ bool place_obj(uint32_t *st, Env &e, Rng &rg, const R
 }
 
 // MiniGridEnv.place_agent (minigrid.py:1072-1090)
+template <bool OOL = false>
 __device__ __forceinline__ bool place_agent(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, int topx, int topy, int sx,
                                             int sy, int max_tries) {
     int x, y;
-    if (!place_obj(st, e, rg, p, CODE_EMPTY, topx, topy, sx, sy, false, max_tries, false, x, y)) return false;
+    if (!place_obj<false, OOL>(st, e, rg, p, CODE_EMPTY, topx, topy, sx, sy, false, max_tries, false, x, y)) return false;
     e.ax = x; e.ay = y;
-    e.dir = rand_int(rg, p, 0, 4);
+    e.dir = OOL ? rand_int_ool(rg, p, 0, 4) : rand_int(rg, p, 0, 4);
     return true;
 }
 
@@ -588,6 +593,7 @@ __device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, con
 // out of line; works on register copies of the caller's Env / Rng (see rand_int_inl)
 template <int GEN>
 __device__ __noinline__ void generate(uint32_t *st, Env &e_, Rng &rg_, const RolloutParams &p, PoolCtx *pc, uint32_t *scr) {
+    if (GEN == GEN_EMPTY) { generate_body<GEN>(st, e_, rg_, p, pc, scr); return; }     // see rand_int_ool
     Env e = e_;
     Rng rg = rg_;
     generate_body<GEN>(st, e, rg, p, pc, scr);
@@ -631,7 +637,7 @@ __device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, con
     int x, y;
     if (GEN == GEN_EMPTY) {                              // envs/empty.py:30-57 (extra == 0)
         if (!c.random_start) { e.ax = 1; e.ay = 1; e.dir = 0; }
-        else ok = place_agent(st, e, rg, p, 0, 0, W, H, -1);
+        else ok = place_agent<true>(st, e, rg, p, 0, 0, W, H, -1);
         e.flags |= FLAG_PRISTINE;
     } else if (GEN == GEN_DOORKEY) {                     // envs/doorkey.py:15-44
         const int split = rand_int(rg, p, 2, W - 2);
