@@ -100,7 +100,7 @@ typedef void (*rollout_fn)(const RolloutParams);
 template <int V>
 static rollout_fn pick_kernel_v(const mgb_config &c) {
     switch (c.gen) {
-    case MGB_GEN_EMPTY: return c.see_through ? k_rollout<GEN_EMPTY, true, V> : k_rollout<GEN_EMPTY, false, V>;
+    case MGB_GEN_EMPTY: case MGB_GEN_DISTSHIFT: return c.see_through ? k_rollout<GEN_EMPTY, true, V> : k_rollout<GEN_EMPTY, false, V>;
     case MGB_GEN_DOORKEY: return c.see_through ? nullptr : k_rollout<GEN_DOORKEY, false, V>;
     case MGB_GEN_FOURROOMS: return c.see_through ? nullptr : k_rollout<GEN_FOURROOMS, false, V>;
     case MGB_GEN_DYNOBS: return c.see_through ? k_rollout<GEN_DYNOBS, true, V> : nullptr;
@@ -136,6 +136,11 @@ static std::vector<uint32_t> build_template(const mgb_config &c, int GW, int HP)
     case MGB_GEN_EMPTY: case MGB_GEN_DOORKEY: case MGB_GEN_DYNOBS: case MGB_GEN_CROSSING: case MGB_GEN_LAVAGAP:   // crossing.py:31-38, lavagap.py:28-37
         wall_rect(0, 0, W, H);
         set(W - 2, H - 2, CODE_GOAL);                      // empty.py:48, doorkey.py:23, dynamicobstacles.py:43
+        break;
+    case MGB_GEN_DISTSHIFT:                                // distshift.py:30-43
+        wall_rect(0, 0, W, H);
+        set(W - 2, 1, CODE_GOAL);
+        for (int i = 0; i < W - 6; ++i) { set(3 + i, 1, code_of(T_LAVA, C_RED, 0)); set(3 + i, c.gen_param0, code_of(T_LAVA, C_RED, 0)); }
         break;
     case MGB_GEN_FOURROOMS: {                              // fourrooms.py:24-53 (walls only; gaps are drawn on device)
         wall_rect(0, 0, W, H);
@@ -182,6 +187,8 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
         if ((c.width & 1) == 0 || (c.height & 1) == 0 || c.width < 5 || c.height < 5) return fail("mgb_create: Crossing needs an odd grid size (crossing.py:25)");
         if (c.gen_param0 < 0 || (c.gen_param1 & 3) > 2 || (c.gen_param1 & ~7)) return fail("mgb_create: bad Crossing parameters");
     }
+    if (c.gen == MGB_GEN_DISTSHIFT && (c.width < 7 || c.gen_param0 < 1 || c.gen_param0 > c.height - 2 || c.random_start))
+        return fail("mgb_create: bad DistShift parameters (width >= 7, strip2_row inside the grid, fixed start)");
     if (c.gen == MGB_GEN_LAVAGAP && (c.width < 5 || c.height < 5)) return fail("mgb_create: LavaGap needs at least 5x5 (lavagap.py:22)");
     if (c.gen == MGB_GEN_MULTIROOM && (c.gen_param0 < 1 || c.gen_param0 > 8 || c.gen_param1 < 4 || c.gen_param1 > 32 || c.width != c.height))
         return fail("mgb_create: bad MultiRoom parameters (1..8 rooms, maxRoomSize 4..32, square grid)");
@@ -206,7 +213,8 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     h->n_groups = (int32_t)((num_envs + 31) / 32);
     h->view = view_of(c); h->obs_bytes = obs_bytes(h->view);
     DevCfg &d = h->dc;
-    d.gen = c.gen; d.W = c.width; d.H = c.height; d.max_steps = c.max_steps; d.see_through = c.see_through;
+    d.gen = c.gen == MGB_GEN_DISTSHIFT ? MGB_GEN_EMPTY : c.gen;      // DistShift = the Empty kernels on another template
+    d.W = c.width; d.H = c.height; d.max_steps = c.max_steps; d.see_through = c.see_through;
     d.n_actions = c.n_actions; d.n_obst = c.n_obstacles; d.room_size = c.room_size; d.num_rows = c.num_rows;
     d.random_start = c.random_start; d.lava_v1 = c.lava_v1; d.hook = c.hook; d.gp0 = c.gen_param0; d.gp1 = c.gen_param1;
     d.HP = (c.height + 3) / 4 * 4;
@@ -231,7 +239,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
 #endif
     for (int wpb = MAX_WARPS_PER_BLOCK; wpb >= 2; --wpb) {
         if (force && atoi(force) != wpb) continue;
-        const size_t smem = (size_t)table_bytes(c.gen) + (size_t)tmpl_smem_bytes(c.gen, d.GW) + (size_t)wpb * per_warp;
+        const size_t smem = (size_t)table_bytes(d.gen) + (size_t)tmpl_smem_bytes(d.gen, d.GW) + (size_t)wpb * per_warp;
         if (smem > prop.sharedMemPerBlockOptin) continue;
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, wpb * 32, smem) != cudaSuccess || nb < 1) continue;

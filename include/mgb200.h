@@ -44,8 +44,10 @@ enum {
     MGB_GEN_CROSSING = 6,     /* envs/crossing.py:24-99: gen_param0 = num_crossings, gen_param1 = ori (0 h, 1 v, 2 both) | 4 if the
                                  obstacles are walls (SimpleCrossing) instead of lava */
     MGB_GEN_LAVAGAP = 7,      /* envs/lavagap.py:21-60: gen_param0 = const (gap column fixed at width/2), gen_param1 = 1 if walls */
-    MGB_GEN_MULTIROOM = 8     /* envs/multiroom.py:41-241: gen_param0 = number of rooms (min == max in every registered id),
+    MGB_GEN_MULTIROOM = 8,    /* envs/multiroom.py:41-241: gen_param0 = number of rooms (min == max in every registered id),
                                  gen_param1 = maxRoomSize */
+    MGB_GEN_DISTSHIFT = 9     /* envs/distshift.py:30-52: a fixed layout (no draws): goal at (width-2, 1), lava strips in rows 1 and
+                                 gen_param0 = strip2_row, agent at (1,1) facing right.  Runs on the Empty kernels. */
 };
 
 /* static per-env-id configuration: what the reference bakes into constructor kwargs

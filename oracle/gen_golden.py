@@ -39,7 +39,7 @@ SNAP_EVERY = 50
 HOOK_OF_CLASS = {"UnlockPickup": 1, "BlockedUnlockPickup": 1, "ObstructedMazeEnv": 1, "Unlock": 2, "FetchEnv": 3, "GoToDoorEnv": 4, "GoToObjectEnv": 5,
                  "PutNearEnv": 6, "RedBlueDoorEnv": 7, "MemoryEnv": 8}
 GEN_OF_CLASS = {"EmptyEnv": 0, "DoorKeyEnv": 1, "FourRoomsEnv": 2, "DynamicObstaclesEnv": 3, "KeyCorridor": 4,
-                "CrossingEnv": 6, "LavaGapEnv": 7, "MultiRoomEnv": 8}
+                "CrossingEnv": 6, "LavaGapEnv": 7, "MultiRoomEnv": 8, "DistShiftEnv": 9}
 
 
 def gen_params_of(env, gen):
@@ -52,6 +52,9 @@ def gen_params_of(env, gen):
     if gen == 8:      # multiroom.py:21-39
         assert env.minNumRooms == env.maxNumRooms
         return int(env.minNumRooms), int(env.maxRoomSize)
+    if gen == 9:      # distshift.py:9-21
+        assert tuple(env.agent_start_pos) == (1, 1) and env.agent_start_dir == 0
+        return int(env.strip2_row), 0
     return 0, 0
 
 
@@ -279,6 +282,7 @@ VARIANTS = [
     "MiniGrid-SimpleCrossingS9N2-v0", "MiniGrid-SimpleCrossingS11N5-v0",
     "MiniGrid-LavaGapS5-v0", "MiniGrid-LavaGapS7-v0", "MiniGrid-NormalGapS6-v0", "MiniGrid-LavaGapS6-v1",
     "MiniGrid-MultiRoom-N2-S4-v0", "MiniGrid-MultiRoom-N4-S5-v0", "MiniGrid-MultiRoom-N6-v0",
+    "MiniGrid-DistShift1-v0", "MiniGrid-DistShift1-v1", "MiniGrid-DistShift2-v0",
 ]
 # RNG-tape traces (the reference's own MT19937 draws through TapeRecorder.randint / shuffle / choice) for the same files
 TAPE_VARIANTS = ["MiniGrid-LavaCrossingS9N2-v0", "MiniGrid-SimpleCrossingS9N3-v0", "MiniGrid-LavaGapS6-v0", "MiniGrid-MultiRoom-N6-v0"]

@@ -624,6 +624,18 @@ static void gen_multiroom(Env *e) {
     if (place_obj(e, mk_goal(1), 1, best[nbest - 1].topX, best[nbest - 1].topY, 1, best[nbest - 1].sizeX, best[nbest - 1].sizeY, 0, -1, NULL, NULL)) e->err |= 8;   /* :114 */
 }
 
+/* envs/distshift.py:30-52 (agent_start_pos = (1,1), agent_start_dir = 0 in every registered id) */
+static void gen_distshift(Env *e) {
+    Grid *g = &e->grid; int W = g->w, H = g->h;
+    wall_rect(g, 0, 0, W, H);                                           /* :35 */
+    grid_set(g, W - 2, 1, mk_goal(1));                                  /* :38, goal_pos = (width-2, 1) (:19) */
+    for (int i = 0; i < W - 6; i++) {                                   /* :41-43 */
+        grid_set(g, 3 + i, 1, mk(T_LAVA, C_RED));
+        grid_set(g, 3 + i, e->cfg.gen_param0, mk(T_LAVA, C_RED));
+    }
+    e->ax = 1; e->ay = 1; e->adir = 0; e->has_agent = 1;                /* :46-48 */
+}
+
 static void gen_pool(Env *e);
 /* reset (minigrid.py:831-858) */
 static void gen_obs(Env *e, uint8_t *obs, uint8_t *dir);
@@ -643,6 +655,7 @@ static void env_reset(Env *e, uint8_t *obs, uint8_t *dir) {
     case ORC_GEN_CROSSING: gen_crossing(e); break;
     case ORC_GEN_LAVAGAP: gen_lavagap(e); break;
     case ORC_GEN_MULTIROOM: gen_multiroom(e); break;
+    case ORC_GEN_DISTSHIFT: gen_distshift(e); break;
     }
     e->carrying = NONE;
     e->step_count = 0;

@@ -30,7 +30,8 @@ enum {
     ORC_GEN_POOL = 5,        /* reset = one of the uploaded reference layouts (base MiniGridEnv.step only) */
     ORC_GEN_CROSSING = 6,    /* envs/crossing.py:24-99; gen_param0 = num_crossings, gen_param1 = ori | 4 * (obstacle_type == Wall) */
     ORC_GEN_LAVAGAP = 7,     /* envs/lavagap.py:21-60; gen_param0 = const, gen_param1 = (obstacle_type == Wall) */
-    ORC_GEN_MULTIROOM = 8    /* envs/multiroom.py:41-241; gen_param0 = minNumRooms == maxNumRooms, gen_param1 = maxRoomSize */
+    ORC_GEN_MULTIROOM = 8,   /* envs/multiroom.py:41-241; gen_param0 = minNumRooms == maxNumRooms, gen_param1 = maxRoomSize */
+    ORC_GEN_DISTSHIFT = 9    /* envs/distshift.py:30-52; gen_param0 = strip2_row */
 };
 
 typedef struct {

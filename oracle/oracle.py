@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libminigrid_oracle.so")
 
-GEN_EMPTY, GEN_DOORKEY, GEN_FOURROOMS, GEN_DYNOBS, GEN_KEYCORRIDOR, GEN_POOL, GEN_CROSSING, GEN_LAVAGAP, GEN_MULTIROOM = range(9)
+GEN_EMPTY, GEN_DOORKEY, GEN_FOURROOMS, GEN_DYNOBS, GEN_KEYCORRIDOR, GEN_POOL, GEN_CROSSING, GEN_LAVAGAP, GEN_MULTIROOM, GEN_DISTSHIFT = range(10)
 OBS_BYTES = 147
 MAX_OBST = 8
 

@@ -74,6 +74,6 @@ def test_cuda_pool_matches_oracle_batch(name):
 def test_pool_requires_levels():
     import gym_minigrid_b200 as mgb
     with pytest.raises(ValueError, match="level-pool"):
-        mgb.make("MiniGrid-DistShift1-v0", num_envs=4)
+        mgb.make("MiniGrid-SimpleRoom-v0", num_envs=4)
     with pytest.raises(ValueError, match="only for level-pool"):
         mgb.make("MiniGrid-Empty-8x8-v0", num_envs=4, levels=dict(grid=np.zeros((1, 8, 8, 3), np.uint8), agent=np.zeros((1, 3))))

@@ -25,15 +25,17 @@ def header_functions():
 def test_registry_contract():
     for i in HEADLINE:
         assert i in mgb.env_list
-    assert len(mgb.env_list) == len(set(mgb.env_list)) == 81      # 42 with device generators + 39 level-pool-only ids
-    assert sum(1 for i in mgb.env_list if mgb.spec(i)["config"]["gen"] != 5) == 42
+    assert len(mgb.env_list) == len(set(mgb.env_list)) == 81      # 45 with device generators + 36 level-pool-only ids
+    assert sum(1 for i in mgb.env_list if mgb.spec(i)["config"]["gen"] != 5) == 45
     with pytest.raises(AssertionError):            # register.py:12  id must start with "MiniGrid-"
         mgb.register("Foo-v0", "gym_minigrid.envs:EmptyEnv")
     with pytest.raises(AssertionError):            # register.py:13  ids are unique
         mgb.register("MiniGrid-Empty-8x8-v0", "gym_minigrid.envs:EmptyEnv")
     with pytest.raises(KeyError):
         mgb.spec("MiniGrid-MinimapForSparky-v0")    # out of scope (SAR env): loud, not silent
-    assert mgb.spec("MiniGrid-DistShift1-v0")["config"]["gen"] == 5       # level-pool id
+    assert mgb.spec("MiniGrid-SimpleRoom-v0")["config"]["gen"] == 5       # level-pool id (its generator draws from the global np.random)
+    c = mgb.spec("MiniGrid-DistShift2-v0")["config"]                      # distshift.py:62-64: fixed layout
+    assert (c["gen"], c["gen_param0"], c["see_through"]) == (9, 5, 1)
     c = mgb.spec("MiniGrid-MultiRoom-N6-v0")["config"]                    # multiroom.py:255-262: on-device generator
     assert (c["gen"], c["gen_param0"], c["gen_param1"], c["width"], c["max_steps"]) == (8, 6, 10, 25, 120)
     c = mgb.spec("MiniGrid-SimpleCrossingS11N5-v0")["config"]             # crossing.py:135-137
