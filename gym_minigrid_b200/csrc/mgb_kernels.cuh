@@ -54,8 +54,10 @@ constexpr int AXIS_ENTRIES = 88;                                 // v in [-(V-1)
 constexpr int AXIS_BIAS = 10;
 constexpr int MBAR_BYTES = MAX_WARPS_PER_BLOCK * 8;               // one mbarrier per warp (bulk load of the state block)
 __host__ __device__ constexpr int table_bytes(int gen) { return (lut_bytes(gen) + 2 * AXIS_ENTRIES * 4 + MBAR_BYTES + 127) / 128 * 128; }   // 3840 / 1792
-// the template-grid kernels (Empty, Dynamic-Obstacles) keep a copy of the static layout behind the tables (see "pristine")
-__host__ __device__ inline int tmpl_smem_bytes(int gen, int GW) { return (gen == 0 || gen == 3) ? (GW * 4 + 127) / 128 * 128 : 0; }
+// Every kernel with a device generator keeps a copy of the static layout behind the tables: a reset copies it into the
+// env's column from shared memory.  (From global memory that copy was GW dependent L2 round trips -- with episode ends
+// spread over time, i.e. one resetting lane per warp, 10-30 k cycles per reset: Empty-8x8 -24 %, FourRooms -28 %.)
+__host__ __device__ inline int tmpl_smem_bytes(int gen, int GW) { return gen == 5 /* GEN_POOL: no template */ ? 0 : (GW * 4 + 127) / 128 * 128; }
 
 // minigrid.py:40-52 / 27-35 / 57-61
 enum : int { T_UNSEEN = 0, T_EMPTY = 1, T_WALL = 2, T_FLOOR = 3, T_DOOR = 4, T_KEY = 5, T_BALL = 6,
@@ -589,19 +591,19 @@ __device__ __noinline__ bool gen_multiroom(uint32_t *st, Env &e_, Rng &rg_, cons
 }
 
 template <int GEN>
-__device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, PoolCtx *pc, uint32_t *scr);
+__device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, PoolCtx *pc, uint32_t *scr, const uint32_t *tmpl_s);
 // out of line; works on register copies of the caller's Env / Rng (see rand_int_inl)
 template <int GEN>
-__device__ __noinline__ void generate(uint32_t *st, Env &e_, Rng &rg_, const RolloutParams &p, PoolCtx *pc, uint32_t *scr) {
-    if (GEN == GEN_EMPTY) { generate_body<GEN>(st, e_, rg_, p, pc, scr); return; }     // see rand_int_ool
+__device__ __noinline__ void generate(uint32_t *st, Env &e_, Rng &rg_, const RolloutParams &p, PoolCtx *pc, uint32_t *scr, const uint32_t *tmpl_s) {
+    if (GEN == GEN_EMPTY) { generate_body<GEN>(st, e_, rg_, p, pc, scr, tmpl_s); return; }     // see rand_int_ool
     Env e = e_;
     Rng rg = rg_;
-    generate_body<GEN>(st, e, rg, p, pc, scr);
+    generate_body<GEN>(st, e, rg, p, pc, scr, tmpl_s);
     e_ = e;
     rg_ = rg;
 }
 template <int GEN>
-__device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, PoolCtx *pc, uint32_t *scr) {
+__device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, const RolloutParams &p, PoolCtx *pc, uint32_t *scr, const uint32_t *tmpl_s) {
     const DevCfg &c = p.cfg;
     const int W = c.W, H = c.H, HP = c.HP;
     if (GEN == GEN_POOL) {
@@ -613,7 +615,8 @@ __device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, con
         if (p.pool_n <= 0) { rg.err |= ERR_NO_POOL; return; }
         const int lvl = rand_int(rg, p, 0, p.pool_n);
         const uint32_t *src = p.pool + (size_t)lvl * (c.GW + POOL_XW);
-        for (int k = 0; k < c.GW; ++k) st[k * 32] = __ldg(&src[k]);
+#pragma unroll 8
+        for (int k = 0; k < c.GW; ++k) st[k * 32] = __ldg(&src[k]);        // independent loads, eight in flight
         const uint32_t a = __ldg(&src[c.GW]);
         e.ax = a & 0xFF; e.ay = (a >> 8) & 0xFF; e.dir = (a >> 16) & 3;
         pc->level = lvl;
@@ -626,7 +629,7 @@ __device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, con
         // removing the old balls restores the template
         for (int k = 0; k < c.n_obst; ++k) { int ox, oy; obst_get(st, c, k, ox, oy); cell_wr(st, ox * HP + oy, CODE_EMPTY); }
     } else {
-        for (int k = 0; k < c.GW; ++k) st[k * 32] = __ldg(&p.tmpl[k]);
+        for (int k = 0; k < c.GW; ++k) st[k * 32] = tmpl_s[k];           // the CTA's shared-memory copy of the template
     }
     e.dirty = true;
     rg.episode++;
@@ -1365,7 +1368,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
     uint32_t *axis = lut + lut_bytes(GEN) / 4;                                           // [2][AXIS_ENTRIES]
     uint32_t *tmpl_s = reinterpret_cast<uint32_t *>(smem_raw + table_bytes(GEN));
     uint8_t *stage_base = smem_raw + table_bytes(GEN) + tmpl_smem_bytes(GEN, c.GW);
-    if (template_gen(GEN))
+    if (GEN != GEN_POOL)
         for (int i = threadIdx.x; i < c.GW; i += blockDim.x) tmpl_s[i] = __ldg(&p.tmpl[i]);
     constexpr int SB = stage_bytes(V), OB = obs_bytes(V), SB_OBS = GROUP * OB;
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage_base + warp * SB);
@@ -1469,7 +1472,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
                 if (lane == 0) bulk_store_wait_read();
                 __syncwarp();
             }
-            if (m) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, stage_w + lane); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }   // copy-in/out keeps e, rg in registers
+            if (m) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, stage_w + lane, tmpl_s); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }   // copy-in/out keeps e, rg in registers
         }
         const int nsteps = p.T > 0 ? p.T : 1;
         int a_next = 0;
@@ -1535,7 +1538,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
                     if (lane == 0) bulk_store_wait_read();
                     __syncwarp();
                 }
-                if (need_reset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, stage_w + lane); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
+                if (need_reset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, stage_w + lane, tmpl_s); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
             }
             if (gobs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
