@@ -69,6 +69,7 @@ struct mgb_handle {
     int64_t env_id_base = 0;
     int autoreset = 1;
     uint32_t *state = nullptr;
+    uint32_t *spare = nullptr;               // pre-generated next layouts (spare_gen kernels)
     uint32_t *tmpl = nullptr;
     uint32_t *err = nullptr;
     const int32_t *tape = nullptr;
@@ -274,6 +275,13 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     const size_t state_bytes = (size_t)h->n_groups * d.S * 32 * 4;
     if (cudaMalloc(&h->state, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: cudaMalloc(%zu) for env state failed", state_bytes));
     if (cudaMemset(h->state, 0, state_bytes) != cudaSuccess) return cleanup(fail("mgb_create: memset failed"));
+    // Spare layouts (reset_with_spares) for the generators that cost more than a trip to HBM.  Measured with episode ends
+    // spread over time (profiles/r2_desync_spares.txt): KeyCorridorS6R3 +50 %, S3R3 2.6x, SimpleCrossingS11N5 +36 %,
+    // MultiRoom-N6 2.2x; LavaGap's generator is a handful of draws and loses 9 % to the round trip: it goes without.
+    if (MGB_SPARES && (c.gen == MGB_GEN_KEYCORRIDOR || c.gen == MGB_GEN_CROSSING || c.gen == MGB_GEN_MULTIROOM)) {
+        const size_t spare_bytes = (size_t)h->n_groups * spare_words(d.GW) * 32 * 4;
+        if (cudaMalloc(&h->spare, spare_bytes) != cudaSuccess) return cleanup(fail("mgb_create: cudaMalloc(%zu) for the spare layouts failed", spare_bytes));
+    }
     std::vector<uint32_t> t = build_template(c, d.GW, d.HP);
     if (cudaMalloc(&h->tmpl, t.size() * 4) != cudaSuccess || cudaMemcpy(h->tmpl, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
         return cleanup(fail("mgb_create: template upload failed"));
@@ -287,7 +295,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
 int mgb_destroy(mgb_handle *h) {
     if (!h) return 0;
     DeviceGuard guard_(h->device);
-    cudaFree(h->state); cudaFree(h->tmpl); cudaFree(h->err); cudaFree(h->pool);
+    cudaFree(h->state); cudaFree(h->spare); cudaFree(h->tmpl); cudaFree(h->err); cudaFree(h->pool);
     cudaFree(h->policy_scratch);
     cudaFree(h->d_actions); cudaFree(h->d_obs); cudaFree(h->d_done); cudaFree(h->d_dir); cudaFree(h->d_reward);
     for (auto &s : h->pipe) if (s) cudaStreamDestroy(s);
@@ -338,7 +346,7 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
                   int64_t stride, cudaStream_t stream, bool timed, bool order = true) {
     if (ng <= 0) return 0;
     RolloutParams p;
-    p.cfg = h->dc; p.state = h->state; p.tmpl = h->tmpl; p.n_envs = h->n_envs;
+    p.cfg = h->dc; p.state = h->state; p.spare = h->spare; p.tmpl = h->tmpl; p.n_envs = h->n_envs;
     p.group0 = g0; p.n_groups = ng; p.T = T; p.do_reset = do_reset; p.autoreset = h->autoreset;
     p.reset_mask = mask; p.actions = actions; p.obs = obs; p.reward = reward; p.done = done; p.dir = dir;
     p.stride = stride; p.seed = h->seed; p.env_id_base = h->env_id_base;
@@ -366,6 +374,10 @@ int mgb_seed(mgb_handle *h, uint64_t seed) {
     // enqueued before (any stream) is drained first, and the memset is complete before a later reset can be enqueued
     CUDA_OK(cudaDeviceSynchronize());
     CUDA_OK(cudaMemset2D(h->state + (size_t)(d.GW + 2) * 32, (size_t)d.S * 32 * 4, 0, 2 * 32 * 4, h->n_groups));
+    if (h->spare) {                                             // layouts pre-generated under the old seed are void
+        k_clear_flags<<<(unsigned)((h->n_envs + 255) / 256), 256>>>(h->state, d.S, d.GW, h->n_envs, (uint32_t)FLAG_SPARE);
+        CUDA_OK(cudaGetLastError());
+    }
     CUDA_OK(cudaDeviceSynchronize());
     return 0;
 }
@@ -669,3 +681,11 @@ int mgb_error_flags(mgb_handle *h, void *stream, uint32_t *flags_host) {
 }
 
 }  // extern "C"
+
+#ifdef MGB_DEBUG_SPARES
+extern "C" int mgb_debug_spares(unsigned long long *out, int clear) {
+    if (cudaMemcpyFromSymbol(out, mgb::g_spare_dbg, sizeof(unsigned long long) * 8) != cudaSuccess) return 1;
+    if (clear) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(mgb::g_spare_dbg, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -117,6 +117,7 @@ struct DevCfg {
 struct RolloutParams {
     DevCfg cfg;
     uint32_t *state;            // [n_groups][S][32]
+    uint32_t *spare;            // [n_groups][spare_words(GW)][32]: pre-generated next layouts (spare_gen kernels), or NULL
     const uint32_t *tmpl;       // [GW] static part of the layout (walls, fixed goal)
     int64_t n_envs;
     int32_t group0, n_groups;   // group sub-range handled by this launch
@@ -357,6 +358,15 @@ __device__ __forceinline__ void obst_set(uint32_t *st, const DevCfg &c, int k, i
 }
 
 constexpr int FLAG_PRISTINE = 1;
+constexpr int FLAG_SPARE = 2;            // the env's spare block holds the layout of its NEXT episode (see reset_lanes)
+constexpr int SPARE_XW = 5;              // spare block = GW grid words + agent word, target, draws consumed, error bits, episode,
+__host__ __device__ constexpr int spare_words(int GW) { return 2 * GW + SPARE_XW; }      // + GW words where a live grid is parked
+// kernels whose generator is worth more than a trip to HBM (measured: for DoorKey and FourRooms it is not -- fetching a
+// spare layout with one lane costs more than generating it)
+#ifndef MGB_SPARES
+#define MGB_SPARES 1
+#endif
+__host__ __device__ constexpr bool spare_gen(int gen) { return MGB_SPARES && (gen == GEN_KEYCORRIDOR || gen == GEN_PROC); }
 __host__ __device__ constexpr bool template_gen(int gen) { return gen == GEN_EMPTY || gen == GEN_DYNOBS; }
 constexpr uint32_t CODE_BLUE_BALL = (uint32_t)code_of(T_BALL, C_BLUE, 0);
 
@@ -1345,6 +1355,99 @@ __device__ __forceinline__ void bulk_commit() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+// Reset of the lanes with `need` set (auto-reset after a done step, or mgb_reset).  A generator is a long scalar routine:
+// run for ONE finished env it costs the warp as much as run for all 32, and with episode ends spread over time (a
+// KeyCorridor policy that picks up its target) that is what happens -- 2.9e10 -> 1.7e10 env-steps/s.  So whenever some
+// lane has to generate, every lane of the warp that holds no spare layout generates the layout of its own NEXT episode in
+// the same pass (it depends only on seed, env id and episode number) and parks it in the env's spare block in HBM; a later
+// reset of such a lane is a copy.  A lane that pre-generates parks its live grid in HBM, runs the generator in place in
+// shared memory, stores the result and fetches its grid back.  Results are bit-identical to generating at the reset.
+#ifdef MGB_DEBUG_SPARES
+__device__ unsigned long long g_spare_dbg[8];     // calls, consumed, stale, passes, lanes generating live, lanes generating ahead
+#define SPARE_DBG(i, n) atomicAdd(&g_spare_dbg[i], (unsigned long long)(n))
+#else
+#define SPARE_DBG(i, n)
+#endif
+// 4-byte asynchronous copies global -> shared (LDGSTS): a lane fetches a whole grid column with every word in flight at
+// once and no registers.  It matters: under the kernel's write stream a dependent HBM read takes several microseconds.
+__device__ __forceinline__ void cp_async_word(uint32_t dst_sa, const uint32_t *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_sa), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+template <int GEN>
+__device__ __noinline__ void reset_with_spares(bool need, bool valid, uint32_t *st, int group, Env &e, Rng &rg,
+                                               const RolloutParams &p, uint32_t *scr, const uint32_t *tmpl_s) {
+    const int GW = p.cfg.GW;
+    const bool spares = p.spare != nullptr && p.tape == nullptr;
+    uint32_t *const spc = p.spare + (size_t)group * spare_words(GW) * 32 + (threadIdx.x & 31);      // words 0..GW+4: the spare
+    uint32_t *const park = spc + (size_t)(GW + SPARE_XW) * 32;                                      // words GW+5..: parking rows
+    const uint32_t st_sa = (uint32_t)__cvta_generic_to_shared(st);
+    uint32_t &fw = st[(GW + 1) * 32];                                 // FLAG_SPARE stays in the state word (k_rollout carries it over)
+    if ((threadIdx.x & 31) == 0) SPARE_DBG(0, 1);
+    if (spares && need && (fw & (FLAG_SPARE << 24))) {              // 1. a reset with a spare at hand is a copy: ONE round trip
+        fw &= ~((uint32_t)FLAG_SPARE << 24);
+        for (int k = 0; k < GW; ++k) cp_async_word(st_sa + (uint32_t)k * 128u, spc + k * 32);
+        const uint32_t a = __ldcg(&spc[GW * 32]), tg = __ldcg(&spc[(GW + 1) * 32]), nd = __ldcg(&spc[(GW + 2) * 32]);
+        const uint32_t er = __ldcg(&spc[(GW + 3) * 32]), ep = __ldcg(&spc[(GW + 4) * 32]);
+        cp_async_wait_all();
+        SPARE_DBG(ep == rg.episode + 1u ? 1 : 2, 1);
+        if (ep == rg.episode + 1u) {                                  // the layout of exactly the episode that starts now (else: the
+            e.ax = a & 0xFF; e.ay = (a >> 8) & 0xFF; e.dir = (a >> 16) & 3; e.carry = 0; e.steps = 0;     // generator below overwrites it)
+            e.target = (int)tg; e.dirty = true;
+            rg.episode++; rg.ndraws = nd; rg.rblk = 0xFFFFFFFFu; rg.err |= er;
+            need = false;
+        }
+    }
+    if (!__any_sync(0xFFFFFFFFu, need)) return;
+    if (GEN == GEN_PROC && p.cfg.gen == GEN_MULTIROOM) {              // the MultiRoom generator scribbles in the staging block
+        if ((threadIdx.x & 31) == 0) bulk_store_wait_read();
+        __syncwarp();
+    }
+    const bool pre = spares && valid && !need && !(fw & (FLAG_SPARE << 24));   // 2. somebody generates: so does everybody without a spare
+    if ((threadIdx.x & 31) == 0) SPARE_DBG(3, 1);
+    if (need) SPARE_DBG(4, 1);
+    if (pre) SPARE_DBG(5, 1);
+    if (pre) {
+#pragma unroll 8
+        for (int k = 0; k < GW; ++k) __stcg(&park[k * 32], st[k * 32]);         // the live grid waits in HBM meanwhile
+    }
+    if (need || pre) {
+        Env te = e; Rng tr = rg;
+        generate<GEN>(st, te, tr, p, nullptr, scr, tmpl_s);
+        if (!pre) { e = te; rg = tr; }
+        else {
+#pragma unroll 8
+            for (int k = 0; k < GW; ++k) __stcg(&spc[k * 32], st[k * 32]);
+            __stcg(&spc[GW * 32], (uint32_t)te.ax | ((uint32_t)te.ay << 8) | ((uint32_t)te.dir << 16));
+            __stcg(&spc[(GW + 1) * 32], (uint32_t)te.target);
+            __stcg(&spc[(GW + 2) * 32], tr.ndraws);
+            __stcg(&spc[(GW + 3) * 32], tr.err & ~rg.err);
+            __stcg(&spc[(GW + 4) * 32], tr.episode);
+            fw |= (uint32_t)FLAG_SPARE << 24;
+            __threadfence();                                             // the parked rows were written by this thread, long ago
+            for (int k = 0; k < GW; ++k) cp_async_word(st_sa + (uint32_t)k * 128u, park + k * 32);
+            cp_async_wait_all();
+        }
+    }
+}
+template <int GEN>
+__device__ __forceinline__ void reset_lanes(bool need, bool valid, uint32_t *st, int group, Env &e, Rng &rg, PoolCtx &pc,
+                                            const RolloutParams &p, uint32_t *scr, const uint32_t *tmpl_s) {
+    if (spare_gen(GEN)) {
+        if (__any_sync(0xFFFFFFFFu, need)) {
+            Env te = e; Rng tr = rg;                                  // copy-in/out keeps e, rg in registers
+            reset_with_spares<GEN>(need, valid, st, group, te, tr, p, scr, tmpl_s);
+            e = te; rg = tr;
+        }
+    } else if (need) {
+        Env te = e; Rng tr = rg; PoolCtx tp = pc;
+        generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, scr, tmpl_s);
+        e = te; rg = tr; if (GEN == GEN_POOL) pc = tp;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // the persistent rollout kernel (also serves reset and single step)
 // ------------------------------------------------------------------------------------------
@@ -1445,7 +1548,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         {
             const uint32_t w0 = st[(GW + 0) * 32], w1 = st[(GW + 1) * 32];
             e.ax = w0 & 0xFF; e.ay = (w0 >> 8) & 0xFF; e.dir = (w0 >> 16) & 3; e.carry = w0 >> 24;
-            e.steps = w1 & 0xFFFF; e.target = (w1 >> 16) & 0xFF; e.flags = w1 >> 24;
+            e.steps = w1 & 0xFFFF; e.target = (w1 >> 16) & 0xFF; e.flags = (w1 >> 24) & FLAG_PRISTINE;
             rg.episode = st[(GW + 2) * 32]; rg.ndraws = st[(GW + 3) * 32];
             if (GEN == GEN_POOL) {
                 pc.level = (int)st[(GW + XWORDS) * 32];
@@ -1468,11 +1571,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
 
         if (p.do_reset) {
             const bool m = valid && (!p.reset_mask || p.reset_mask[lid]);
-            if (GEN == GEN_PROC && c.gen == GEN_MULTIROOM && __any_sync(0xFFFFFFFFu, m)) {   // the MultiRoom generator scribbles in the staging block
-                if (lane == 0) bulk_store_wait_read();
-                __syncwarp();
-            }
-            if (m) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, stage_w + lane, tmpl_s); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }   // copy-in/out keeps e, rg in registers
+            reset_lanes<GEN>(m, valid, st, group, e, rg, pc, p, stage_w + lane, tmpl_s);
         }
         const int nsteps = p.T > 0 ? p.T : 1;
         int a_next = 0;
@@ -1534,11 +1633,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
                         }
                     }
                 }
-                if (GEN == GEN_PROC && c.gen == GEN_MULTIROOM && __any_sync(0xFFFFFFFFu, need_reset)) {   // the MultiRoom generator scribbles in the staging block
-                    if (lane == 0) bulk_store_wait_read();
-                    __syncwarp();
-                }
-                if (need_reset) { Env te = e; Rng tr = rg; PoolCtx tp = pc; generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, stage_w + lane, tmpl_s); e = te; rg = tr; if (GEN == GEN_POOL) pc = tp; }
+                reset_lanes<GEN>(need_reset, valid, st, group, e, rg, pc, p, stage_w + lane, tmpl_s);
             }
             if (gobs) {
                 if (lane == 0) bulk_store_wait_read();          // previous block has left shared memory
@@ -1571,7 +1666,8 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         }
         // ---- write the state back ----
         st[(GW + 0) * 32] = (uint32_t)e.ax | ((uint32_t)e.ay << 8) | ((uint32_t)e.dir << 16) | ((uint32_t)e.carry << 24);
-        st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16) | ((uint32_t)e.flags << 24);
+        st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16) | ((uint32_t)e.flags << 24)
+                            | (spare_gen(GEN) ? st[(GW + 1) * 32] & ((uint32_t)FLAG_SPARE << 24) : 0u);
         st[(GW + 2) * 32] = rg.episode;
         st[(GW + 3) * 32] = rg.ndraws;
         if (GEN == GEN_POOL) st[(GW + XWORDS) * 32] = (uint32_t)pc.level;
@@ -1644,6 +1740,13 @@ __global__ void k_materialize(DevCfg c, uint32_t *state, const uint32_t *__restr
     base[(c.GW + 1) * 32] = fw & ~((uint32_t)FLAG_PRISTINE << 24);
 }
 
+// clears flag bits of every env (mgb_seed: another seed invalidates the pre-generated layouts)
+__global__ void k_clear_flags(uint32_t *state, int S, int GW, int64_t n, uint32_t bits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    state[((i >> 5) * S + GW + 1) * 32 + (i & 31)] &= ~(bits << 24);
+}
+
 // one thread per (env, state word)
 __global__ void k_set_state(const StateIO io) {
     const DevCfg &c = io.cfg;
@@ -1686,7 +1789,8 @@ __global__ void k_set_state(const StateIO io) {
         *dst = w;
     } else if (k == c.GW + 1) {
         uint32_t w = *dst;
-        if (io.grid || io.obstacles) w &= 0x00FFFFFFu;      // flags: an uploaded grid / ball list ends 'template + balls' (state_io materialises the grid first)
+        if (io.grid || io.obstacles) w &= ~((uint32_t)FLAG_PRISTINE << 24);      // an uploaded grid / ball list ends 'template + balls' (state_io materialises the grid first)
+        if (io.rng) w &= ~((uint32_t)FLAG_SPARE << 24);        // another episode counter: the pre-generated next layout is not this env's any more
         if (io.agent) w = (w & 0xFFFF0000u) | (uint32_t)(io.agent[n * 4 + 3] & 0xFFFF);
         if (io.target) {
             const uint8_t *q = io.target + n * 2;

@@ -516,3 +516,82 @@ def test_handle_calls_leave_the_current_device_alone():
     assert torch.cuda.current_device() == 0
     x = torch.ones(4, device="cuda")
     assert x.device.index == 0
+
+
+def _scatter_step_counts(env, orc, rs, lo_left, hi_left, max_steps):
+    """give every env its own remaining time: step_count = max_steps - left, left drawn from [lo_left, hi_left)"""
+    so = orc.get_state()
+    left = rs.randint(lo_left, hi_left, size=so["agent"].shape[0])
+    so["agent"][:, 3] = max_steps - left
+    orc.set_state(so)
+    env.set_state({"agent": torch.as_tensor(so["agent"])})
+
+
+@pytest.mark.parametrize("env_id", ["MiniGrid-DoorKey-5x5-v0", "MiniGrid-DoorKey-16x16-v0", "MiniGrid-FourRooms-v0",
+                                    "MiniGrid-KeyCorridorS6R3-v0", "MiniGrid-KeyCorridorS3R1-v0", "MiniGrid-LavaCrossingS9N2-v0",
+                                    "MiniGrid-SimpleCrossingS11N5-v0", "MiniGrid-LavaGapS7-v0", "MiniGrid-MultiRoom-N4-S5-v0"])
+def test_spread_out_episode_ends_match_oracle(env_id):
+    """Episode ends that do NOT come in lock-step: each env reaches its time limit at its own step, so resets hit single
+    lanes of a warp.  The kernels then generate next-episode layouts ahead of time for the other lanes of the warp (spare
+    layouts) and later resets copy them; outputs and state must stay bit-identical to the oracle, which generates at the
+    reset.  Three rounds so that spares are made, consumed, and made again; rollouts and single-step launches mixed; a
+    grid upload in between must leave the spares usable, an rng upload must drop them."""
+    from oracle.oracle import OracleVec
+    mgb = _mgb()
+    cfg = _oracle_cfg(env_id)
+    N, T, seed, base = 1024 + 32 + 5, 48, 7, 5000
+    rs = np.random.RandomState(11)
+    env = mgb.make(env_id, num_envs=N, seed=seed, env_id_base=base)
+    orc = OracleVec(cfg, N, seed=seed, env0=base)
+    o0 = env.reset()
+    ro0, _ = orc.reset()
+    assert_same(env_id + " reset obs", _np(o0["image"]), ro0)
+    for rnd in range(4):
+        _scatter_step_counts(env, orc, rs, 1, 40, cfg["max_steps"])
+        if rnd == 2:                                   # same state, uploaded in full (rng included): pre-generated layouts are dropped
+            so = orc.get_state()
+            env.set_state({k: torch.as_tensor(so[k].astype(np.int64) if k == "rng" else so[k]) for k in so})
+        actions = rs.randint(0, cfg["n_actions"], size=(T, N)).astype(np.uint8)
+        want = orc.rollout(actions, autoreset=True)
+        if rnd % 2 == 0:
+            o, r, dn, dr = [_np(x) for x in env.rollout(torch.as_tensor(actions))]
+        else:
+            res = []
+            for t in range(T):
+                ob, r, dn, _ = env.step(torch.as_tensor(actions[t]))
+                res.append((_np(ob["image"]).copy(), _np(r).copy(), _np(dn).copy(), _np(ob["direction"]).copy()))
+            o, r, dn, dr = [np.stack(x) for x in zip(*res)]
+        tag = "%s round %d" % (env_id, rnd)
+        assert want[2].sum() >= N, tag                 # every env ended an episode in this round
+        assert_same(tag + " done", dn.astype(np.uint8), want[2])
+        assert_same(tag + " obs", o, want[0])
+        assert_same(tag + " dir", dr, want[3])
+        assert_same(tag + " reward bits", bits(r), bits(want[1]))
+        s, so = env.get_state(), orc.get_state()
+        for key in ("grid", "aux", "agent", "carrying", "target"):
+            assert_same(tag + " state." + key, _np(s[key]), so[key])
+        assert_same(tag + " state.rng", _np(s["rng"]).view(np.uint32), so["rng"])
+    env.check_errors()
+
+
+def test_reseed_drops_pre_generated_layouts():
+    """a layout generated ahead of time belongs to (seed, env, episode): after env.seed() the same episode numbers come round
+    again under another seed and must not pick up the old layouts"""
+    from oracle.oracle import OracleVec
+    mgb = _mgb()
+    env_id = "MiniGrid-DoorKey-6x6-v0"
+    cfg = _oracle_cfg(env_id)
+    N, T = 96, 40
+    rs = np.random.RandomState(3)
+    env = mgb.make(env_id, num_envs=N, seed=1)
+    for seed in (1, 2, 1):
+        env.seed(seed)
+        orc = OracleVec(cfg, N, seed=seed)
+        env.reset(); orc.reset()
+        _scatter_step_counts(env, orc, rs, 1, 30, cfg["max_steps"])
+        actions = rs.randint(0, cfg["n_actions"], size=(T, N)).astype(np.uint8)
+        want = orc.rollout(actions, autoreset=True)
+        got = [_np(x) for x in env.rollout(torch.as_tensor(actions))]
+        assert_same("seed %d obs" % seed, got[0], want[0])
+        assert_same("seed %d done" % seed, got[2].astype(np.uint8), want[2])
+        assert_same("seed %d state.grid" % seed, _np(env.get_state()["grid"]), orc.get_state()["grid"])
