@@ -366,6 +366,9 @@ __host__ __device__ constexpr int spare_words(int GW) { return 2 * GW + SPARE_XW
 #ifndef MGB_SPARES
 #define MGB_SPARES 1
 #endif
+#ifndef MGB_EMPTY_QUICK
+#define MGB_EMPTY_QUICK 1
+#endif
 __host__ __device__ constexpr bool spare_gen(int gen) { return MGB_SPARES && (gen == GEN_KEYCORRIDOR || gen == GEN_PROC); }
 __host__ __device__ constexpr bool template_gen(int gen) { return gen == GEN_EMPTY || gen == GEN_DYNOBS; }
 constexpr uint32_t CODE_BLUE_BALL = (uint32_t)code_of(T_BALL, C_BLUE, 0);
@@ -1441,7 +1444,18 @@ __device__ __forceinline__ void reset_lanes(bool need, bool valid, uint32_t *st,
             reset_with_spares<GEN>(need, valid, st, group, te, tr, p, scr, tmpl_s);
             e = te; rg = tr;
         }
-    } else if (need) {
+    } else {
+#if MGB_EMPTY_QUICK
+        // Empty with a fixed start, grid untouched (it always is): the reset is a handful of register moves.  Out of line it
+        // costs a call with its spills and fills -- local memory is an L2 round trip here -- which is what a policy that
+        // reaches the goal every dozen steps would pay on nearly every warp-step.
+        if (GEN == GEN_EMPTY && need && !p.cfg.random_start && (e.flags & FLAG_PRISTINE)) {
+            e.ax = 1; e.ay = 1; e.dir = 0; e.carry = 0; e.steps = 0; e.target = 0;
+            rg.episode++; if (!p.tape) rg.ndraws = 0; rg.rblk = 0xFFFFFFFFu;
+            need = false;
+        }
+#endif
+        if (!need) return;
         Env te = e; Rng tr = rg; PoolCtx tp = pc;
         generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, scr, tmpl_s);
         e = te; rg = tr; if (GEN == GEN_POOL) pc = tp;
