@@ -376,15 +376,20 @@ constexpr uint32_t CODE_BLUE_BALL = (uint32_t)code_of(T_BALL, C_BLUE, 0);
 // grid of a pristine env into the lane's shared-memory column: template words + the balls of the obstacle list
 // (which is already in shared memory: words GW+XWORDS..)
 // `tmpl_s`: the CTA's shared-memory copy of the template (all lanes read the same word: a broadcast, no global latency)
-__device__ __forceinline__ void rebuild_pristine_grid(uint32_t *st, const RolloutParams &p, const uint32_t *tmpl_s) {
-    const DevCfg &c = p.cfg;
+// template -> the lane's column, four words per shared-memory load (16-byte aligned: tmpl_s sits behind the 128-byte-padded tables)
+__device__ __forceinline__ void copy_template(uint32_t *st, const uint32_t *tmpl_s, int GW) {
     const uint4 *t4 = reinterpret_cast<const uint4 *>(tmpl_s);
     int k = 0;
-    for (; k + 4 <= c.GW; k += 4) {
+#pragma unroll 4
+    for (; k + 4 <= GW; k += 4) {
         const uint4 v = t4[k >> 2];
         st[k * 32] = v.x; st[(k + 1) * 32] = v.y; st[(k + 2) * 32] = v.z; st[(k + 3) * 32] = v.w;
     }
-    for (; k < c.GW; ++k) st[k * 32] = tmpl_s[k];
+    for (; k < GW; ++k) st[k * 32] = tmpl_s[k];
+}
+__device__ __forceinline__ void rebuild_pristine_grid(uint32_t *st, const RolloutParams &p, const uint32_t *tmpl_s) {
+    const DevCfg &c = p.cfg;
+    copy_template(st, tmpl_s, c.GW);
     for (int j = 0; j < c.n_obst; ++j) {
         int ox, oy;
         obst_get(st, c, j, ox, oy);
@@ -642,7 +647,7 @@ __device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, con
         // removing the old balls restores the template
         for (int k = 0; k < c.n_obst; ++k) { int ox, oy; obst_get(st, c, k, ox, oy); cell_wr(st, ox * HP + oy, CODE_EMPTY); }
     } else {
-        for (int k = 0; k < c.GW; ++k) st[k * 32] = tmpl_s[k];           // the CTA's shared-memory copy of the template
+        copy_template(st, tmpl_s, c.GW);                                // from the CTA's shared-memory copy
     }
     e.dirty = true;
     rg.episode++;
