@@ -25,3 +25,18 @@ python profiles/tools/summarize.py gpurun_out/$tag.ncu-rep $tag k_rolloutILi0ELb
 rm -f gpurun_out/$tag.ncu-rep
 python profiles/tools/sustained.py --seconds 4 > gpurun_out/${R}_sustained.txt 2> gpurun_out/${R}_sustained.err
 tail -3 gpurun_out/${R}_sustained.txt
+# 5. episode ends spread over time (every env its own remaining time) next to the lock-step case: the five BASELINE configs
+#    and the generator families that keep spare layouts; then the spare-layout counters of one KeyCorridor run
+#    (build/ab/dbg.so = the same source with -DMGB_DEBUG_SPARES=1, build/ab/nospares.so = -DMGB_SPARES=0)
+(python -c "from gym_minigrid_b200 import _lib; print('# library:', _lib.load().mgb_version().decode())"
+ for e in MiniGrid-Empty-8x8-v0 MiniGrid-DoorKey-16x16-v0 MiniGrid-FourRooms-v0 MiniGrid-Dynamic-Obstacles-16x16-v0 MiniGrid-KeyCorridorS6R3-v0 \
+          MiniGrid-KeyCorridorS3R3-v0 MiniGrid-SimpleCrossingS11N5-v0 MiniGrid-LavaCrossingS9N2-v0 MiniGrid-MultiRoom-N6-v0 MiniGrid-DistShift1-v0; do
+   timeout 120 python profiles/tools/desync.py $e 40
+ done) > gpurun_out/${R}_desync.txt 2>&1
+if [ -f build/ab/nospares.so ]; then
+ (for e in MiniGrid-KeyCorridorS6R3-v0 MiniGrid-KeyCorridorS3R3-v0 MiniGrid-SimpleCrossingS11N5-v0 MiniGrid-LavaCrossingS9N2-v0 MiniGrid-MultiRoom-N6-v0; do
+   MGB_LIB=$PWD/build/ab/nospares.so timeout 120 python profiles/tools/desync.py $e 40 | sed "s|^|-DMGB_SPARES=0 |"
+ done) > gpurun_out/${R}_desync_without_spares.txt 2>&1
+fi
+[ -f build/ab/dbg.so ] && MGB_LIB=$PWD/build/ab/dbg.so timeout 120 python profiles/tools/spare_probe.py MiniGrid-KeyCorridorS6R3-v0 44 > gpurun_out/${R}_spare_probe_keycorridor.txt 2>&1
+tail -4 gpurun_out/${R}_desync.txt
