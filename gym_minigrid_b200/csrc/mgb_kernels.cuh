@@ -359,6 +359,7 @@ __device__ __forceinline__ void obst_set(uint32_t *st, const DevCfg &c, int k, i
 
 constexpr int FLAG_PRISTINE = 1;
 constexpr int FLAG_SPARE = 2;            // the env's spare block holds the layout of its NEXT episode (see reset_lanes)
+constexpr int LONE_SHIFT = 26;           // two bits of the flags byte: the warp's count of lone resets (reset_with_spares)
 constexpr int SPARE_XW = 5;              // spare block = GW grid words + agent word, target, draws consumed, error bits, episode,
 __host__ __device__ constexpr int spare_words(int GW) { return 2 * GW + SPARE_XW; }      // + GW words where a live grid is parked
 // kernels whose generator is worth more than a trip to HBM (measured: for DoorKey and FourRooms it is not -- fetching a
@@ -1394,6 +1395,7 @@ __device__ __noinline__ void reset_with_spares(bool need, bool valid, uint32_t *
     const uint32_t st_sa = (uint32_t)__cvta_generic_to_shared(st);
     uint32_t &fw = st[(GW + 1) * 32];                                 // FLAG_SPARE stays in the state word (k_rollout carries it over)
     if ((threadIdx.x & 31) == 0) SPARE_DBG(0, 1);
+    const int n_need = __popc(__ballot_sync(0xFFFFFFFFu, need));    // lanes that reset in this call (with or without a spare)
     if (spares && need && (fw & (FLAG_SPARE << 24))) {              // 1. a reset with a spare at hand is a copy: ONE round trip
         fw &= ~((uint32_t)FLAG_SPARE << 24);
         for (int k = 0; k < GW; ++k) cp_async_word(st_sa + (uint32_t)k * 128u, spc + k * 32);
@@ -1409,11 +1411,18 @@ __device__ __noinline__ void reset_with_spares(bool need, bool valid, uint32_t *
         }
     }
     if (!__any_sync(0xFFFFFFFFu, need)) return;
+    // Generating ahead pays when the warp's episodes really end at scattered steps.  A warp in lock step with one straggler
+    // (an env that once ended early) would run a 32-lane pass -- ~100 us on one warp of a persistent launch, i.e. on its
+    // tail -- for every lone reset of that env: sustained KeyCorridor lost 5 % to it.  So the warp counts its lone resets
+    // (two bits of the flags byte, zeroed by a reset of eight or more lanes) and generates ahead from the second on.
+    uint32_t lone = (fw >> LONE_SHIFT) & 3u;
+    lone = n_need >= 8 ? 0u : min(lone + 1u, 3u);
+    fw = (fw & ~(3u << LONE_SHIFT)) | (lone << LONE_SHIFT);
     if (GEN == GEN_PROC && p.cfg.gen == GEN_MULTIROOM) {              // the MultiRoom generator scribbles in the staging block
         if ((threadIdx.x & 31) == 0) bulk_store_wait_read();
         __syncwarp();
     }
-    const bool pre = spares && valid && !need && !(fw & (FLAG_SPARE << 24));   // 2. somebody generates: so does everybody without a spare
+    const bool pre = spares && lone >= 2u && valid && !need && !(fw & (FLAG_SPARE << 24));   // 2. somebody generates: so does everybody without a spare
     if ((threadIdx.x & 31) == 0) SPARE_DBG(3, 1);
     if (need) SPARE_DBG(4, 1);
     if (pre) SPARE_DBG(5, 1);
@@ -1686,7 +1695,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         // ---- write the state back ----
         st[(GW + 0) * 32] = (uint32_t)e.ax | ((uint32_t)e.ay << 8) | ((uint32_t)e.dir << 16) | ((uint32_t)e.carry << 24);
         st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16) | ((uint32_t)e.flags << 24)
-                            | (spare_gen(GEN) ? st[(GW + 1) * 32] & ((uint32_t)FLAG_SPARE << 24) : 0u);
+                            | (spare_gen(GEN) ? st[(GW + 1) * 32] & (((uint32_t)FLAG_SPARE << 24) | (3u << LONE_SHIFT)) : 0u);
         st[(GW + 2) * 32] = rg.episode;
         st[(GW + 3) * 32] = rg.ndraws;
         if (GEN == GEN_POOL) st[(GW + XWORDS) * 32] = (uint32_t)pc.level;
