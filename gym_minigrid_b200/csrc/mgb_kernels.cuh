@@ -139,6 +139,8 @@ struct RolloutParams {
                                 //   tcode | mcode<<8 ; tx|ty<<8|A.x<<16|A.y<<24 ; B.x|B.y<<8|C.x<<16|C.y<<24 ; D.x|D.y<<8
     int32_t pool_n;
     uint32_t *err;
+    uint32_t *ticket;           // multi-step launches: groups beyond a warp's first are handed out by this counter (NULL: static stride)
+    uint32_t ticket_base;       // the counter's value when this launch starts (it is never reset: a launch advances it by n_groups)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -366,6 +368,9 @@ __host__ __device__ constexpr int spare_words(int GW) { return 2 * GW + SPARE_XW
 // spare layout with one lane costs more than generating it)
 #ifndef MGB_SPARES
 #define MGB_SPARES 1
+#endif
+#ifndef MGB_DYNAMIC_GROUPS
+#define MGB_DYNAMIC_GROUPS 1
 #endif
 #ifndef MGB_EMPTY_QUICK
 #define MGB_EMPTY_QUICK 1
@@ -1520,7 +1525,15 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
     const int64_t stride = p.stride;
     uint32_t phase = 0;
     bool cols_hold_template = false;       // warp-uniform: every column of the warp's state block holds exactly the template grid
-    for (int g = blockIdx.x * wpb + warp; g < p.n_groups; g += gridDim.x * wpb) {
+    // Groups: a warp's first is fixed; the following ones come from a ticket counter in multi-step launches -- the time a
+    // group takes varies (rejection sampling, generator passes), and with a fixed stride the launch ends with the unluckiest
+    // warp's sum of ~14 groups.  The ticket is taken at the top of the group it follows: its latency is hidden.
+    for (int g = blockIdx.x * wpb + warp; (unsigned)g < (unsigned)p.n_groups;) {
+        int g_next = g + gridDim.x * wpb;
+#if MGB_DYNAMIC_GROUPS
+        uint32_t tk = 0;
+        if (p.ticket != nullptr && lane == 0) tk = atomicAdd(p.ticket, 1u) - p.ticket_base;
+#endif
         const int group = p.group0 + g;
         uint32_t *gst = p.state + (size_t)group * S * 32 + lane;
         // The step loop holds no global load: a lane fetches the actions of its env for 32 steps at once (one HBM latency
@@ -1537,7 +1550,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         // bulk load and action load are L2 hits: +3 %.  Measured and rejected for the kernels with large state blocks, which
         // are HBM-bound in this mode (DoorKey-16x16 -16 %, FourRooms -10 %, Dynamic-Obstacles -1.5 %).
         if (GEN == GEN_EMPTY && p.T <= 1) {
-            const int gn = g + gridDim.x * wpb;
+            const int gn = g_next;
             if (gn < p.n_groups) {
                 const uint32_t *nb = p.state + (size_t)(p.group0 + gn) * S * 32;
                 for (int r = GW + lane; r < S; r += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)r * 32));
@@ -1718,6 +1731,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         if (GEN == GEN_EMPTY) cols_hold_template = __all_sync(0xFFFFFFFFu, e.flags & FLAG_PRISTINE);
         if (rg.err) atomicOr(p.err, rg.err);
         __syncwarp();
+#if MGB_DYNAMIC_GROUPS
+        if (p.ticket != nullptr) g_next = gridDim.x * wpb + (int)__shfl_sync(0xFFFFFFFFu, tk, 0);
+#endif
+        g = g_next;
     }
     if (lane == 0) bulk_store_wait_all();
 }
