@@ -357,7 +357,7 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
     // group tickets (multi-step launches, which a handle runs one at a time): the counter is never reset -- a launch takes
     // exactly n_groups tickets, one per group processed, so the host knows its value at the start of the next launch
     p.ticket = nullptr; p.ticket_base = 0;
-    if (MGB_DYNAMIC_GROUPS && T > 1) { p.ticket = h->ticket; p.ticket_base = h->ticket_base; h->ticket_base += (uint32_t)ng; }
+    if (MGB_DYNAMIC_GROUPS && (T > 1 || MGB_DYNAMIC_STEP) && order) { p.ticket = h->ticket; p.ticket_base = h->ticket_base; h->ticket_base += (uint32_t)ng; }
     rollout_fn fn = pick_kernel(h->cfg);
     const mgb_handle::Shape &sh = h->shape[T > 1 ? 0 : 1];
     const int want = (ng + sh.warps_per_block - 1) / sh.warps_per_block;

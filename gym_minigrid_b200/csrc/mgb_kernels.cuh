@@ -372,6 +372,9 @@ __host__ __device__ constexpr int spare_words(int GW) { return 2 * GW + SPARE_XW
 #ifndef MGB_DYNAMIC_GROUPS
 #define MGB_DYNAMIC_GROUPS 1
 #endif
+#ifndef MGB_DYNAMIC_STEP
+#define MGB_DYNAMIC_STEP 1          // tickets for single-step launches and resets too (never for the host pipeline's concurrent chunks)
+#endif
 #ifndef MGB_EMPTY_QUICK
 #define MGB_EMPTY_QUICK 1
 #endif
@@ -1545,18 +1548,6 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         const uint8_t *arow_p = p.actions + (int64_t)lane * p.stride + (int64_t)group * 32;
         const bool afast = ((p.stride & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.actions) & 15) == 0) && ((int64_t)group * 32 + 32 <= p.n_envs);
         if (PACKED && p.T > 1) actions_issue(arow, arow_p, lane < p.T, afast);
-        // Single-step launches are bound by the latency of the state round trip.  For the Empty kernels (4 rows of state per
-        // group once the grid is implied) the rows and actions of the warp's NEXT group are pulled into L2 now, so that its
-        // bulk load and action load are L2 hits: +3 %.  Measured and rejected for the kernels with large state blocks, which
-        // are HBM-bound in this mode (DoorKey-16x16 -16 %, FourRooms -10 %, Dynamic-Obstacles -1.5 %).
-        if (GEN == GEN_EMPTY && p.T <= 1) {
-            const int gn = g_next;
-            if (gn < p.n_groups) {
-                const uint32_t *nb = p.state + (size_t)(p.group0 + gn) * S * 32;
-                for (int r = GW + lane; r < S; r += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)r * 32));
-                if (lane == 0 && p.T > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + (int64_t)(p.group0 + gn) * 32));
-            }
-        }
         // ---- load the group's state block: S coalesced 128-byte rows -> bank == lane ----
         // Single-step launches of the template-grid kernels (Empty, Dynamic-Obstacles) first fetch only the non-grid rows;
         // when every env of the group is pristine -- the normal case -- the grid rows never cross HBM at all (they are
@@ -1577,6 +1568,22 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
             cols_hold_template = false;
         }
         st_warp[S * 32 + lane] = (uint32_t)CODE_WALL * 0x01010101u;        // out-of-grid pad (minigrid.py:469)
+        // Single-step launches are bound by the latency of the state round trip.  For the Empty kernels (4 rows of state per
+        // group once the grid is implied) the rows and actions of the warp's NEXT group are pulled into L2 now, so that its
+        // bulk load and action load are L2 hits: +3 %.  Measured and rejected for the kernels with large state blocks, which
+        // are HBM-bound in this mode (DoorKey-16x16 -16 %, FourRooms -10 %, Dynamic-Obstacles -1.5 %).
+        // (After this group's own load has arrived: by then the ticket naming the next group has too.)
+        if (GEN == GEN_EMPTY && p.T <= 1) {
+            int gn = g_next;
+#if MGB_DYNAMIC_GROUPS
+            if (p.ticket != nullptr) gn = gridDim.x * wpb + (int)__shfl_sync(0xFFFFFFFFu, tk, 0);
+#endif
+            if ((unsigned)gn < (unsigned)p.n_groups) {
+                const uint32_t *nb = p.state + (size_t)(p.group0 + gn) * S * 32;
+                for (int r = GW + lane; r < S; r += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)r * 32));
+                if (lane == 0 && p.T > 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.actions + (int64_t)(p.group0 + gn) * 32));
+            }
+        }
         Env e;
         Rng rg;
         PoolCtx pc;
