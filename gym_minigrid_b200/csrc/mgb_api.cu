@@ -72,8 +72,7 @@ struct mgb_handle {
     uint32_t *spare = nullptr;               // pre-generated next layouts (spare_gen kernels)
     uint32_t *tmpl = nullptr;
     uint32_t *err = nullptr;
-    uint32_t *ticket = nullptr;              // group ticket counter of multi-step launches (see launch())
-    uint32_t ticket_base = 0;
+    uint32_t *ticket = nullptr;              // {next group ticket, warps done}: zeroed by the kernel itself when its last warp leaves
     const int32_t *tape = nullptr;
     const int64_t *tape_off = nullptr;
     uint32_t *pool = nullptr;
@@ -288,7 +287,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     if (cudaMalloc(&h->tmpl, t.size() * 4) != cudaSuccess || cudaMemcpy(h->tmpl, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
         return cleanup(fail("mgb_create: template upload failed"));
     if (cudaMalloc(&h->err, 4) != cudaSuccess || cudaMemset(h->err, 0, 4) != cudaSuccess) return cleanup(fail("mgb_create: err flag alloc failed"));
-    if (cudaMalloc(&h->ticket, 4) != cudaSuccess || cudaMemset(h->ticket, 0, 4) != cudaSuccess) return cleanup(fail("mgb_create: ticket counter alloc failed"));
+    if (cudaMalloc(&h->ticket, 8) != cudaSuccess || cudaMemset(h->ticket, 0, 8) != cudaSuccess) return cleanup(fail("mgb_create: ticket counter alloc failed"));
     if (cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming) != cudaSuccess) return cleanup(fail("mgb_create: event creation failed"));
     if (cudaDeviceSynchronize() != cudaSuccess) return cleanup(fail("mgb_create: device synchronisation failed"));   // the memsets above ran on the legacy stream
     *out = h;
@@ -354,10 +353,8 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
     p.reset_mask = mask; p.actions = actions; p.obs = obs; p.reward = reward; p.done = done; p.dir = dir;
     p.stride = stride; p.seed = h->seed; p.env_id_base = h->env_id_base;
     p.tape = h->tape; p.tape_off = h->tape_off; p.err = h->err; p.pool = h->pool; p.pool_n = h->pool_n;
-    // group tickets (multi-step launches, which a handle runs one at a time): the counter is never reset -- a launch takes
-    // exactly n_groups tickets, one per group processed, so the host knows its value at the start of the next launch
-    p.ticket = nullptr; p.ticket_base = 0;
-    if (MGB_DYNAMIC_GROUPS && (T > 1 || MGB_DYNAMIC_STEP) && order) { p.ticket = h->ticket; p.ticket_base = h->ticket_base; h->ticket_base += (uint32_t)ng; }
+    // group tickets: for the launches a handle runs one at a time (not the host pipeline's concurrent chunks, order == false)
+    p.ticket = (MGB_DYNAMIC_GROUPS && (T > 1 || MGB_DYNAMIC_STEP) && order) ? h->ticket : nullptr;
     rollout_fn fn = pick_kernel(h->cfg);
     const mgb_handle::Shape &sh = h->shape[T > 1 ? 0 : 1];
     const int want = (ng + sh.warps_per_block - 1) / sh.warps_per_block;

@@ -139,8 +139,8 @@ struct RolloutParams {
                                 //   tcode | mcode<<8 ; tx|ty<<8|A.x<<16|A.y<<24 ; B.x|B.y<<8|C.x<<16|C.y<<24 ; D.x|D.y<<8
     int32_t pool_n;
     uint32_t *err;
-    uint32_t *ticket;           // multi-step launches: groups beyond a warp's first are handed out by this counter (NULL: static stride)
-    uint32_t ticket_base;       // the counter's value when this launch starts (it is never reset: a launch advances it by n_groups)
+    uint32_t *ticket;           // [2] {next ticket, warps done}: groups beyond a warp's first are handed out by the counter; the last
+                                // warp to leave zeroes both words for the next launch (NULL: fixed stride)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -1528,14 +1528,18 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
     const int64_t stride = p.stride;
     uint32_t phase = 0;
     bool cols_hold_template = false;       // warp-uniform: every column of the warp's state block holds exactly the template grid
-    // Groups: a warp's first is fixed; the following ones come from a ticket counter in multi-step launches -- the time a
-    // group takes varies (rejection sampling, generator passes), and with a fixed stride the launch ends with the unluckiest
-    // warp's sum of ~14 groups.  The ticket is taken at the top of the group it follows: its latency is hidden.
-    for (int g = blockIdx.x * wpb + warp; (unsigned)g < (unsigned)p.n_groups;) {
+    // Groups: a warp's first is fixed; the following ones come from a ticket counter -- the time a group takes varies
+    // (rejection sampling, generator passes), and with a fixed stride the launch ends with the unluckiest warp's sum of ~14
+    // groups.  The ticket is taken at the top of the group it follows: its latency is hidden.  Every warp that had a first
+    // group ends on a ticket beyond the last group; the last such warp to leave zeroes the counter for the next launch (all
+    // other warps have taken their last ticket by then), so nothing about it lives on the host: a launch replayed from a CUDA
+    // graph finds the counter as a fresh one does.
+    const int g_first = blockIdx.x * wpb + warp;
+    for (int g = g_first; (unsigned)g < (unsigned)p.n_groups;) {
         int g_next = g + gridDim.x * wpb;
 #if MGB_DYNAMIC_GROUPS
         uint32_t tk = 0;
-        if (p.ticket != nullptr && lane == 0) tk = atomicAdd(p.ticket, 1u) - p.ticket_base;
+        if (p.ticket != nullptr && lane == 0) tk = atomicAdd(p.ticket, 1u);
 #endif
         const int group = p.group0 + g;
         uint32_t *gst = p.state + (size_t)group * S * 32 + lane;
@@ -1743,6 +1747,12 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
 #endif
         g = g_next;
     }
+#if MGB_DYNAMIC_GROUPS
+    if (p.ticket != nullptr && lane == 0 && g_first < p.n_groups) {
+        const uint32_t takers = (uint32_t)min((int64_t)gridDim.x * wpb, (int64_t)p.n_groups);
+        if (atomicAdd(p.ticket + 1, 1u) == takers - 1u) { p.ticket[0] = 0u; p.ticket[1] = 0u; }
+    }
+#endif
     if (lane == 0) bulk_store_wait_all();
 }
 

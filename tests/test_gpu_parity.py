@@ -595,3 +595,77 @@ def test_reseed_drops_pre_generated_layouts():
         assert_same("seed %d obs" % seed, got[0], want[0])
         assert_same("seed %d done" % seed, got[2].astype(np.uint8), want[2])
         assert_same("seed %d state.grid" % seed, _np(env.get_state()["grid"]), orc.get_state()["grid"])
+
+
+def test_group_tickets_survive_odd_launch_shapes():
+    """Groups beyond a warp's first are handed out by a device-side ticket counter that the kernel itself zeroes when its
+    last warp leaves.  Mix launch kinds and sizes on one handle -- fewer groups than resident warps, exactly one group, many
+    more groups than warps; resets with a mask, single steps, rollouts, the host pipeline -- and require the outputs to stay
+    equal to the oracle's: a counter left non-zero by any of them would make the next launch skip or repeat groups."""
+    from oracle.oracle import OracleVec
+    mgb = _mgb()
+    env_id = "MiniGrid-DoorKey-8x8-v0"
+    cfg = _oracle_cfg(env_id)
+    rs = np.random.RandomState(2)
+    for N in (1, 33, 32 * 700 + 5, 32 * 5000):
+        env = mgb.make(env_id, num_envs=N, seed=11)
+        orc = OracleVec(cfg, N, seed=11)
+        env.reset(); orc.reset()
+        for rnd in range(3):
+            a = rs.randint(0, cfg["n_actions"], size=(5, N)).astype(np.uint8)
+            want = orc.rollout(a)
+            got = [_np(x) for x in env.rollout(torch.as_tensor(a))]
+            assert_same("N=%d rollout %d obs" % (N, rnd), got[0], want[0])
+            a1 = rs.randint(0, cfg["n_actions"], size=N).astype(np.uint8)
+            w1 = orc.step(a1)
+            ob, r, dn, _ = env.step(torch.as_tensor(a1))
+            assert_same("N=%d step %d obs" % (N, rnd), _np(ob["image"]), w1[0])
+            a2 = rs.randint(0, cfg["n_actions"], size=N).astype(np.uint8)
+            w2 = orc.step(a2)
+            h = env.step_host(a2)
+            assert_same("N=%d step_host %d obs" % (N, rnd), _np(h[0]["image"]), w2[0])
+            m = rs.randint(0, 2, size=N).astype(np.uint8)
+            wo, _ = orc.reset(m)
+            go = env.reset(mask=torch.as_tensor(m))
+            assert_same("N=%d masked reset %d obs" % (N, rnd), _np(go["image"])[m == 1], wo[m == 1])    # the oracle fills only the rows it reset
+        env.check_errors()
+
+
+def test_rollout_replayed_from_a_cuda_graph():
+    """mgb_rollout keeps nothing per launch on the host (the group ticket counter is zeroed by the kernel itself), so a
+    launch captured in a CUDA graph can be replayed: three replays must give what three launches give."""
+    from oracle.oracle import OracleVec
+    mgb = _mgb()
+    env_id = "MiniGrid-FourRooms-v0"
+    cfg = _oracle_cfg(env_id)
+    N, T = 32 * 300 + 3, 8
+    rs = np.random.RandomState(4)
+    env = mgb.make(env_id, num_envs=N, seed=5)
+    orc = OracleVec(cfg, N, seed=5)
+    env.reset(); orc.reset()
+    acts = torch.zeros((T, N), dtype=torch.uint8, device=env.device)
+    out = env.rollout(acts)                                   # buffers to reuse; also warms up
+    orc.rollout(np.zeros((T, N), np.uint8))
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    a0 = rs.randint(0, cfg["n_actions"], size=(T, N)).astype(np.uint8)
+    acts.copy_(torch.as_tensor(a0))
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        try:
+            with torch.cuda.graph(g, stream=s):
+                env.rollout(acts, out=out)
+        except Exception as e:                                # pragma: no cover
+            pytest.skip("capture not possible here: %r" % (e,))
+    torch.cuda.synchronize()
+    # the capture itself does not run the launch: replay it three times with fresh actions
+    for rep in range(3):
+        a = a0 if rep == 0 else rs.randint(0, cfg["n_actions"], size=(T, N)).astype(np.uint8)
+        acts.copy_(torch.as_tensor(a))
+        g.replay()
+        torch.cuda.synchronize()
+        want = orc.rollout(a)
+        assert_same("replay %d obs" % rep, _np(out[0]), want[0])
+        assert_same("replay %d done" % rep, _np(out[2]).astype(np.uint8), want[2])
+    assert_same("state after replays", _np(env.get_state()["grid"]), orc.get_state()["grid"])
