@@ -2,7 +2,10 @@
 """Long-horizon soak: GPU rollout vs the C oracle, bit for bit, N envs x STEPS env-steps per config (auto-reset on),
 in chunks so that the outputs fit in memory.  Test infrastructure (uses oracle/); run on a GPU box:
 
-    PYTHONPATH=. python profiles/tools/soak.py [N] [STEPS] [env ids ...]
+    PYTHONPATH=. python profiles/tools/soak.py [N] [STEPS] [--scatter] [env ids ...]
+
+--scatter: every env starts at its own step count, so that episode ends hit single lanes of a warp (spare layouts, in-register
+resets and the lone-reset counters are exercised at scale instead of lock-step regeneration).
 """
 import sys
 import time
@@ -13,6 +16,9 @@ import torch
 import gym_minigrid_b200 as mgb
 from oracle.oracle import OracleVec
 
+SCATTER = "--scatter" in sys.argv
+if SCATTER:
+    sys.argv.remove("--scatter")
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 15
 STEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 CHUNK = 50
@@ -25,6 +31,11 @@ for env_id in (sys.argv[3:] or IDS):
     g0, o0 = env.reset(), orc.reset()
     assert np.array_equal(g0["image"].cpu().numpy(), o0[0])
     rs = np.random.RandomState(1)
+    if SCATTER:
+        so = orc.get_state()
+        so["agent"][:, 3] = rs.randint(0, cfg["max_steps"] - 1, size=N)
+        orc.set_state(so)
+        env.set_state({"agent": torch.as_tensor(so["agent"])})
     t0, dones = time.time(), 0
     for c in range(STEPS // CHUNK):
         a = rs.randint(0, cfg["n_actions"], size=(CHUNK, N)).astype(np.uint8)
