@@ -221,6 +221,7 @@ int mgb_create(const mgb_config *cfg, int64_t num_envs, int device, uint64_t see
     d.random_start = c.random_start; d.lava_v1 = c.lava_v1; d.hook = c.hook; d.gp0 = c.gen_param0; d.gp1 = c.gen_param1;
     d.HP = (c.height + 3) / 4 * 4;
     d.GW = c.width * d.HP / 4;
+    d.goal_idx = c.gen == MGB_GEN_EMPTY ? (c.width - 2) * d.HP + c.height - 2 : (c.gen == MGB_GEN_DISTSHIFT ? (c.width - 2) * d.HP + 1 : -1);   // build_template
     d.S = d.GW + XWORDS + (c.n_obstacles > 0 ? OBST_WORDS : 0) + (c.gen == MGB_GEN_POOL ? 1 : 0);   // pool: + level word
     h->sm_count = prop.multiProcessorCount;
     auto cleanup = [&](int rc) { mgb_destroy(h); return rc; };

@@ -109,6 +109,7 @@ __host__ __device__ inline uint32_t lut_entry(int code) {
 struct DevCfg {
     int32_t gen, W, H, max_steps, see_through, n_actions, n_obst, room_size, num_rows, random_start, lava_v1, hook;
     int32_t gp0, gp1;   // generator parameters (mgb_config.gen_param0/1)
+    int32_t goal_idx;   // Empty / DistShift: cell index x*HP + y of the template's goal (FLAG_GOAL_GONE), else -1
     int32_t HP;   // grid column pitch in cells: H rounded up to a multiple of 4 (one column = HP/4 words)
     int32_t GW;   // grid words per env = W*HP/4; cell (x,y) = byte (y&3) of word x*HP/4 + (y>>2)
     int32_t S;    // state words per env
@@ -360,6 +361,9 @@ __device__ __forceinline__ void obst_set(uint32_t *st, const DevCfg &c, int k, i
 }
 
 constexpr int FLAG_PRISTINE = 1;
+constexpr int FLAG_GOAL_GONE = 16;       // Empty kernels, with FLAG_PRISTINE: ... except that the goal was toggled away (the one edit an
+                                         // Empty grid can suffer, minigrid.py:171-177): still implied, still never crosses HBM
+constexpr int FLAGS_IMPLIED = FLAG_PRISTINE | FLAG_GOAL_GONE;
 constexpr int FLAG_SPARE = 2;            // the env's spare block holds the layout of its NEXT episode (see reset_lanes)
 constexpr int LONE_SHIFT = 26;           // two bits of the flags byte: the warp's count of lone resets (reset_with_spares)
 constexpr int SPARE_XW = 5;              // spare block = GW grid words + agent word, target, draws consumed, error bits, episode,
@@ -396,7 +400,7 @@ __device__ __forceinline__ void copy_template(uint32_t *st, const uint32_t *tmpl
     }
     for (; k < GW; ++k) st[k * 32] = tmpl_s[k];
 }
-__device__ __forceinline__ void rebuild_pristine_grid(uint32_t *st, const RolloutParams &p, const uint32_t *tmpl_s) {
+__device__ __forceinline__ void rebuild_pristine_grid(uint32_t *st, const RolloutParams &p, const uint32_t *tmpl_s, int flags) {
     const DevCfg &c = p.cfg;
     copy_template(st, tmpl_s, c.GW);
     for (int j = 0; j < c.n_obst; ++j) {
@@ -404,13 +408,16 @@ __device__ __forceinline__ void rebuild_pristine_grid(uint32_t *st, const Rollou
         obst_get(st, c, j, ox, oy);
         cell_wr(st, ox * c.HP + oy, CODE_BLUE_BALL);
     }
+    if (flags & FLAG_GOAL_GONE) cell_wr(st, c.goal_idx, CODE_EMPTY);
 }
 
 // grid word k of env `base` (column of the state block in HBM) as the state readers must see it
 __device__ __forceinline__ uint32_t grid_word(const DevCfg &c, const uint32_t *base, const uint32_t *tmpl, int k) {
-    const bool pristine = template_gen(c.gen) && ((base[(c.GW + 1) * 32] >> 24) & FLAG_PRISTINE);
+    const uint32_t fl = base[(c.GW + 1) * 32] >> 24;
+    const bool pristine = template_gen(c.gen) && (fl & FLAG_PRISTINE);
     if (!pristine) return base[k * 32];
     uint32_t w = tmpl[k];
+    if ((fl & FLAG_GOAL_GONE) && (c.goal_idx >> 2) == k) { const int sh = (c.goal_idx & 3) * 8; w = (w & ~(0xFFu << sh)) | ((uint32_t)CODE_EMPTY << sh); }
     for (int j = 0; j < c.n_obst; ++j) {
         const uint32_t o = base[(c.GW + XWORDS + (j >> 1)) * 32] >> ((j & 1) * 16);
         const int idx = (int)(o & 0xFF) * c.HP + (int)((o >> 8) & 0xFF);
@@ -668,7 +675,7 @@ __device__ __forceinline__ void generate_body(uint32_t *st, Env &e, Rng &rg, con
     if (GEN == GEN_EMPTY) {                              // envs/empty.py:30-57 (extra == 0)
         if (!c.random_start) { e.ax = 1; e.ay = 1; e.dir = 0; }
         else ok = place_agent<true>(st, e, rg, p, 0, 0, W, H, -1);
-        e.flags |= FLAG_PRISTINE;
+        e.flags = (e.flags & ~FLAG_GOAL_GONE) | FLAG_PRISTINE;
     } else if (GEN == GEN_DOORKEY) {                     // envs/doorkey.py:15-44
         const int split = rand_int(rg, p, 2, W - 2);
         for (int j = 0; j < H; ++j) cell_wr(st, split * HP + j, CODE_WALL);
@@ -1076,7 +1083,8 @@ __device__ __forceinline__ void transition(uint32_t *st, Env &e, Rng &rg, const 
         if (tog_vanish && fc >= CODE_KEYBOX0) nv = (uint32_t)code_of(T_KEY, (int)fc - CODE_KEYBOX0, 0);   // Box.toggle: cell := contents (:355-360)
         cell_wr(st, fidx, nv);
         e.dirty = true;
-        e.flags &= ~FLAG_PRISTINE;
+        if (GEN == GEN_EMPTY && tog_vanish && fidx == c.goal_idx) e.flags |= FLAG_GOAL_GONE;      // still implied (harmless if not pristine)
+        else e.flags &= ~FLAGS_IMPLIED;
         e.carry = pick ? (int)fc : (drop ? 0 : e.carry);
     }
     if (e.steps >= c.max_steps) done = true;
@@ -1472,6 +1480,7 @@ __device__ __forceinline__ void reset_lanes(bool need, bool valid, uint32_t *st,
         // costs a call with its spills and fills -- local memory is an L2 round trip here -- which is what a policy that
         // reaches the goal every dozen steps would pay on nearly every warp-step.
         if (GEN == GEN_EMPTY && need && !p.cfg.random_start && (e.flags & FLAG_PRISTINE)) {
+            if (e.flags & FLAG_GOAL_GONE) { cell_wr(st, p.cfg.goal_idx, CODE_GOAL); e.flags &= ~FLAG_GOAL_GONE; }
             e.ax = 1; e.ay = 1; e.dir = 0; e.carry = 0; e.steps = 0; e.target = 0;
             rg.episode++; if (!p.tape) rg.ndraws = 0; rg.rblk = 0xFFFFFFFFu;
             need = false;
@@ -1600,7 +1609,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         {
             const uint32_t w0 = st[(GW + 0) * 32], w1 = st[(GW + 1) * 32];
             e.ax = w0 & 0xFF; e.ay = (w0 >> 8) & 0xFF; e.dir = (w0 >> 16) & 3; e.carry = w0 >> 24;
-            e.steps = w1 & 0xFFFF; e.target = (w1 >> 16) & 0xFF; e.flags = (w1 >> 24) & FLAG_PRISTINE;
+            e.steps = w1 & 0xFFFF; e.target = (w1 >> 16) & 0xFF; e.flags = (w1 >> 24) & FLAGS_IMPLIED;
             rg.episode = st[(GW + 2) * 32]; rg.ndraws = st[(GW + 3) * 32];
             if (GEN == GEN_POOL) {
                 pc.level = (int)st[(GW + XWORDS) * 32];
@@ -1615,7 +1624,10 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         if (template_gen(GEN)) {
             // the grid rows of a pristine env in HBM are don't-care: rebuild.  An Empty grid IS the template, so once a warp's
             // columns hold it (left there by the previous all-pristine group of a single-step launch) there is nothing to do.
-            if ((e.flags & FLAG_PRISTINE) && !(GEN == GEN_EMPTY && cols_hold_template)) rebuild_pristine_grid(st, p, tmpl_s);
+            if (e.flags & FLAG_PRISTINE) {
+                if (!(GEN == GEN_EMPTY && cols_hold_template)) rebuild_pristine_grid(st, p, tmpl_s, e.flags);
+                else if (e.flags & FLAG_GOAL_GONE) cell_wr(st, c.goal_idx, CODE_EMPTY);
+            }
         }
 
         const bool full = ((int64_t)group * 32 + 32) <= p.n_envs;
@@ -1739,7 +1751,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
             __syncwarp();
             for (int k = k0; k < S; ++k) gst[k * 32] = st_warp[k * 32 + lane];
         }
-        if (GEN == GEN_EMPTY) cols_hold_template = __all_sync(0xFFFFFFFFu, e.flags & FLAG_PRISTINE);
+        if (GEN == GEN_EMPTY) cols_hold_template = __all_sync(0xFFFFFFFFu, (e.flags & FLAGS_IMPLIED) == FLAG_PRISTINE);
         if (rg.err) atomicOr(p.err, rg.err);
         __syncwarp();
 #if MGB_DYNAMIC_GROUPS
@@ -1799,7 +1811,7 @@ __global__ void k_materialize(DevCfg c, uint32_t *state, const uint32_t *__restr
     const uint32_t fw = base[(c.GW + 1) * 32];
     if (!((fw >> 24) & FLAG_PRISTINE)) return;
     for (int k = 0; k < c.GW; ++k) base[k * 32] = grid_word(c, base, tmpl, k);
-    base[(c.GW + 1) * 32] = fw & ~((uint32_t)FLAG_PRISTINE << 24);
+    base[(c.GW + 1) * 32] = fw & ~((uint32_t)FLAGS_IMPLIED << 24);
 }
 
 // clears flag bits of every env (mgb_seed: another seed invalidates the pre-generated layouts)
@@ -1851,7 +1863,7 @@ __global__ void k_set_state(const StateIO io) {
         *dst = w;
     } else if (k == c.GW + 1) {
         uint32_t w = *dst;
-        if (io.grid || io.obstacles) w &= ~((uint32_t)FLAG_PRISTINE << 24);      // an uploaded grid / ball list ends 'template + balls' (state_io materialises the grid first)
+        if (io.grid || io.obstacles) w &= ~((uint32_t)FLAGS_IMPLIED << 24);      // an uploaded grid / ball list ends 'template + balls' (state_io materialises the grid first)
         if (io.rng) w &= ~((uint32_t)FLAG_SPARE << 24);        // another episode counter: the pre-generated next layout is not this env's any more
         if (io.agent) w = (w & 0xFFFF0000u) | (uint32_t)(io.agent[n * 4 + 3] & 0xFFFF);
         if (io.target) {
