@@ -18,7 +18,12 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls
  *     enqueue and return immediately unless stated otherwise.
  *   - there is no CPU fallback: without a CUDA device mgb_create fails.
- *   - a handle is bound to one device and is not thread-safe.
+ *   - a handle is bound to one device and is not thread-safe; its calls all read and write the
+ *     handle's env state, so issue them one at a time, in stream order (different handles are
+ *     independent).  Nothing about a launch is kept on the host: mgb_reset / mgb_step /
+ *     mgb_rollout may be captured in a CUDA graph and replayed.
+ *   - device memory per env: the state block (80-1500 bytes) and, for the
+ *     KeyCorridor / crossing / MultiRoom generators, a spare-layout block of about twice that.
  */
 #ifndef MGB200_H
 #define MGB200_H
