@@ -355,7 +355,7 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
     p.stride = stride; p.seed = h->seed; p.env_id_base = h->env_id_base;
     p.tape = h->tape; p.tape_off = h->tape_off; p.err = h->err; p.pool = h->pool; p.pool_n = h->pool_n;
     // group tickets: for the launches a handle runs one at a time (not the host pipeline's concurrent chunks, order == false)
-    p.ticket = (MGB_DYNAMIC_GROUPS && (T > 1 || MGB_DYNAMIC_STEP) && order) ? h->ticket : nullptr;
+    p.ticket = (MGB_DYNAMIC_GROUPS && order) ? h->ticket : nullptr;
     rollout_fn fn = pick_kernel(h->cfg);
     const mgb_handle::Shape &sh = h->shape[T > 1 ? 0 : 1];
     const int want = (ng + sh.warps_per_block - 1) / sh.warps_per_block;

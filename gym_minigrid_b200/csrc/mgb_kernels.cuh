@@ -255,21 +255,11 @@ __device__ __noinline__ int rand_int_ool(Rng &e, const RolloutParams &p, int low
 #ifndef MGB_DYN_BLOCKS
 #define MGB_DYN_BLOCKS 5
 #endif
-#ifndef MGB_DYN_ROLLED
-#define MGB_DYN_ROLLED 0       // experiment: Philox blocks of the window in a rolled loop (code size)
-#endif
-#ifndef MGB_DYN_HOIST
-#define MGB_DYN_HOIST 0        // experiment: step-loop invariants in registers for the Dynamic-Obstacles kernel too
-#endif
 constexpr int DYN_BLOCKS = MGB_DYN_BLOCKS;
 __host__ __device__ constexpr int draw_blocks(int V) { return (3 * V * V / 4) / 4 < DYN_BLOCKS ? (3 * V * V / 4) / 4 : DYN_BLOCKS; }
 template <int NB>
 __device__ __noinline__ void prefetch_draws(uint32_t *draws, uint32_t first_block, uint32_t stream, int64_t gid, uint64_t seed) {
-#if MGB_DYN_ROLLED
-#pragma unroll 1
-#else
 #pragma unroll
-#endif
     for (int j = 0; j < NB; ++j) {
         uint32_t o0, o1, o2, o3;
         philox4x32_10(first_block + j, stream, (uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), o0, o1, o2, o3);
@@ -374,19 +364,10 @@ __host__ __device__ constexpr int spare_words(int GW) { return 2 * GW + SPARE_XW
 #define MGB_SPARES 1
 #endif
 #ifndef MGB_DYNAMIC_GROUPS
-#define MGB_DYNAMIC_GROUPS 1
-#endif
-#ifndef MGB_TICKET_AFTER_LOOP
-#define MGB_TICKET_AFTER_LOOP 1
+#define MGB_DYNAMIC_GROUPS 1        // 0: every launch hands out groups by a fixed stride (the A/B of profiles/r2_ab_group_tickets.txt)
 #endif
 #ifndef MGB_TICKET_LEAD
-#define MGB_TICKET_LEAD 4
-#endif
-#ifndef MGB_DYNAMIC_STEP
-#define MGB_DYNAMIC_STEP 1          // tickets for single-step launches and resets too (never for the host pipeline's concurrent chunks)
-#endif
-#ifndef MGB_EMPTY_QUICK
-#define MGB_EMPTY_QUICK 1
+#define MGB_TICKET_LEAD 4           // Empty rollouts: steps before a group's last at which the next ticket is taken
 #endif
 __host__ __device__ constexpr bool spare_gen(int gen) { return MGB_SPARES && (gen == GEN_KEYCORRIDOR || gen == GEN_PROC); }
 __host__ __device__ constexpr bool template_gen(int gen) { return gen == GEN_EMPTY || gen == GEN_DYNOBS; }
@@ -1481,7 +1462,6 @@ __device__ __forceinline__ void reset_lanes(bool need, bool valid, uint32_t *st,
             e = te; rg = tr;
         }
     } else {
-#if MGB_EMPTY_QUICK
         // Empty with a fixed start, grid untouched (it always is): the reset is a handful of register moves.  Out of line it
         // costs a call with its spills and fills -- local memory is an L2 round trip here -- which is what a policy that
         // reaches the goal every dozen steps would pay on nearly every warp-step.
@@ -1491,7 +1471,6 @@ __device__ __forceinline__ void reset_lanes(bool need, bool valid, uint32_t *st,
             rg.episode++; if (!p.tape) rg.ndraws = 0; rg.rblk = 0xFFFFFFFFu;
             need = false;
         }
-#endif
         if (!need) return;
         Env te = e; Rng tr = rg; PoolCtx tp = pc;
         generate<GEN>(st, te, tr, p, GEN == GEN_POOL ? &tp : nullptr, scr, tmpl_s);
@@ -1552,13 +1531,11 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
     const int g_first = blockIdx.x * wpb + warp;
     for (int g = g_first; (unsigned)g < (unsigned)p.n_groups;) {
         int g_next = g + gridDim.x * wpb;
-#if MGB_DYNAMIC_GROUPS
         uint32_t tk = 0;        // Empty rollouts take it as late as its latency allows (MGB_TICKET_LEAD steps before the group's last):
                                 // a warp that claims its next group early still holds it when the tickets run out -- a longer tail
         constexpr bool LATE_TICKET = GEN == GEN_EMPTY && SEE;      // measured: Empty +1.8 %; DoorKey -3.4 % (the test in its step loop costs
                                                                     // ten registers), FourRooms / KeyCorridor / Dynamic-Obstacles +-1 %
-        if (!((LATE_TICKET || MGB_TICKET_AFTER_LOOP) && p.T > 1) && p.ticket != nullptr && lane == 0) tk = atomicAdd(p.ticket, 1u);     // at the top
-#endif
+        if (p.T <= 1 && p.ticket != nullptr && lane == 0) tk = atomicAdd(p.ticket, 1u);     // single steps, resets: at the top
         const int group = p.group0 + g;
         uint32_t *gst = p.state + (size_t)group * S * 32 + lane;
         // The step loop holds no global load: a lane fetches the actions of its env for 32 steps at once (one HBM latency
@@ -1597,9 +1574,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         // (After this group's own load has arrived: by then the ticket naming the next group has too.)
         if (GEN == GEN_EMPTY && p.T <= 1) {
             int gn = g_next;
-#if MGB_DYNAMIC_GROUPS
             if (p.ticket != nullptr) gn = gridDim.x * wpb + (int)__shfl_sync(0xFFFFFFFFu, tk, 0);
-#endif
             if ((unsigned)gn < (unsigned)p.n_groups) {
                 const uint32_t *nb = p.state + (size_t)(p.group0 + gn) * S * 32;
                 for (int r = GW + lane; r < S; r += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + (size_t)r * 32));
@@ -1656,7 +1631,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         // loop invariants spelled out: ptxas otherwise re-derives them from the parameter bank on every step
         // (69 of the occluded kernel's 880 instructions per step were this bookkeeping).  HOIST is off for the
         // see-through kernels: at their 64 registers the extra live values cost more than the bookkeeping (measured -4 %).
-        constexpr bool HOIST = !SEE || (MGB_DYN_HOIST && GEN == GEN_DYNOBS);
+        constexpr bool HOIST = !SEE;
         const bool stepping = p.T > 0, multi = PACKED && p.T > 1;
         const bool w_rew = valid && stepping && p.reward != nullptr, w_done = valid && stepping && p.done != nullptr;
         const bool w_dir = valid && p.dir != nullptr;
@@ -1665,9 +1640,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         const int64_t obs_pitch = stride * OB;
         const int t_ticket = max(nsteps - MGB_TICKET_LEAD, 0);
         for (int t = 0; t < nsteps; ++t) {
-#if MGB_DYNAMIC_GROUPS
             if (LATE_TICKET && p.T > 1 && t == t_ticket && p.ticket != nullptr && lane == 0) tk = atomicAdd(p.ticket, 1u);
-#endif
             double reward = 0.0; bool done = false;
             if (!HOIST) {
                 o = (int64_t)t * stride + lid;
@@ -1741,9 +1714,7 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
                 if (p.dir) p.dir[o] = (uint8_t)e.dir;
             }
         }
-#if MGB_DYNAMIC_GROUPS
-        if (MGB_TICKET_AFTER_LOOP && !LATE_TICKET && p.T > 1 && p.ticket != nullptr && lane == 0) tk = atomicAdd(p.ticket, 1u);
-#endif
+        if (!LATE_TICKET && p.T > 1 && p.ticket != nullptr && lane == 0) tk = atomicAdd(p.ticket, 1u);     // the other rollouts: after the step loop
         // ---- write the state back ----
         st[(GW + 0) * 32] = (uint32_t)e.ax | ((uint32_t)e.ay << 8) | ((uint32_t)e.dir << 16) | ((uint32_t)e.carry << 24);
         st[(GW + 1) * 32] = (uint32_t)(e.steps & 0xFFFF) | ((uint32_t)e.target << 16) | ((uint32_t)e.flags << 24)
@@ -1770,17 +1741,13 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
         if (GEN == GEN_EMPTY) cols_hold_template = __all_sync(0xFFFFFFFFu, (e.flags & FLAGS_IMPLIED) == FLAG_PRISTINE);
         if (rg.err) atomicOr(p.err, rg.err);
         __syncwarp();
-#if MGB_DYNAMIC_GROUPS
         if (p.ticket != nullptr) g_next = gridDim.x * wpb + (int)__shfl_sync(0xFFFFFFFFu, tk, 0);
-#endif
         g = g_next;
     }
-#if MGB_DYNAMIC_GROUPS
     if (p.ticket != nullptr && lane == 0 && g_first < p.n_groups) {
         const uint32_t takers = (uint32_t)min((int64_t)gridDim.x * wpb, (int64_t)p.n_groups);
         if (atomicAdd(p.ticket + 1, 1u) == takers - 1u) { p.ticket[0] = 0u; p.ticket[1] = 0u; }
     }
-#endif
     if (lane == 0) bulk_store_wait_all();
 }
 
