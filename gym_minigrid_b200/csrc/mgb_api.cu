@@ -361,7 +361,18 @@ static int launch(mgb_handle *h, int32_t g0, int32_t ng, int32_t T, int do_reset
     const int want = (ng + sh.warps_per_block - 1) / sh.warps_per_block;
     const int grid = std::max(1, std::min(want, h->sm_count * sh.blocks_per_sm));
     if (timed && h->timing) CUDA_OK(cudaEventRecord(h->ev0, stream));
+#if MGB_PDL
+    {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3((unsigned)(sh.warps_per_block * 32)); lc.dynamicSmemBytes = sh.smem_bytes; lc.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        CUDA_OK(cudaLaunchKernelEx(&lc, fn, p));
+    }
+#else
     fn<<<grid, sh.warps_per_block * 32, sh.smem_bytes, stream>>>(p);
+#endif
     CUDA_OK(cudaGetLastError());
     if (timed && h->timing) { CUDA_OK(cudaEventRecord(h->ev1, stream)); h->ev_valid = true; }
     if (order) CUDA_OK(cudaEventRecord(h->order_ev, stream));

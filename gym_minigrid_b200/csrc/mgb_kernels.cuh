@@ -366,6 +366,9 @@ __host__ __device__ constexpr int spare_words(int GW) { return 2 * GW + SPARE_XW
 #ifndef MGB_DYNAMIC_GROUPS
 #define MGB_DYNAMIC_GROUPS 1        // 0: every launch hands out groups by a fixed stride (the A/B of profiles/r2_ab_group_tickets.txt)
 #endif
+#ifndef MGB_PDL
+#define MGB_PDL 1      // 0: plain launches (the A/B of profiles/r2_ab_pdl.txt)
+#endif
 #ifndef MGB_TICKET_LEAD
 #define MGB_TICKET_LEAD 4           // Empty rollouts: steps before a group's last at which the next ticket is taken
 #endif
@@ -1491,6 +1494,11 @@ template <int GEN, bool SEE, int V>
 __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
     const __grid_constant__ RolloutParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+#if MGB_PDL
+    // programmatic dependent launch: the next launch on the stream may place its CTAs on SMs that this grid has left and run
+    // its prologue (tables, template) there; it touches nothing a predecessor wrote before griddepcontrol.wait below
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     constexpr bool PACKED = !SEE;     // rollouts of the occluded kernels hold 32 steps of actions in 4 registers (see below)
     const DevCfg &c = p.cfg;
     // the warp index goes through a lane-0 broadcast so that ptxas knows it is warp-uniform: everything derived from
@@ -1517,6 +1525,9 @@ __global__ void __launch_bounds__(MAX_THREADS, MGB_MIN_BLOCKS(GEN)) k_rollout(
     const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(axis + 2 * AXIS_ENTRIES) + (uint32_t)warp * 8u;
     if (lane == 0) mbar_init(mbar_sa, 1);
     __syncthreads();
+#if MGB_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");       // everything before us on the stream has completed and is visible
+#endif
 
     const int S = c.S, GW = c.GW;
     const int64_t stride = p.stride;
